@@ -1,0 +1,157 @@
+"""GraphBatch: the flat edge-index layout every kernel ingests (DESIGN.md "HBM layout").
+
+A batch is the disjoint union of G graphs, stored as struct-of-arrays so that a
+warp reading one graph touches contiguous int32 runs:
+
+  node_off int64[G+1]   node k of graph g is global node node_off[g]+k
+  edge_off int64[G+1]   directed entries of graph g are [edge_off[g], edge_off[g+1])
+  src,dst  int32[E]     LOCAL node ids, in the caller's edge_index column order
+  x        int32[N]     node type (ZINC atom index)            optional
+  edge_attr int32[E]    edge type (ZINC bond index, 1-based)   optional
+  query_u,query_v int32[G]                                     optional (shortest_path)
+  y                     labels, never touched by a kernel
+
+Mirrors what the reference holds per graph as PyG ``Data(edge_index, x, edge_attr,
+y, num_nodes, query_u, query_v)`` (graph_data_loader/graph_token_dataset_autograph.py:
+385-394, graph_data_loader/zinc_dataset_autograph.py:51-73).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, fields
+from typing import Optional, Sequence
+
+import torch
+
+
+@dataclass
+class GraphBatch:
+    node_off: torch.Tensor
+    edge_off: torch.Tensor
+    src: torch.Tensor
+    dst: torch.Tensor
+    x: Optional[torch.Tensor] = None
+    edge_attr: Optional[torch.Tensor] = None
+    query_u: Optional[torch.Tensor] = None
+    query_v: Optional[torch.Tensor] = None
+    y: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------
+    @property
+    def num_graphs(self) -> int:
+        return int(self.node_off.numel()) - 1
+
+    @property
+    def device(self) -> torch.device:
+        return self.src.device
+
+    def num_nodes(self) -> torch.Tensor:
+        return (self.node_off[1:] - self.node_off[:-1])
+
+    def num_entries(self) -> torch.Tensor:
+        return (self.edge_off[1:] - self.edge_off[:-1])
+
+    def to(self, device, non_blocking: bool = False) -> "GraphBatch":
+        kw = {}
+        for f in fields(self):
+            v = getattr(self, f.name)
+            kw[f.name] = None if v is None else v.to(device, non_blocking=non_blocking)
+        return GraphBatch(**kw)
+
+    def pin_memory(self) -> "GraphBatch":
+        kw = {}
+        for f in fields(self):
+            v = getattr(self, f.name)
+            kw[f.name] = None if v is None else v.pin_memory()
+        return GraphBatch(**kw)
+
+    def input_bytes(self) -> int:
+        return sum(getattr(self, f.name).numel() * getattr(self, f.name).element_size()
+                   for f in fields(self) if getattr(self, f.name) is not None and f.name != "y")
+
+    def validate(self) -> None:
+        """Host-side shape/dtype contract check (the kernels trust it)."""
+        G = self.num_graphs
+        if self.node_off.dtype != torch.int64 or self.edge_off.dtype != torch.int64:
+            raise TypeError("node_off/edge_off must be int64")
+        if self.edge_off.numel() != G + 1:
+            raise ValueError("edge_off must have G+1 entries")
+        for name in ("src", "dst", "x", "edge_attr", "query_u", "query_v"):
+            v = getattr(self, name)
+            if v is not None and v.dtype != torch.int32:
+                raise TypeError(f"{name} must be int32")
+        if self.src.numel() != self.dst.numel():
+            raise ValueError("src/dst length mismatch")
+        if self.edge_attr is not None and self.edge_attr.numel() != self.src.numel():
+            raise ValueError("edge_attr must have one entry per edge_index column")
+
+    # ------------------------------------------------------------------
+    def graph(self, g: int):
+        """Per-graph views: (num_nodes, src, dst, x|None, edge_attr|None)."""
+        n0, n1 = int(self.node_off[g]), int(self.node_off[g + 1])
+        e0, e1 = int(self.edge_off[g]), int(self.edge_off[g + 1])
+        return (n1 - n0, self.src[e0:e1], self.dst[e0:e1],
+                None if self.x is None else self.x[n0:n1],
+                None if self.edge_attr is None else self.edge_attr[e0:e1])
+
+    def slice(self, g0: int, g1: int) -> "GraphBatch":
+        """Contiguous shard [g0, g1) - how ranks partition a dataset."""
+        n0, n1 = int(self.node_off[g0]), int(self.node_off[g1])
+        e0, e1 = int(self.edge_off[g0]), int(self.edge_off[g1])
+        opt = lambda t, a, b: None if t is None else t[a:b]
+        return GraphBatch(self.node_off[g0:g1 + 1] - n0, self.edge_off[g0:g1 + 1] - e0,
+                          self.src[e0:e1], self.dst[e0:e1], opt(self.x, n0, n1),
+                          opt(self.edge_attr, e0, e1), opt(self.query_u, g0, g1),
+                          opt(self.query_v, g0, g1), opt(self.y, g0, g1))
+
+    # ------------------------------------------------------------------
+    @staticmethod
+    def from_lists(num_nodes: Sequence[int], edge_lists: Sequence, x_lists=None, attr_lists=None,
+                   queries=None, y=None) -> "GraphBatch":
+        """edge_lists[g] = iterable of (u, v) (directed entries, caller order)."""
+        G = len(num_nodes)
+        node_off = torch.zeros(G + 1, dtype=torch.int64)
+        node_off[1:] = torch.as_tensor(list(num_nodes), dtype=torch.int64).cumsum(0)
+        cnt = [len(e) for e in edge_lists]
+        edge_off = torch.zeros(G + 1, dtype=torch.int64)
+        edge_off[1:] = torch.as_tensor(cnt, dtype=torch.int64).cumsum(0)
+        flat = [p for e in edge_lists for p in e]
+        if flat:
+            ed = torch.as_tensor(flat, dtype=torch.int32).reshape(-1, 2)
+            src, dst = ed[:, 0].contiguous(), ed[:, 1].contiguous()
+        else:
+            src = torch.zeros(0, dtype=torch.int32)
+            dst = torch.zeros(0, dtype=torch.int32)
+        cat = lambda ls: torch.as_tensor([v for l in ls for v in l], dtype=torch.int32)
+        xs = None if x_lists is None else cat(x_lists)
+        at = None if attr_lists is None else cat(attr_lists)
+        qu = qv = None
+        if queries is not None:
+            qu = torch.as_tensor([q[0] for q in queries], dtype=torch.int32)
+            qv = torch.as_tensor([q[1] for q in queries], dtype=torch.int32)
+        yy = None if y is None else torch.as_tensor(y)
+        return GraphBatch(node_off, edge_off, src, dst, xs, at, qu, qv, yy)
+
+    @staticmethod
+    def from_data_list(data_list: Sequence) -> "GraphBatch":
+        """From PyG-style ``Data`` objects (duck-typed: edge_index[2,E], num_nodes,
+        optional x, edge_attr, query_u, query_v, y)."""
+        G = len(data_list)
+        nn = [int(d.num_nodes) for d in data_list]
+        node_off = torch.zeros(G + 1, dtype=torch.int64)
+        node_off[1:] = torch.as_tensor(nn, dtype=torch.int64).cumsum(0)
+        ne = [int(d.edge_index.shape[1]) for d in data_list]
+        edge_off = torch.zeros(G + 1, dtype=torch.int64)
+        edge_off[1:] = torch.as_tensor(ne, dtype=torch.int64).cumsum(0)
+        if G:
+            ei = torch.cat([d.edge_index.reshape(2, -1) for d in data_list], dim=1).to(torch.int32)
+        else:
+            ei = torch.zeros(2, 0, dtype=torch.int32)
+        has = lambda a: G > 0 and getattr(data_list[0], a, None) is not None
+        x = torch.cat([d.x.reshape(-1) for d in data_list]).to(torch.int32) if has("x") else None
+        ea = torch.cat([d.edge_attr.reshape(-1) for d in data_list]).to(torch.int32) if has("edge_attr") else None
+        qu = qv = None
+        if has("query_u") and has("query_v"):
+            qu = torch.as_tensor([int(d.query_u) for d in data_list], dtype=torch.int32)
+            qv = torch.as_tensor([int(d.query_v) for d in data_list], dtype=torch.int32)
+        y = torch.cat([d.y.reshape(-1)[:1] for d in data_list]) if has("y") else None
+        return GraphBatch(node_off, edge_off, ei[0].contiguous(), ei[1].contiguous(), x, ea, qu, qv, y)
