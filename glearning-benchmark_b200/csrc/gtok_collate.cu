@@ -1,0 +1,143 @@
+// gtok_collate.cu - K4: ragged token rows -> padded [B, Lmax] int64 batch + bool mask.
+//
+// Replaces (reference, Python row-copy loops run once per DataLoader step):
+//   collate      graph_data_loader/data_loader.py:488-497   (IBTT; pad = vocab["<pad>"])
+//   collate_fn   trainer/train_agtt.py:276-302              (AGTT; pad = Graph2TrailTokenizer.pad = 5)
+//   X = full((B, Lmax), pad, long); attn = zeros(bool); X[i,:len]=row; attn[i,:len]=True
+// Lmax is the longest row OF THAT BATCH (not max_len), which the batched entry
+// point reproduces per batch.
+//
+// One warp per output row: 16-byte streaming stores for X (2 tokens / lane) and
+// for the mask (16 flags / lane); source rows are read with 8-byte coalesced loads
+// (source and destination 16-byte phases differ, so only the store side is vectorised).
+// Algorithmic bytes: 8*sum(len) read + 9*B*Lmax written (+ 12 B/row of row metadata).
+#include "gtok_common.cuh"
+
+namespace gtok {
+
+constexpr int kColThreads = 256;
+constexpr int kColWarps = kColThreads / 32;
+
+__device__ __forceinline__ unsigned long long mask_bytes(int nvalid) {
+  // low `nvalid` bytes (0..8) = 0x01
+  if (nvalid <= 0) return 0ull;
+  if (nvalid >= 8) return 0x0101010101010101ull;
+  return 0x0101010101010101ull >> (8 * (8 - nvalid));
+}
+
+__device__ __forceinline__ void warp_collate_row(const int64_t* __restrict__ src, int len, int Lmax, int64_t pad,
+                                                 int64_t* __restrict__ xrow, uint8_t* __restrict__ arow) {
+  warp_write_row(xrow, Lmax, [&](int p) -> int64_t { return p < len ? __ldcs(src + p) : pad; });
+  // mask row: scalar head up to 16-byte alignment, 16-byte interior, scalar tail
+  const int lane = lane_id();
+  int head = (int)((16 - (reinterpret_cast<uintptr_t>(arow) & 15)) & 15);
+  if (head > Lmax) head = Lmax;
+  if (lane < head) arow[lane] = (uint8_t)(lane < len);
+  const int nvec = (Lmax - head) >> 4;
+  for (int j = lane; j < nvec; j += kWarp) {
+    const int p = head + 16 * j;
+    const int nv = len - p;
+    ulonglong2 m = make_ulonglong2(mask_bytes(nv), mask_bytes(nv - 8));
+    __stcs(reinterpret_cast<ulonglong2*>(arow + p), m);
+  }
+  const int tail = head + 16 * nvec;
+  if (tail + lane < Lmax && lane < 16) arow[tail + lane] = (uint8_t)(tail + lane < len);
+}
+
+__global__ void __launch_bounds__(kColThreads)
+pad_mask_kernel(const int64_t* __restrict__ tok, const int64_t* __restrict__ row_start,
+                const int32_t* __restrict__ row_len, const int64_t* __restrict__ batch_idx, int64_t B,
+                int64_t Lmax, int64_t pad, int64_t* __restrict__ X, uint8_t* __restrict__ attn) {
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < B; r += nwarps) {
+    const int64_t i = batch_idx ? __ldg(batch_idx + r) : r;
+    int len = __ldg(row_len + i);
+    if (len > Lmax) len = (int)Lmax;
+    warp_collate_row(tok + __ldg(row_start + i), len, (int)Lmax, pad, X + r * Lmax, attn + r * Lmax);
+  }
+}
+
+__global__ void __launch_bounds__(kColThreads)
+batch_extents_kernel(const int32_t* __restrict__ row_len, const int64_t* __restrict__ batch_idx, int64_t G,
+                     int64_t B, int32_t* __restrict__ lmax_out, int32_t* __restrict__ cells_out) {
+  // one warp per batch: max over its rows
+  const int lane = lane_id();
+  const int64_t nb = (G + B - 1) / B;
+  const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= nb) return;
+  const int64_t r0 = k * B, r1 = (r0 + B < G) ? r0 + B : G;
+  int m = 0;
+  for (int64_t r = r0 + lane; r < r1; r += kWarp) {
+    const int64_t i = batch_idx ? __ldg(batch_idx + r) : r;
+    m = max(m, __ldg(row_len + i));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(kFull, m, d));
+  if (lane == 0) {
+    lmax_out[k] = m;
+    cells_out[k] = (int32_t)((r1 - r0) * m);
+  }
+}
+
+__global__ void __launch_bounds__(kColThreads)
+pad_mask_batched_kernel(const int64_t* __restrict__ tok, const int64_t* __restrict__ row_start,
+                        const int32_t* __restrict__ row_len, const int64_t* __restrict__ batch_idx, int64_t G,
+                        int64_t B, const int32_t* __restrict__ lmax, const int64_t* __restrict__ xoff, int64_t pad,
+                        int64_t* __restrict__ X, uint8_t* __restrict__ attn) {
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < G; r += nwarps) {
+    const int64_t k = r / B;
+    const int64_t i = batch_idx ? __ldg(batch_idx + r) : r;
+    const int Lm = __ldg(lmax + k);
+    const int64_t base = __ldg(xoff + k) + (r - k * B) * Lm;
+    warp_collate_row(tok + __ldg(row_start + i), __ldg(row_len + i), Lm, pad, X + base, attn + base);
+  }
+}
+
+}  // namespace gtok
+
+extern "C" int gtok_pad_mask(const int64_t* tok, const int64_t* row_start, const int32_t* row_len,
+                             const int64_t* batch_idx, int64_t B, int64_t Lmax, int64_t pad_id, int64_t* X,
+                             uint8_t* attn, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(B >= 0 && Lmax >= 0, GTOK_EINVAL, "pad_mask: negative shape");
+  if (B == 0 || Lmax == 0) return GTOK_OK;
+  GTOK_REQUIRE(Lmax < (1ll << 31), GTOK_EINVAL, "pad_mask: Lmax too large");
+  GTOK_REQUIRE(tok && row_start && row_len && X && attn, GTOK_EINVAL, "pad_mask: null pointer");
+  GTOK_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0, GTOK_EINVAL, "pad_mask: X must be 16-byte aligned");
+  const int64_t work = (B + kColWarps - 1) / kColWarps;
+  const int grid = persistent_grid(pad_mask_kernel, kColThreads, 0, work);
+  pad_mask_kernel<<<grid, kColThreads, 0, (cudaStream_t)stream>>>(tok, row_start, row_len, batch_idx, B, Lmax, pad_id, X, attn);
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}
+
+extern "C" int gtok_batch_extents(const int32_t* row_len, const int64_t* batch_idx, int64_t G, int64_t B,
+                                  int32_t* lmax_out, int32_t* cells_out, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(G >= 0 && B > 0, GTOK_EINVAL, "batch_extents: need G >= 0 and B > 0");
+  if (G == 0) return GTOK_OK;
+  GTOK_REQUIRE(row_len && lmax_out && cells_out, GTOK_EINVAL, "batch_extents: null pointer");
+  const int64_t nb = (G + B - 1) / B;
+  const int64_t blocks = (nb + kColWarps - 1) / kColWarps;
+  batch_extents_kernel<<<(unsigned)blocks, kColThreads, 0, (cudaStream_t)stream>>>(row_len, batch_idx, G, B, lmax_out, cells_out);
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}
+
+extern "C" int gtok_pad_mask_batched(const int64_t* tok, const int64_t* row_start, const int32_t* row_len,
+                                     const int64_t* batch_idx, int64_t G, int64_t B, const int32_t* lmax,
+                                     const int64_t* xoff, int64_t pad_id, int64_t* X, uint8_t* attn, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(G >= 0 && B > 0, GTOK_EINVAL, "pad_mask_batched: need G >= 0 and B > 0");
+  if (G == 0) return GTOK_OK;
+  GTOK_REQUIRE(tok && row_start && row_len && lmax && xoff && X && attn, GTOK_EINVAL, "pad_mask_batched: null pointer");
+  GTOK_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0, GTOK_EINVAL, "pad_mask_batched: X must be 16-byte aligned");
+  const int64_t work = (G + kColWarps - 1) / kColWarps;
+  const int grid = persistent_grid(pad_mask_batched_kernel, kColThreads, 0, work);
+  pad_mask_batched_kernel<<<grid, kColThreads, 0, (cudaStream_t)stream>>>(tok, row_start, row_len, batch_idx, G, B, lmax, xoff, pad_id, X, attn);
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}

@@ -1,0 +1,79 @@
+// gtok_common.cuh - shared device/host helpers for the sm_100a tokenization kernels.
+//
+// All kernels here are HBM-bound integer gathers/scatters (no FLOPs, no tensor
+// cores).  The rules that matter (blackwell_cuda_programming.md G1, G2, G11, G13):
+// full-sector coalesced 16-byte stores of the int64 token stream, grids sized as
+// a multiple of the SM count with enough resident warps to cover DRAM latency, and
+// small lookup tables served from L1/shared memory.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gtok.h"
+
+namespace gtok {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int sm_count();  // cached, <0 on error
+
+#define GTOK_CUDA_TRY(expr)                                   \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return ::gtok::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define GTOK_REQUIRE(cond, code, ...)      \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::gtok::set_error(__VA_ARGS__);      \
+      return (code);                       \
+    }                                      \
+  } while (0)
+
+// Launch geometry for "one warp per graph, persistent grid-stride" kernels.
+template <typename K>
+inline int persistent_grid(K kernel, int block, size_t smem, int64_t work_blocks) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  int64_t cap = (int64_t)sm_count() * per_sm;
+  if (cap < 1) cap = 148;
+  int64_t g = work_blocks < cap ? work_blocks : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// streaming (evict-first) stores: the token stream is written once and consumed
+// by a later kernel / the trainer, never re-read by the producer.
+__device__ __forceinline__ void st_stream_i64x2(int64_t* p, int64_t a, int64_t b) {
+  __stcs(reinterpret_cast<longlong2*>(p), make_longlong2(a, b));
+}
+__device__ __forceinline__ void st_stream_i64(int64_t* p, int64_t a) { __stcs(p, a); }
+
+// Write row[0..L) = tok(p) with one warp: 16-byte vector stores on the 16-byte
+// aligned interior, scalar stores on the (at most one) head and tail element.
+// tok(p) must be callable for any 0 <= p < L by any lane.
+template <typename F>
+__device__ __forceinline__ void warp_write_row(int64_t* __restrict__ row, int L, F tok) {
+  const int lane = lane_id();
+  const int head = (int)((reinterpret_cast<uintptr_t>(row) >> 3) & 1);  // 1 if row is 8- but not 16-byte aligned
+  if (head && lane == 0 && L > 0) st_stream_i64(row, (int64_t)tok(0));
+  const int npair = (L - head) >> 1;
+  for (int j = lane; j < npair; j += kWarp) {
+    const int p = head + 2 * j;
+    const int64_t a = (int64_t)tok(p);
+    const int64_t b = (int64_t)tok(p + 1);
+    st_stream_i64x2(row + p, a, b);
+  }
+  const int tail = head + 2 * npair;
+  if (tail < L && lane == 31) st_stream_i64(row + tail, (int64_t)tok(tail));
+}
+
+}  // namespace gtok

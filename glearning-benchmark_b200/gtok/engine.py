@@ -1,0 +1,329 @@
+"""Host side of the engine: torch CUDA tensors in, torch CUDA tensors out, every
+byte of arithmetic done by libgtok.so kernels (no torch op computes a token).
+
+PyTorch is plumbing here: device memory, the current stream, and (in bench.py)
+torch.distributed.  Each function names the reference code it stands in for.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+from .batch import GraphBatch
+
+ZINC_ATOMS = ["C", "N", "O", "F", "P", "S", "Cl", "Br", "I"]       # zinc_vocab.py:21
+ZINC_BONDS = ["single", "double", "triple", "aromatic"]           # zinc_vocab.py:25
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("gtok kernels need CUDA tensors (there is no CPU fallback)")
+
+
+@dataclass
+class Ragged:
+    """Ragged int64 token rows: row g = tokens[offsets[g]:offsets[g+1]]."""
+    tokens: torch.Tensor      # int64 [total]
+    offsets: torch.Tensor     # int64 [G+1]
+    lengths: torch.Tensor     # int32 [G]
+
+    @property
+    def num_rows(self) -> int:
+        return int(self.lengths.numel())
+
+    def row(self, g: int) -> torch.Tensor:
+        o = self.offsets[g:g + 2].tolist()
+        return self.tokens[o[0]:o[1]]
+
+    def rows_cpu(self):
+        t, o = self.tokens.cpu(), self.offsets.cpu().tolist()
+        return [t[o[i]:o[i + 1]] for i in range(len(o) - 1)]
+
+
+def _batch_c(b: GraphBatch, max_nodes: Optional[int], max_entries: Optional[int]) -> _lib.GraphBatchC:
+    G = b.num_graphs
+    if max_nodes is None:
+        max_nodes = int(b.num_nodes().max()) if G else 0
+    if max_entries is None:
+        max_entries = int(b.num_entries().max()) if G else 0
+    return _lib.GraphBatchC(G, _ptr(b.node_off), _ptr(b.edge_off), _ptr(b.src), _ptr(b.dst), _ptr(b.x),
+                            _ptr(b.edge_attr), _ptr(b.query_u), _ptr(b.query_v), max(1, max_nodes), max(1, max_entries))
+
+
+def node_token_table(vocab: Dict[str, int], size: int, device) -> torch.Tensor:
+    """node_tok[k] = vocab.get(str(k), vocab['<pad>']) - the lookup the reference does
+    per token with a dict (data_loader.py:482)."""
+    pad = vocab["<pad>"]
+    return torch.tensor([vocab.get(str(k), pad) for k in range(size)], dtype=torch.int32, device=device)
+
+
+def scan_offsets(lengths: torch.Tensor) -> torch.Tensor:
+    """K0: int32[G] -> int64[G+1] exclusive offsets."""
+    _require_cuda(lengths)
+    G = lengths.numel()
+    off = torch.empty(G + 1, dtype=torch.int64, device=lengths.device)
+    nbytes = lib.gtok_scan_workspace_bytes(G)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=lengths.device)
+    check(lib.gtok_scan_offsets(_ptr(lengths), G, _ptr(off), _ptr(ws), nbytes, _stream()))
+    return off
+
+
+# ---------------------------------------------------------------------------
+# K1: graph-token IBTT  (external serializer + data_loader.py:465-486)
+# ---------------------------------------------------------------------------
+def ibtt_rules(vocab: Dict[str, int], task: str, max_len: int, table_size: int, device):
+    pad = vocab["<pad>"]
+    g = lambda t: vocab.get(t, pad)
+    tbl = node_token_table(vocab, table_size, device)
+    if task == "cycle_check":
+        tcode, ttok = _lib.TASK_CYCLE_CHECK, g("has_cycle")
+    elif task == "shortest_path":
+        tcode, ttok = _lib.TASK_SHORTEST_PATH, g("shortest_distance")
+    else:
+        raise ValueError(f"unsupported graph-token task {task!r}")
+    r = _lib.IbttRulesC(tcode, int(max_len), g("<bos>"), g("<e>"), g("<n>"), g("<q>"), g("<p>"), ttok, pad,
+                        tbl.numel(), _ptr(tbl))
+    return r, tbl      # keep tbl alive as long as r is used
+
+
+def tokenize_ibtt(batch: GraphBatch, vocab: Dict[str, int], task: str, max_len: int,
+                  max_nodes: Optional[int] = None, out: Optional[torch.Tensor] = None) -> Ragged:
+    _require_cuda(batch.src)
+    dev = batch.device
+    G = batch.num_graphs
+    if max_nodes is None:
+        max_nodes = int(batch.num_nodes().max()) if G else 0
+    bc = _batch_c(batch, max_nodes, 1)
+    rules, tbl = ibtt_rules(vocab, task, max_len, max(1, max_nodes), dev)
+    lengths = torch.empty(G, dtype=torch.int32, device=dev)
+    check(lib.gtok_ibtt_lengths(C.byref(bc), C.byref(rules), _ptr(lengths), _stream()))
+    off = scan_offsets(lengths)
+    total = int(off[-1]) if G else 0
+    if out is None:
+        out = torch.empty(total, dtype=torch.int64, device=dev)
+    elif out.numel() < total:
+        raise ValueError("output buffer too small")
+    check(lib.gtok_ibtt_serialize(C.byref(bc), C.byref(rules), _ptr(off), _ptr(out), _stream()))
+    return Ragged(out[:total], off, lengths)
+
+
+# ---------------------------------------------------------------------------
+# K2: ZINC IBTT  (zinc_dataset_indexbase.py:143-227 + data_loader.py:465-486)
+# ---------------------------------------------------------------------------
+def zinc_vocab_c(vocab: Dict[str, int], item_max_len: int, ds_max_len: int, table_size: int, device):
+    pad = vocab["<pad>"]
+    g = lambda t: vocab.get(t, pad)
+    tbl = node_token_table(vocab, table_size, device)
+    v = _lib.ZincVocabC()
+    v.item_max_len, v.ds_max_len = int(item_max_len), int(ds_max_len)
+    v.tok_bos, v.tok_eos, v.tok_atom, v.tok_bond = g("<bos>"), g("<eos>"), g("<atom>"), g("<bond>")
+    v.tok_q, v.tok_regression, v.tok_p = g("<q>"), g("regression"), g("<p>")
+    for i, a in enumerate(ZINC_ATOMS):
+        v.atom_tok[i] = g(a)
+    for i, b in enumerate(ZINC_BONDS):
+        v.bond_tok[i] = g(b)
+    v.atom_oov, v.bond_oov, v.oov = g("X"), g("unknown"), pad
+    v.node_tok_len, v.node_tok = tbl.numel(), _ptr(tbl)
+    return v, tbl
+
+
+def tokenize_zinc(batch: GraphBatch, vocab: Dict[str, int], max_len: int, item_max_len: Optional[int] = None,
+                  max_nodes: Optional[int] = None, max_entries: Optional[int] = None,
+                  out: Optional[torch.Tensor] = None) -> Ragged:
+    _require_cuda(batch.src)
+    if batch.x is None:
+        raise ValueError("ZINC tokenization needs batch.x (atom types)")
+    dev = batch.device
+    G = batch.num_graphs
+    bc = _batch_c(batch, max_nodes, max_entries)
+    zv, tbl = zinc_vocab_c(vocab, max_len if item_max_len is None else item_max_len, max_len, bc.max_nodes, dev)
+    lengths = torch.empty(G, dtype=torch.int32, device=dev)
+    check(lib.gtok_zinc_lengths(C.byref(bc), C.byref(zv), _ptr(lengths), _stream()))
+    off = scan_offsets(lengths)
+    total = int(off[-1]) if G else 0
+    if out is None:
+        out = torch.empty(total, dtype=torch.int64, device=dev)
+    elif out.numel() < total:
+        raise ValueError("output buffer too small")
+    check(lib.gtok_zinc_serialize(C.byref(bc), C.byref(zv), _ptr(off), _ptr(out), _stream()))
+    return Ragged(out[:total], off, lengths)
+
+
+# ---------------------------------------------------------------------------
+# K4: collate  (data_loader.py:488-497, train_agtt.py:276-302)
+# ---------------------------------------------------------------------------
+def pad_mask(tokens: torch.Tensor, row_start: torch.Tensor, row_len: torch.Tensor, pad_id: int,
+             batch_idx: Optional[torch.Tensor] = None, lmax: Optional[int] = None):
+    """One batch: -> (X int64[B,Lmax], attn bool[B,Lmax])."""
+    _require_cuda(tokens, row_start, row_len, batch_idx)
+    B = int(batch_idx.numel() if batch_idx is not None else row_len.numel())
+    if lmax is None:
+        sel = row_len if batch_idx is None else row_len[batch_idx]
+        lmax = int(sel.max()) if B else 0
+    X = torch.empty((B, lmax), dtype=torch.int64, device=tokens.device)
+    attn = torch.empty((B, lmax), dtype=torch.bool, device=tokens.device)
+    check(lib.gtok_pad_mask(_ptr(tokens), _ptr(row_start), _ptr(row_len), _ptr(batch_idx), B, lmax, int(pad_id),
+                            _ptr(X), _ptr(attn), _stream()))
+    return X, attn
+
+
+@dataclass
+class PaddedEpoch:
+    """All batches of one pass, padded per batch exactly as collate() would."""
+    X: torch.Tensor           # int64 flat
+    attn: torch.Tensor        # bool flat
+    xoff: torch.Tensor        # int64 [nb+1] (device)
+    lmax: torch.Tensor        # int32 [nb]   (device)
+    batch_size: int
+    num_rows: int
+    _host: Optional[tuple] = None
+
+    @property
+    def num_batches(self) -> int:
+        return int(self.lmax.numel())
+
+    def _h(self):
+        if self._host is None:
+            self._host = (self.xoff.cpu().tolist(), self.lmax.cpu().tolist())
+        return self._host
+
+    def batch(self, k: int):
+        xoff, lmax = self._h()
+        rows = min(self.batch_size, self.num_rows - k * self.batch_size)
+        sl = slice(xoff[k], xoff[k + 1])
+        return self.X[sl].view(rows, lmax[k]), self.attn[sl].view(rows, lmax[k])
+
+
+def pad_mask_epoch(tokens: torch.Tensor, row_start: torch.Tensor, row_len: torch.Tensor, pad_id: int,
+                   batch_size: int, batch_idx: Optional[torch.Tensor] = None,
+                   X: Optional[torch.Tensor] = None, attn: Optional[torch.Tensor] = None) -> PaddedEpoch:
+    _require_cuda(tokens, row_start, row_len, batch_idx)
+    dev = tokens.device
+    G = int(batch_idx.numel() if batch_idx is not None else row_len.numel())
+    B = int(batch_size)
+    nb = (G + B - 1) // B
+    lmax = torch.empty(nb, dtype=torch.int32, device=dev)
+    cells = torch.empty(nb, dtype=torch.int32, device=dev)
+    check(lib.gtok_batch_extents(_ptr(row_len), _ptr(batch_idx), G, B, _ptr(lmax), _ptr(cells), _stream()))
+    xoff = scan_offsets(cells)
+    if X is None or attn is None:
+        total = int(xoff[-1]) if nb else 0
+        X = torch.empty(total, dtype=torch.int64, device=dev)
+        attn = torch.empty(total, dtype=torch.bool, device=dev)
+    check(lib.gtok_pad_mask_batched(_ptr(tokens), _ptr(row_start), _ptr(row_len), _ptr(batch_idx), G, B, _ptr(lmax),
+                                    _ptr(xoff), int(pad_id), _ptr(X), _ptr(attn), _stream()))
+    return PaddedEpoch(X, attn, xoff, lmax, B, G)
+
+
+# ---------------------------------------------------------------------------
+# K3: SENT  (AutoGraph Graph2TrailTokenizer + train_agtt.py:171-273)
+# ---------------------------------------------------------------------------
+@dataclass
+class CsrBatch:
+    """Canonical undirected CSR of a GraphBatch (see include/gtok.h GtokCsrBatch)."""
+    node_off: torch.Tensor
+    rowptr: torch.Tensor
+    col: torch.Tensor
+    eattr: Optional[torch.Tensor]
+    x: Optional[torch.Tensor]
+    query_u: Optional[torch.Tensor]
+    query_v: Optional[torch.Tensor]
+    max_nodes: int
+    max_nnz: int
+
+    @property
+    def num_graphs(self) -> int:
+        return int(self.node_off.numel()) - 1
+
+    def input_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in
+                   (self.node_off, self.rowptr, self.col, self.eattr, self.x) if t is not None)
+
+
+def build_csr(batch: GraphBatch) -> CsrBatch:
+    """edge_index (any orientation, duplicates allowed) -> canonical undirected CSR.
+    One-off ingest per dataset (what to_undirected/coalesce does inside AutoGraph per
+    call); plain torch ops - plumbing, not the hot path.  The label of {u,v} is the
+    edge_attr of its FIRST directed entry in caller order (oracle: canonical_csr)."""
+    dev = batch.device
+    G = batch.num_graphs
+    E = batch.src.numel()
+    n = batch.num_nodes()
+    Ntot = int(batch.node_off[-1]) if G else 0
+    gid = torch.repeat_interleave(torch.arange(G, device=dev), batch.num_entries())
+    u = batch.src.to(torch.int64) + batch.node_off[gid]
+    v = batch.dst.to(torch.int64) + batch.node_off[gid]
+    keep = u != v
+    idx = torch.arange(E, device=dev)[keep]
+    a, b = torch.minimum(u, v)[keep], torch.maximum(u, v)[keep]
+    key = a * max(Ntot, 1) + b
+    order = torch.argsort(key, stable=True)           # stable: first directed entry first
+    ks = key[order]
+    first = torch.ones_like(ks, dtype=torch.bool)
+    first[1:] = ks[1:] != ks[:-1]
+    sel = order[first]
+    ua, ub = a[sel], b[sel]
+    attr = None if batch.edge_attr is None else batch.edge_attr[idx[sel]]
+    rows = torch.cat([ua, ub])
+    cols = torch.cat([ub, ua])
+    o2 = torch.argsort(rows * max(Ntot, 1) + cols)
+    rows, cols = rows[o2], cols[o2]
+    deg = torch.bincount(rows, minlength=Ntot)
+    rowptr = torch.zeros(Ntot + 1, dtype=torch.int64, device=dev)
+    rowptr[1:] = deg.cumsum(0)
+    if rowptr[-1] >= 2 ** 31:
+        raise ValueError("CSR with >= 2^31 entries: shard the dataset")
+    gnode = torch.repeat_interleave(torch.arange(G, device=dev), n)
+    col_local = (cols - batch.node_off[gnode[rows]]).to(torch.int32)
+    eattr = None if attr is None else torch.cat([attr, attr])[o2].to(torch.int32)
+    nnz_g = rowptr[batch.node_off[1:]] - rowptr[batch.node_off[:-1]]
+    return CsrBatch(batch.node_off, rowptr.to(torch.int32), col_local, eattr, batch.x, batch.query_u, batch.query_v,
+                    int(n.max()) if G else 1, int(nnz_g.max()) if G else 0)
+
+
+@dataclass
+class SentConfig:
+    idx_offset: int = 6
+    node_idx_offset: int = 0
+    edge_idx_offset: int = 0
+    max_length: int = 600
+    labeled: bool = False
+    edge_label_shift: int = 0
+    remap_zinc: bool = False
+    append_query: bool = False
+
+
+def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: int = 0,
+                  choice_words: Optional[torch.Tensor] = None, choice_off: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None, stride: Optional[int] = None):
+    """-> (tokens int64[G, stride], lengths int32[G]); row g valid up to lengths[g]."""
+    _require_cuda(csr.node_off, csr.rowptr, csr.col)
+    dev = csr.node_off.device
+    G = csr.num_graphs
+    need = cfg.max_length + (3 if cfg.append_query else 0)
+    if stride is None:
+        stride = need + (need & 1)          # even stride keeps every row 16-byte aligned
+    if out is None:
+        out = torch.empty((G, stride), dtype=torch.int64, device=dev)
+    lengths = torch.empty(G, dtype=torch.int32, device=dev)
+    cc = _lib.CsrBatchC(G, _ptr(csr.node_off), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.eattr), _ptr(csr.x),
+                        _ptr(csr.query_u), _ptr(csr.query_v), max(1, csr.max_nodes), max(0, csr.max_nnz))
+    sc = _lib.SentCfgC(cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset, cfg.max_length, int(cfg.labeled),
+                       cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query))
+    ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))
+    check(lib.gtok_sent_tokenize(C.byref(cc), C.byref(sc), C.byref(ch), _ptr(lengths), _ptr(out), int(stride), _stream()))
+    return out, lengths

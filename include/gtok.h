@@ -1,0 +1,198 @@
+/*
+ * gtok.h - C ABI of the B200 graph-tokenization engine (libgtok.so).
+ *
+ * Drop-in boundary for ONE hot path of KevinBian107/GLearning-Benchmark: batched
+ * graph -> token-sequence -> padded batch, feeding its IBTT and AGTT transformers.
+ * The reference has no FFI on this path (it is pure Python); each
+ * entry point below states the reference Python it replaces (file:line under the
+ * reference checkout).  The reference-side binding (ctypes) is shown in
+ * INTEGRATION.md and shipped as glearning-benchmark_b200/gtok/_lib.py.
+ *
+ * Conventions
+ *   - every pointer inside the structs and every buffer argument is a DEVICE
+ *     pointer owned by the caller (the host side passes torch CUDA tensors'
+ *     data_ptr()); the library allocates nothing persistent and keeps no state
+ *     besides a thread-local error string.  The only exceptions are marked HOST.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     All work is enqueued on it; no call synchronises the device.
+ *   - return 0 on success, a negative GTOK_E* otherwise; gtok_last_error() gives
+ *     the message for the calling thread.
+ *   - token ids are int64 on output (torch.long, data_loader.py:483,491), graph
+ *     structure is int32, offsets are int64.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns GTOK_ECUDA.
+ */
+#ifndef GTOK_H_
+#define GTOK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTOK_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define GTOK_API __attribute__((visibility("default")))
+#else
+#define GTOK_API
+#endif
+
+enum {
+  GTOK_OK = 0,
+  GTOK_EINVAL = -1,       /* bad argument (null pointer, negative size, ...) */
+  GTOK_ECUDA = -2,        /* CUDA runtime error / no device */
+  GTOK_EUNSUPPORTED = -3, /* shape outside what the kernels cover (see message) */
+  GTOK_EWORKSPACE = -4    /* workspace too small */
+};
+
+/* Disjoint union of G graphs in edge-index (COO) form, caller's column order.
+ * Mirrors PyG Data(edge_index, x, edge_attr, num_nodes, query_u, query_v) as the
+ * reference builds it (graph_token_dataset_autograph.py:385-394,
+ * zinc_dataset_autograph.py:51-73). */
+typedef struct GtokGraphBatch {
+  int64_t num_graphs;
+  const int64_t* node_off;   /* [G+1] */
+  const int64_t* edge_off;   /* [G+1] directed entries of graph g: [edge_off[g], edge_off[g+1]) */
+  const int32_t* src;        /* [E] local node ids */
+  const int32_t* dst;        /* [E] */
+  const int32_t* x;          /* [N] node type, or NULL */
+  const int32_t* edge_attr;  /* [E] edge type, or NULL */
+  const int32_t* query_u;    /* [G] or NULL (shortest_path) */
+  const int32_t* query_v;    /* [G] or NULL */
+  int32_t max_nodes;         /* upper bound on nodes per graph   (0 = unknown) */
+  int32_t max_entries;       /* upper bound on entries per graph (0 = unknown) */
+} GtokGraphBatch;
+
+/* graph-token rule set (docs/synthetic_data.md:46-68, docs/models.md:22) with the
+ * vocabulary already resolved by the unchanged host code (build_vocab_from_texts,
+ * data_loader.py:451-463): the kernels never assume id(str(k)) = base + k. */
+enum { GTOK_TASK_CYCLE_CHECK = 0, GTOK_TASK_SHORTEST_PATH = 1 };
+typedef struct GtokIbttRules {
+  int32_t task;          /* GTOK_TASK_* */
+  int32_t max_len;       /* TokenDataset max_len: ids[:max_len] (data_loader.py:482) */
+  int32_t tok_bos, tok_e, tok_n, tok_q, tok_p;
+  int32_t tok_task;      /* id("has_cycle") or id("shortest_distance") */
+  int32_t oov;           /* vocab["<pad>"]: id of any token missing from the vocab */
+  int32_t node_tok_len;
+  const int32_t* node_tok; /* [node_tok_len] node_tok[k] = vocab.get(str(k), oov) */
+} GtokIbttRules;
+
+/* ZINC molecular rule set (zinc_dataset_indexbase.py:143-227 + zinc_vocab.py:35-78). */
+typedef struct GtokZincVocab {
+  int32_t item_max_len;  /* ZINCTokenizationDataset.max_len (text truncation, :216-221) */
+  int32_t ds_max_len;    /* TokenDataset max_len (data_loader.py:482) */
+  int32_t tok_bos, tok_eos, tok_atom, tok_bond, tok_q, tok_regression, tok_p;
+  int32_t atom_tok[9];   /* id of 'C','N','O','F','P','S','Cl','Br','I' */
+  int32_t atom_oov;      /* id of 'X' (x outside 0..8, zinc_dataset_indexbase.py:104) */
+  int32_t bond_tok[4];   /* id of single,double,triple,aromatic (edge_attr 1..4) */
+  int32_t bond_oov;      /* id of 'unknown' (:138-139) */
+  int32_t oov;           /* vocab["<pad>"] */
+  int32_t node_tok_len;
+  const int32_t* node_tok; /* [node_tok_len] id(str(k)) */
+} GtokZincVocab;
+
+/* Canonical undirected CSR of the same G graphs, what SENT walks every epoch:
+ * rows sorted by neighbour id, no self loops, no duplicate neighbours.  Built once
+ * per dataset (host side: gtok/csr.py). */
+typedef struct GtokCsrBatch {
+  int64_t num_graphs;
+  const int64_t* node_off;   /* [G+1] */
+  const int32_t* rowptr;     /* [N_total+1] global: neighbours of global node i are col[rowptr[i] .. rowptr[i+1]) */
+  const int32_t* col;        /* [nnz] LOCAL neighbour ids */
+  const int32_t* eattr;      /* [nnz] edge type per CSR entry, or NULL */
+  const int32_t* x;          /* [N_total] node type, or NULL */
+  const int32_t* query_u;    /* [G] or NULL */
+  const int32_t* query_v;    /* [G] or NULL */
+  int32_t max_nodes;         /* upper bound on nodes per graph (required, > 0) */
+  int32_t max_nnz;           /* upper bound on CSR entries per graph (required, > 0) */
+} GtokCsrBatch;
+
+/* SENT configuration: the observable contract of AutoGraph's Graph2TrailTokenizer
+ * (train_agtt.py:514-542) plus the fused post-processing of
+ * TokenizedGraphDataset.__getitem__ (train_agtt.py:246-273). */
+typedef struct GtokSentCfg {
+  int32_t idx_offset;        /* 6 + len(dataset_names) */
+  int32_t node_idx_offset;   /* idx_offset + max_num_nodes        (labeled) */
+  int32_t edge_idx_offset;   /* node_idx_offset + num_node_types  (labeled) */
+  int32_t max_length;        /* tokens[:max_length] */
+  int32_t labeled;           /* labeled_graph */
+  int32_t edge_label_shift;  /* edge label token = edge_idx_offset + attr + shift */
+  int32_t remap_zinc;        /* apply remap_zinc_tokens (train_agtt.py:171-244) */
+  int32_t append_query;      /* append [idx_offset+N, idx_offset+u, idx_offset+v] (:257-267) */
+} GtokSentCfg;
+
+/* Where the walk's random words come from (oracle/sent_oracle.py "pick"). */
+typedef struct GtokChoice {
+  uint64_t seed;               /* Philox-4x32-10 key when stream == NULL */
+  int64_t graph_id_base;       /* global id of graph 0 of this batch (rank sharding keeps streams invariant) */
+  const uint32_t* stream;      /* explicit choice words, or NULL */
+  const int64_t* stream_off;   /* [G+1] words of graph g are stream[stream_off[g] .. stream_off[g+1]) */
+} GtokChoice;
+
+GTOK_API int gtok_version(void);
+GTOK_API const char* gtok_last_error(void);
+/* HOST: number of SMs of the current device, or a negative GTOK_E*. */
+GTOK_API int gtok_device_sm_count(void);
+
+/* K1a  lengths of TokenDataset sequences for graph-token graphs:
+ *      min(max_len, 3E + N + 5|7)  (data_loader.py:471-484 applied to the
+ *      serializer grammar).  len_out int32[G]. */
+GTOK_API int gtok_ibtt_lengths(const GtokGraphBatch* batch, const GtokIbttRules* rules,
+                      int32_t* len_out, void* stream);
+
+/* K0   exclusive scan of per-graph lengths -> ragged offsets (implicit in the
+ *      reference's Python list building).  off_out int64[G+1].  ws must hold
+ *      gtok_scan_workspace_bytes(G) bytes. */
+GTOK_API size_t gtok_scan_workspace_bytes(int64_t num_items);
+GTOK_API int gtok_scan_offsets(const int32_t* len, int64_t num_items, int64_t* off_out,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* K1b  graph-token serializer + TokenDataset.__init__ id lookup, strip after
+ *      <p>, truncation (external graph-token grammar + data_loader.py:465-486).
+ *      tok_out int64[off[G]], row g at tok_out[off[g] .. off[g+1]). */
+GTOK_API int gtok_ibtt_serialize(const GtokGraphBatch* batch, const GtokIbttRules* rules,
+                        const int64_t* off, int64_t* tok_out, void* stream);
+
+/* K2a/K2b  ZINCTokenizationDataset.tokenize_molecule + __getitem__ truncation +
+ *      TokenDataset (zinc_dataset_indexbase.py:143-227, data_loader.py:465-486). */
+GTOK_API int gtok_zinc_lengths(const GtokGraphBatch* batch, const GtokZincVocab* vocab,
+                      int32_t* len_out, void* stream);
+GTOK_API int gtok_zinc_serialize(const GtokGraphBatch* batch, const GtokZincVocab* vocab,
+                        const int64_t* off, int64_t* tok_out, void* stream);
+
+/* K3   Graph2TrailTokenizer.__call__ (external AutoGraph; spec in
+ *      oracle/sent_oracle.py) + remap_zinc_tokens + query append
+ *      (train_agtt.py:171-273).  Row g is written at tok_out[g*stride ..], its
+ *      length to len_out[g]; stride >= max_length (+3 with append_query). */
+GTOK_API int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cfg, const GtokChoice* choice,
+                       int32_t* len_out, int64_t* tok_out, int64_t stride, void* stream);
+
+/* K4   collate / collate_fn (data_loader.py:488-497, train_agtt.py:276-302):
+ *      X[b, :len] = row, X[b, len:] = pad_id, attn[b, :len] = 1.  Row b is
+ *      tok[row_start[i] .. row_start[i] + row_len[i]) with i = batch_idx ? batch_idx[b] : b.
+ *      X int64[B, Lmax], attn uint8[B, Lmax] (torch.bool storage). */
+GTOK_API int gtok_pad_mask(const int64_t* tok, const int64_t* row_start, const int32_t* row_len,
+                  const int64_t* batch_idx, int64_t B, int64_t Lmax, int64_t pad_id,
+                  int64_t* X, uint8_t* attn, void* stream);
+
+/* K4b  a whole epoch of batches in one launch (same reference functions, called
+ *      once per DataLoader step there): rows are grouped B at a time in
+ *      batch_idx order (batch k = rows [k*B, min(G,(k+1)*B))); batch k is padded
+ *      to its OWN Lmax_k = max row_len in the batch, exactly as collate does.
+ *      gtok_batch_extents writes lmax int32[nb] and cells int32[nb]
+ *      (= rows_k * Lmax_k; the caller scans cells into xoff int64[nb+1] with
+ *      gtok_scan_offsets); gtok_pad_mask_batched then writes batch k at
+ *      X + xoff[k] / attn + xoff[k], row-major [rows_k, Lmax_k]. nb = ceil(G/B). */
+GTOK_API int gtok_batch_extents(const int32_t* row_len, const int64_t* batch_idx, int64_t G, int64_t B,
+                       int32_t* lmax_out, int32_t* cells_out, void* stream);
+GTOK_API int gtok_pad_mask_batched(const int64_t* tok, const int64_t* row_start, const int32_t* row_len,
+                          const int64_t* batch_idx, int64_t G, int64_t B, const int32_t* lmax,
+                          const int64_t* xoff, int64_t pad_id, int64_t* X, uint8_t* attn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTOK_H_ */

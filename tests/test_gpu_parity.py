@@ -1,0 +1,353 @@
+"""GPU parity tests: CUDA kernels (through the C-ABI, via gtok.engine) vs the oracle
+and vs the golden fixtures made from the reference itself.  Bit-exact everywhere
+(integer / index work).  Run with: pytest -m gpu
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import gt_examples, sha_int64
+from oracle import ibtt_oracle as O
+from oracle import sent_oracle as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _gb_from_recs(recs, with_query):
+    from gtok.batch import GraphBatch
+    return GraphBatch.from_lists([r["n"] for r in recs], [r["edges"] for r in recs],
+                                 queries=[r["query"] for r in recs] if with_query else None)
+
+
+# --------------------------------------------------------------------------- K0
+@pytest.mark.parametrize("n", [0, 1, 5, 2047, 2048, 2049, 100003, 1 << 20, 3_000_017])
+def test_scan_offsets(dev, n):
+    from gtok import engine
+    g = torch.Generator().manual_seed(n)
+    lens = torch.randint(0, 1025, (n,), generator=g, dtype=torch.int32)
+    off = engine.scan_offsets(lens.to(dev)).cpu()
+    want = torch.zeros(n + 1, dtype=torch.int64)
+    want[1:] = lens.to(torch.int64).cumsum(0)
+    assert torch.equal(off, want)
+
+
+def test_scan_offsets_beyond_int32(dev):
+    from gtok import engine
+    n = 3_000_000
+    lens = torch.full((n,), 1024, dtype=torch.int32, device=dev)
+    off = engine.scan_offsets(lens)
+    assert int(off[-1]) == n * 1024 > 2 ** 31
+    assert int(off[n // 2]) == (n // 2) * 1024
+
+
+# --------------------------------------------------------------------------- K1
+GT_CASES = [("cycle_check", 1000, 600, 600), ("shortest_path", 200, 600, 60), ("cycle_check", 64, 97, 30)]
+
+
+@pytest.mark.parametrize("task,G,max_len,max_vocab", GT_CASES)
+def test_ibtt_graph_token_matches_reference_golden(dev, golden_gt, task, G, max_len, max_vocab):
+    from gtok import engine
+    gold = golden_gt[f"{task}_G{G}_L{max_len}_V{max_vocab}"]
+    vocab = gold["vocab"]
+    recs, texts, ex = gt_examples(task, G)
+    kept = [r for r, e in zip(recs, ex) if e["label"] is not None]       # C3 filter happens on the host
+    gb = _gb_from_recs(kept, task == "shortest_path").to(dev)
+    rag = engine.tokenize_ibtt(gb, vocab, task, max_len)
+    rows = rag.rows_cpu()
+    assert [len(r) for r in rows] == gold["lengths"]
+    assert sha_int64([r.numpy() for r in rows]) == gold["ids_sha256"]
+    assert [r.tolist() for r in rows[:24]] == gold["first_seqs"]
+    # K4 on every batch of 128, against the reference's own collate output
+    ep = engine.pad_mask_epoch(rag.tokens, rag.offsets, rag.lengths, vocab["<pad>"], 128)
+    assert ep.num_batches == len(gold["batch_sha"])
+    for k, (shp, xs, as_, _) in enumerate(gold["batch_sha"]):
+        X, A = ep.batch(k)
+        assert list(X.shape) == shp and A.dtype == torch.bool
+        assert sha_int64([X.cpu().numpy()]) == xs
+        assert hashlib.sha256(A.cpu().numpy().tobytes()).hexdigest() == as_
+    X, A = engine.pad_mask(rag.tokens, rag.offsets, rag.lengths, vocab["<pad>"],
+                           batch_idx=torch.arange(8, device=dev))
+    assert X.cpu().tolist() == gold["collate8"]["X"] and A.cpu().to(torch.int64).tolist() == gold["collate8"]["attn"]
+
+
+def test_ibtt_random_shapes_vs_oracle(dev):
+    """empty edge lists, single nodes, OOV node ids (vocab cap), odd/even row starts, both tasks."""
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    rng = np.random.default_rng(5)
+    for task in ("cycle_check", "shortest_path"):
+        recs = []
+        for i in range(300):
+            n = int(rng.integers(1, 70))
+            m = int(rng.integers(0, 3 * n)) if i % 7 else 0
+            edges = [(int(rng.integers(0, n)), int(rng.integers(0, n))) for _ in range(m)]
+            recs.append({"n": n, "edges": edges, "query": (int(rng.integers(0, n)), int(rng.integers(0, n)))})
+        vocab = {t: i for i, t in enumerate(O.SPECIAL)}
+        for k in rng.permutation(40):                      # only 40 of up to 70 node ids known, shuffled ids
+            vocab[str(int(k))] = len(vocab)
+        vocab["has_cycle"] = len(vocab)
+        vocab["shortest_distance"] = len(vocab)
+        for max_len in (600, 33, 1):
+            gb = GraphBatch.from_lists([r["n"] for r in recs], [r["edges"] for r in recs],
+                                       queries=[r["query"] for r in recs]).to(dev)
+            rows = engine.tokenize_ibtt(gb, vocab, task, max_len).rows_cpu()
+            for r, got in zip(recs, rows):
+                src = np.asarray([a for a, _ in r["edges"]], dtype=np.int32)
+                dst = np.asarray([b for _, b in r["edges"]], dtype=np.int32)
+                want = O.ibtt_ids(r["n"], src, dst, task, vocab, max_len, r["query"])
+                assert got.tolist() == want.tolist()
+
+
+def test_ibtt_empty_batch(dev):
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    gb = GraphBatch.from_lists([], []).to(dev)
+    rag = engine.tokenize_ibtt(gb, {t: i for i, t in enumerate(O.SPECIAL)}, "cycle_check", 64, max_nodes=1)
+    assert rag.tokens.numel() == 0 and rag.offsets.cpu().tolist() == [0]
+
+
+def test_ibtt_roundtrip_property_large(dev):
+    """Size-independent property at scale: detokenised rows parse back (reference inverse
+    parser grammar, graph_token_dataset_autograph.py:14-54) to the input edge lists, and
+    the total length equals the closed form."""
+    from gtok import engine, synth
+    G = 200_000
+    gb = synth.er_graph_token(G, seed=11, device=dev)
+    vocab = {t: i for i, t in enumerate(O.SPECIAL)}
+    for k in range(49):
+        vocab[str(k)] = len(vocab)
+    vocab["has_cycle"] = len(vocab)
+    itos = {i: t for t, i in vocab.items()}
+    rag = engine.tokenize_ibtt(gb, vocab, "cycle_check", 600)
+    n, e = gb.num_nodes(), gb.num_entries()
+    want_len = torch.clamp(3 * e + n + 5, max=600).to(torch.int32)
+    assert torch.equal(rag.lengths, want_len)
+    assert int(rag.offsets[-1]) == int(want_len.sum())
+    cpu = gb.to("cpu")
+    for g in list(range(0, G, G // 50)):
+        row = rag.row(g).cpu().tolist()
+        nn, s, d, _, _ = cpu.graph(g)
+        if len(row) < 600:
+            nodes, edges = O.parse_graph_text(" ".join(itos[t] for t in row))
+            assert nodes == list(range(nn)) and edges == list(zip(s.tolist(), d.tolist()))
+
+
+# --------------------------------------------------------------------------- K2
+def _zinc_batch(mols, dev):
+    from gtok.batch import GraphBatch
+    return GraphBatch.from_lists([m["n"] for m in mols], [list(zip(m["src"], m["dst"])) for m in mols],
+                                 x_lists=[m["x"] for m in mols], attr_lists=[m["attr"] for m in mols]).to(dev)
+
+
+@pytest.mark.parametrize("max_len", [1024, 120, 121, 122, 64])
+def test_zinc_matches_reference_golden(dev, golden_zinc, max_len):
+    from gtok import engine
+    gold = golden_zinc[f"L{max_len}"]
+    vocab = gold["vocab"]
+    gb = _zinc_batch(golden_zinc["mols"], dev)
+    rag = engine.tokenize_zinc(gb, vocab, max_len)
+    rows = rag.rows_cpu()
+    assert [len(r) for r in rows] == gold["lengths"]
+    assert sha_int64([r.numpy() for r in rows]) == gold["ids_sha256"]
+    assert [r.tolist() for r in rows[:32]] == gold["first_seqs"]
+    X, A = engine.pad_mask(rag.tokens, rag.offsets, rag.lengths, vocab["<pad>"], batch_idx=torch.arange(8, device=dev))
+    assert X.cpu().tolist() == gold["collate8"]["X"] and A.cpu().to(torch.int64).tolist() == gold["collate8"]["attn"]
+
+
+def test_zinc_adversarial_vs_oracle(dev):
+    """duplicates, self loops, reversed-first orientation, no edges, single atom, OOV atoms/bonds,
+    ids missing from the vocab, many columns (second kernel variant)."""
+    from gtok import engine
+    rng = np.random.default_rng(9)
+    vocab = O.zinc_fixed_vocab()
+    vocab = O.zinc_extend_vocab(vocab, [str(k) for k in rng.permutation(30)] + ["X"])     # no 'unknown', ids >= 30 OOV
+    for big in (False, True):
+        mols = []
+        for i in range(200):
+            n = int(rng.integers(1, 45))
+            m = int(rng.integers(0, 200 if big else 100)) if i % 9 else 0
+            s = rng.integers(0, n, m)
+            d = rng.integers(0, n, m)
+            mols.append({"n": n, "src": s.tolist(), "dst": d.tolist(), "x": rng.integers(-1, 12, n).tolist(),
+                         "attr": rng.integers(0, 7, m).tolist()})
+        gb = _zinc_batch(mols, dev)
+        for max_len in (1024, 77):
+            rows = engine.tokenize_zinc(gb, vocab, max_len).rows_cpu()
+            for mo, got in zip(mols, rows):
+                want = O.zinc_ids(mo["x"], mo["src"], mo["dst"], mo["attr"], vocab, max_len, max_len)
+                assert got.tolist() == want.tolist()
+
+
+def test_zinc_properties_large(dev):
+    """1M ZINC-shaped molecules (BASELINE config 2 size): closed-form lengths, checksum of a
+    strided sample against the oracle, structural invariants on every row start."""
+    from gtok import engine, synth
+    G = 1_000_000
+    gb = synth.zinc_shaped(G, seed=0, device=dev)
+    vocab = O.zinc_extend_vocab(O.zinc_fixed_vocab(), [str(k) for k in range(37)] + ["X", "unknown"])
+    rag = engine.tokenize_zinc(gb, vocab, 1024)
+    n, ed = gb.num_nodes(), gb.num_entries()
+    assert torch.equal(rag.lengths.to(torch.int64), 2 * n + 4 * (ed // 2) + 4)      # both directions present
+    assert int(rag.offsets[-1]) == int(rag.lengths.sum())
+    assert bool((rag.tokens[rag.offsets[:-1]] == vocab["<bos>"]).all())
+    assert bool((rag.tokens[rag.offsets[1:] - 1] == vocab["<p>"]).all())
+    cpu = gb.to("cpu")
+    for g in range(0, G, G // 64):
+        nn, s, d, x, a = cpu.graph(g)
+        want = O.zinc_ids(x.tolist(), s.tolist(), d.tolist(), a.tolist(), vocab, 1024, 1024)
+        assert rag.row(g).cpu().tolist() == want.tolist()
+
+
+# --------------------------------------------------------------------------- K4
+def test_collate_permuted_batches(dev):
+    from gtok import engine
+    rng = np.random.default_rng(2)
+    lens = rng.integers(0, 50, 1000)
+    seqs = [rng.integers(0, 999, l).astype(np.int64) for l in lens]
+    tok = torch.from_numpy(np.concatenate(seqs)).to(dev)
+    rl = torch.from_numpy(lens.astype(np.int32)).to(dev)
+    rs = torch.zeros(1001, dtype=torch.int64)
+    rs[1:] = torch.from_numpy(lens).cumsum(0)
+    rs = rs.to(dev)
+    perm = rng.permutation(1000)
+    ep = engine.pad_mask_epoch(tok, rs, rl, 7, 37, batch_idx=torch.from_numpy(perm).to(dev))
+    for k in range(ep.num_batches):
+        idx = perm[k * 37:(k + 1) * 37]
+        if max(len(seqs[i]) for i in idx) == 0:
+            continue
+        Xw, Aw, _ = O.collate([seqs[i] for i in idx], [0] * len(idx), 7)
+        X, A = ep.batch(k)
+        assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+        X1, A1 = engine.pad_mask(tok, rs, rl, 7, batch_idx=torch.from_numpy(idx).to(dev))
+        assert np.array_equal(X1.cpu().numpy(), Xw) and np.array_equal(A1.cpu().numpy(), Aw)
+
+
+# --------------------------------------------------------------------------- K3
+def _sent_inputs(recs, dev, labeled_mols=None):
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    if labeled_mols is None:
+        gb = GraphBatch.from_lists([r["n"] for r in recs], [r["edges"] for r in recs],
+                                   queries=[r["query"] for r in recs] if recs and recs[0].get("query") else None)
+    else:
+        gb = GraphBatch.from_lists([m["n"] for m in labeled_mols],
+                                   [list(zip(m["src"], m["dst"])) for m in labeled_mols],
+                                   x_lists=[m["x"] for m in labeled_mols], attr_lists=[m["attr"] for m in labeled_mols])
+    return gb, engine.build_csr(gb.to(dev))
+
+
+def test_sent_unlabeled_seeded_vs_oracle(dev):
+    from gtok import engine, synth
+    recs = synth.er_config1_numpy(300, seed=4, task="cycle_check")
+    recs += [{"n": 1, "edges": [], "query": None}, {"n": 5, "edges": [], "query": None},
+             {"n": 2, "edges": [(0, 1)], "query": None}, {"n": 6, "edges": [(0, 1), (2, 3), (4, 5)], "query": None}]
+    gb, csr = _sent_inputs(recs, dev)
+    for max_length, seed, base in ((600, 0, 0), (600, 12345678901234, 1000), (40, 3, 7)):
+        cfg = engine.SentConfig(idx_offset=6, max_length=max_length)
+        tok, ln = engine.tokenize_sent(csr, cfg, seed=seed, graph_id_base=base)
+        tok, ln = tok.cpu(), ln.cpu().tolist()
+        ocfg = S.SentConfig(idx_offset=6, max_length=max_length)
+        for g, r in enumerate(recs):
+            rp, col, _ = S.canonical_csr(r["n"], [e[0] for e in r["edges"]], [e[1] for e in r["edges"]])
+            want = S.sent_tokenize(r["n"], rp, col, ocfg, S.PhiloxWords(seed, base + g))
+            assert tok[g, :ln[g]].tolist() == want.tolist(), (g, max_length, seed)
+
+
+def test_sent_labeled_remap_vs_oracle(dev, golden_zinc):
+    from gtok import engine
+    mols = golden_zinc["mols"][:128]
+    gb, csr = _sent_inputs(None, dev, labeled_mols=mols)
+    nmax = max(m["n"] for m in mols)
+    for remap in (False, True):
+        cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 9, max_length=1024,
+                                labeled=True, remap_zinc=remap)
+        tok, ln = engine.tokenize_sent(csr, cfg, seed=99)
+        tok, ln = tok.cpu(), ln.cpu().tolist()
+        ocfg = S.SentConfig(6, 6 + nmax, 6 + nmax + 9, 1024, True)
+        for g, m in enumerate(mols):
+            rp, col, ea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"])
+            want = S.sent_tokenize(m["n"], rp, col, ocfg, S.PhiloxWords(99, g), x=m["x"], eattr=ea)
+            if remap:
+                want = O.remap_zinc(want, 6, 6 + nmax, 6 + nmax + 9)
+            assert tok[g, :ln[g]].tolist() == want.tolist(), g
+
+
+def test_sent_choice_stream_replay_and_query(dev):
+    """Explicit choice words (the deterministic-replay mode) + fused <q> u v append."""
+    from gtok import engine, synth
+    recs = synth.er_config1_numpy(64, seed=8, task="shortest_path")
+    gb, csr = _sent_inputs(recs, dev)
+    rng = np.random.default_rng(0)
+    words = [rng.integers(0, 2 ** 32, 2 * r["n"] + 2, dtype=np.uint64).astype(np.uint32) for r in recs]
+    words[3] = words[3][:2]                                   # short stream: words past the end read as 0
+    woff = np.zeros(len(recs) + 1, dtype=np.int64)
+    woff[1:] = np.cumsum([len(w) for w in words])
+    cw = torch.from_numpy(np.concatenate(words).view(np.int32)).to(dev)
+    cfg = engine.SentConfig(idx_offset=6, max_length=600, append_query=True)
+    tok, ln = engine.tokenize_sent(csr, cfg, choice_words=cw, choice_off=torch.from_numpy(woff).to(dev))
+    tok, ln = tok.cpu(), ln.cpu().tolist()
+    ocfg = S.SentConfig(idx_offset=6, max_length=600)
+    for g, r in enumerate(recs):
+        rp, col, _ = S.canonical_csr(r["n"], [e[0] for e in r["edges"]], [e[1] for e in r["edges"]])
+        want = S.sent_tokenize(r["n"], rp, col, ocfg, S.StreamWords(words[g]))
+        want = O.append_query(want, 6, r["n"], r["query"][0], r["query"][1])
+        assert tok[g, :ln[g]].tolist() == want.tolist(), g
+
+
+def test_sent_validity_and_distribution_large(dev):
+    """Free-running mode at scale: every sampled row decodes to the input graph (each edge covered
+    exactly once); trail-length and token-frequency statistics match the oracle run with OTHER seeds."""
+    from gtok import engine, synth
+    G = 100_000
+    gb = synth.er_graph_token(G, seed=21, device=dev)
+    csr = engine.build_csr(gb)
+    cfg = engine.SentConfig(idx_offset=6, max_length=2000)
+    tok, ln = engine.tokenize_sent(csr, cfg, seed=777)
+    cpu = gb.to("cpu")
+    ocfg = S.SentConfig(idx_offset=6, max_length=2000)
+    lens_gpu, lens_cpu, resets_gpu, resets_cpu = [], [], 0, 0
+    sample = list(range(0, G, G // 400))
+    tk = tok[torch.tensor(sample, device=dev)].cpu()
+    lns = ln[torch.tensor(sample, device=dev)].cpu().tolist()
+    for j, g in enumerate(sample):
+        n, s, d, _, _ = cpu.graph(g)
+        row = tk[j, :lns[j]].tolist()
+        nn, edges, _ = S.sent_decode(row, ocfg)
+        rp, col, _ = S.canonical_csr(n, s.tolist(), d.tolist())
+        assert nn == n and len(edges) == len(col) // 2
+        vis = S.visit_order(n, rp, col, S.PhiloxWords(777, g))
+        want_edges = {(min(vis[a], vis[b]), max(vis[a], vis[b])) for a, b in zip(s.tolist(), d.tolist())}
+        assert set(edges) == want_edges
+        lens_gpu.append(len(row))
+        resets_gpu += row.count(S.RESET)
+        o = S.sent_tokenize(n, rp, col, ocfg, S.PhiloxWords(4242, g))
+        lens_cpu.append(len(o))
+        resets_cpu += o.tolist().count(S.RESET)
+    # same graphs, independent randomness: means within 3 sigma of each other
+    a, b = np.asarray(lens_gpu, float), np.asarray(lens_cpu, float)
+    diff = a - b
+    assert abs(diff.mean()) < 4 * diff.std() / np.sqrt(len(diff)) + 1e-9
+    assert abs(resets_gpu - resets_cpu) < 6 * np.sqrt(resets_gpu + resets_cpu + 1)
+
+
+def test_sent_sharding_invariance(dev):
+    """Rank shards see the same rows as the single-GPU run (seeds keyed by GLOBAL graph id)."""
+    from gtok import engine, synth
+    gb = synth.er_graph_token(4096, seed=1, device="cpu")
+    cfg = engine.SentConfig(idx_offset=6, max_length=600)
+    full, fl = engine.tokenize_sent(engine.build_csr(gb.to(dev)), cfg, seed=5)
+    for r in range(4):
+        sh = gb.slice(r * 1024, (r + 1) * 1024).to(dev)
+        t, l = engine.tokenize_sent(engine.build_csr(sh), cfg, seed=5, graph_id_base=r * 1024)
+        assert torch.equal(l, fl[r * 1024:(r + 1) * 1024])
+        m = torch.arange(t.shape[1], device=dev)[None, :] < l[:, None]
+        assert torch.equal(t[m], full[r * 1024:(r + 1) * 1024][m])
