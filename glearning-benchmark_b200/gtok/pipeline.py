@@ -1,0 +1,236 @@
+"""Whole-dataset pipelines: graphs -> ragged int64 tokens -> per-batch padded X/attn,
+with every buffer preallocated so a pass is nothing but kernel launches (no host
+sync, no allocation).  This is the call a user makes to tokenize an epoch:
+
+    pipe = ZincIbttPipeline(capacity_from=host_batch, vocab=vocab, max_len=1024, batch_size=128)
+    res  = pipe.run(host_batch)          # H2D + 6 kernels (+ D2H of lengths / batch extents)
+
+Stands in for, on the reference side (trainer/train_ibtt.py:231-233, :395-402):
+    [ds[i] for i in range(len(ds))] -> TokenDataset(...) -> DataLoader(collate_fn=collate)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, engine
+from ._lib import lib, check
+from .batch import GraphBatch
+from .engine import _ptr, _stream
+
+
+@dataclass
+class EpochResult:
+    tokens: torch.Tensor      # int64 ragged (device, capacity-sized; valid up to offsets[-1])
+    offsets: torch.Tensor     # int64 [G+1]
+    lengths: torch.Tensor     # int32 [G]
+    padded: engine.PaddedEpoch
+    host_lengths: Optional[torch.Tensor] = None   # pinned copies (e2e mode)
+    host_lmax: Optional[torch.Tensor] = None
+    host_xoff: Optional[torch.Tensor] = None
+
+
+class _PipelineBase:
+    """Shared buffer management: device copies of the graph arrays + outputs."""
+
+    def __init__(self, G: int, n_total: int, e_total: int, tok_capacity: int, pad_capacity: int,
+                 batch_size: int, device, fields: List[str]):
+        self.G, self.B = int(G), int(batch_size)
+        self.device = torch.device(device)
+        d = self.device
+        self.nb = (self.G + self.B - 1) // self.B
+        i32, i64 = torch.int32, torch.int64
+        self.dev_in = {"node_off": torch.empty(G + 1, dtype=i64, device=d),
+                       "edge_off": torch.empty(G + 1, dtype=i64, device=d),
+                       "src": torch.empty(e_total, dtype=i32, device=d),
+                       "dst": torch.empty(e_total, dtype=i32, device=d)}
+        if "x" in fields:
+            self.dev_in["x"] = torch.empty(n_total, dtype=i32, device=d)
+        if "edge_attr" in fields:
+            self.dev_in["edge_attr"] = torch.empty(e_total, dtype=i32, device=d)
+        if "query" in fields:
+            self.dev_in["query_u"] = torch.empty(G, dtype=i32, device=d)
+            self.dev_in["query_v"] = torch.empty(G, dtype=i32, device=d)
+        self.lengths = torch.empty(G, dtype=i32, device=d)
+        self.offsets = torch.empty(G + 1, dtype=i64, device=d)
+        self.tokens = torch.empty(tok_capacity, dtype=i64, device=d)
+        self.lmax = torch.empty(self.nb, dtype=i32, device=d)
+        self.cells = torch.empty(self.nb, dtype=i32, device=d)
+        self.xoff = torch.empty(self.nb + 1, dtype=i64, device=d)
+        self.X = torch.empty(pad_capacity, dtype=i64, device=d)
+        self.attn = torch.empty(pad_capacity, dtype=torch.bool, device=d)
+        self.ws_bytes = lib.gtok_scan_workspace_bytes(max(G, self.nb))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=d)
+        self.h_lengths = torch.empty(G, dtype=i32).pin_memory()
+        self.h_lmax = torch.empty(self.nb, dtype=i32).pin_memory()
+        self.h_xoff = torch.empty(self.nb + 1, dtype=i64).pin_memory()
+        self.kernel_launches_per_pass = 6
+        self.timers = None      # optional list to collect (name, start_event, end_event)
+
+    # -- helpers ---------------------------------------------------------
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.dev_in.values())
+
+    def d2h_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.h_lengths, self.h_lmax, self.h_xoff))
+
+    def upload(self, host: GraphBatch) -> None:
+        """pinned host arrays -> the preallocated device arrays (async on the current stream)."""
+        src = {"node_off": host.node_off, "edge_off": host.edge_off, "src": host.src, "dst": host.dst,
+               "x": host.x, "edge_attr": host.edge_attr, "query_u": host.query_u, "query_v": host.query_v}
+        for k, dst in self.dev_in.items():
+            dst.copy_(src[k], non_blocking=True)
+
+    def use_device_batch(self, dev_batch: GraphBatch) -> None:
+        """Point the pipeline at arrays already resident in HBM (no copy)."""
+        m = {"node_off": dev_batch.node_off, "edge_off": dev_batch.edge_off, "src": dev_batch.src,
+             "dst": dev_batch.dst, "x": dev_batch.x, "edge_attr": dev_batch.edge_attr,
+             "query_u": dev_batch.query_u, "query_v": dev_batch.query_v}
+        for k in list(self.dev_in):
+            self.dev_in[k] = m[k]
+
+    def download(self) -> None:
+        self.h_lengths.copy_(self.lengths, non_blocking=True)
+        self.h_lmax.copy_(self.lmax, non_blocking=True)
+        self.h_xoff.copy_(self.xoff, non_blocking=True)
+
+    def _timed(self, name, fn):
+        if self.timers is None:
+            fn()
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        self.timers.append((name, a, b))
+
+    def _scan(self, lens, n, off):
+        check(lib.gtok_scan_offsets(_ptr(lens), n, _ptr(off), _ptr(self.ws), self.ws_bytes, _stream()))
+
+    def _collate(self, pad_id: int):
+        st = _stream()
+        self._timed("batch_extents", lambda: check(lib.gtok_batch_extents(
+            _ptr(self.lengths), None, self.G, self.B, _ptr(self.lmax), _ptr(self.cells), st)))
+        self._timed("scan_batches", lambda: self._scan(self.cells, self.nb, self.xoff))
+        self._timed("pad_mask_batched", lambda: check(lib.gtok_pad_mask_batched(
+            _ptr(self.tokens), _ptr(self.offsets), _ptr(self.lengths), None, self.G, self.B, _ptr(self.lmax),
+            _ptr(self.xoff), pad_id, _ptr(self.X), _ptr(self.attn), st)))
+
+    def _result(self, e2e: bool) -> EpochResult:
+        pe = engine.PaddedEpoch(self.X, self.attn, self.xoff, self.lmax, self.B, self.G)
+        if e2e:
+            pe._host = None
+            return EpochResult(self.tokens, self.offsets, self.lengths, pe, self.h_lengths, self.h_lmax, self.h_xoff)
+        return EpochResult(self.tokens, self.offsets, self.lengths, pe)
+
+
+class ZincIbttPipeline(_PipelineBase):
+    """BASELINE config 2: IBTT tokenization of ZINC-shaped molecules + collate."""
+
+    def __init__(self, host_batch: GraphBatch, vocab: Dict[str, int], max_len: int, batch_size: int, device):
+        G = host_batch.num_graphs
+        n = host_batch.num_nodes()
+        e = host_batch.num_entries()
+        self.max_nodes = int(n.max()) if G else 1
+        self.max_entries = int(e.max()) if G else 1
+        n_total, e_total = int(host_batch.node_off[-1]), int(host_batch.edge_off[-1])
+        row_bound = min(max_len, 2 * self.max_nodes + 4 * self.max_entries + 4)
+        tok_cap = min(G * row_bound, 2 * n_total + 4 * e_total + 4 * G)
+        super().__init__(G, n_total, e_total, tok_cap + 2, G * row_bound + 2, batch_size, device, ["x", "edge_attr"])
+        self.vocab = vocab
+        self.pad_id = int(vocab["<pad>"])
+        self.zv, self._tbl = engine.zinc_vocab_c(vocab, max_len, max_len, self.max_nodes, self.device)
+
+    def _batch_c(self):
+        d = self.dev_in
+        return _lib.GraphBatchC(self.G, _ptr(d["node_off"]), _ptr(d["edge_off"]), _ptr(d["src"]), _ptr(d["dst"]),
+                                _ptr(d["x"]), _ptr(d["edge_attr"]), None, None, max(1, self.max_nodes),
+                                max(1, self.max_entries))
+
+    def launch(self) -> None:
+        """The hot path on whatever dev_in points at: 6 kernels, no sync."""
+        bc = self._batch_c()
+        st = _stream()
+        self._timed("zinc_lengths", lambda: check(lib.gtok_zinc_lengths(C.byref(bc), C.byref(self.zv), _ptr(self.lengths), st)))
+        self._timed("scan_rows", lambda: self._scan(self.lengths, self.G, self.offsets))
+        self._timed("zinc_serialize", lambda: check(lib.gtok_zinc_serialize(
+            C.byref(bc), C.byref(self.zv), _ptr(self.offsets), _ptr(self.tokens), st)))
+        self._collate(self.pad_id)
+
+    def run(self, host_batch: GraphBatch) -> EpochResult:
+        """Public end-to-end call: pinned host graphs in, device batches + host row metadata out."""
+        self.upload(host_batch)
+        self.launch()
+        self.download()
+        torch.cuda.current_stream().synchronize()
+        return self._result(True)
+
+    def algorithmic_bytes(self, total_tokens: int, padded_cells: int) -> Dict[str, int]:
+        """SURVEY.md 8d per-graph figures x the graphs of one launch."""
+        G = self.G
+        n_total = self.dev_in["x"].numel()
+        e_total = self.dev_in["src"].numel()
+        return {
+            "zinc_lengths": 8 * e_total + 16 * G + 4 * G,
+            "scan_rows": 4 * G + 8 * (G + 1),
+            "zinc_serialize": 12 * e_total + 4 * n_total + 16 * G + 8 * total_tokens,
+            "batch_extents": 4 * G + 8 * self.nb,
+            "scan_batches": 4 * self.nb + 8 * (self.nb + 1),
+            "pad_mask_batched": 8 * total_tokens + 9 * padded_cells,
+        }
+
+
+class GraphTokenIbttPipeline(_PipelineBase):
+    """BASELINE config 1/5: IBTT tokenization of graph-token graphs + collate."""
+
+    def __init__(self, host_batch: GraphBatch, vocab: Dict[str, int], task: str, max_len: int, batch_size: int, device):
+        G = host_batch.num_graphs
+        n = host_batch.num_nodes()
+        e = host_batch.num_entries()
+        self.max_nodes = int(n.max()) if G else 1
+        q = 5 if task == "cycle_check" else 7
+        n_total, e_total = int(host_batch.node_off[-1]), int(host_batch.edge_off[-1])
+        row_bound = min(max_len, int((3 * e + n).max()) + q) if G else 1
+        tok_cap = min(G * row_bound, 3 * e_total + n_total + q * G)
+        fields = ["query"] if task == "shortest_path" else []
+        super().__init__(G, n_total, e_total, tok_cap + 2, G * row_bound + 2, batch_size, device, fields)
+        self.task = task
+        self.pad_id = int(vocab["<pad>"])
+        self.rules, self._tbl = engine.ibtt_rules(vocab, task, max_len, self.max_nodes, self.device)
+
+    def _batch_c(self):
+        d = self.dev_in
+        return _lib.GraphBatchC(self.G, _ptr(d["node_off"]), _ptr(d["edge_off"]), _ptr(d["src"]), _ptr(d["dst"]),
+                                None, None, _ptr(d.get("query_u")), _ptr(d.get("query_v")), max(1, self.max_nodes), 1)
+
+    def launch(self) -> None:
+        bc = self._batch_c()
+        st = _stream()
+        self._timed("ibtt_lengths", lambda: check(lib.gtok_ibtt_lengths(C.byref(bc), C.byref(self.rules), _ptr(self.lengths), st)))
+        self._timed("scan_rows", lambda: self._scan(self.lengths, self.G, self.offsets))
+        self._timed("ibtt_serialize", lambda: check(lib.gtok_ibtt_serialize(
+            C.byref(bc), C.byref(self.rules), _ptr(self.offsets), _ptr(self.tokens), st)))
+        self._collate(self.pad_id)
+
+    def run(self, host_batch: GraphBatch) -> EpochResult:
+        self.upload(host_batch)
+        self.launch()
+        self.download()
+        torch.cuda.current_stream().synchronize()
+        return self._result(True)
+
+    def algorithmic_bytes(self, total_tokens: int, padded_cells: int) -> Dict[str, int]:
+        G = self.G
+        e_total = self.dev_in["src"].numel()
+        qb = 8 * G if self.task == "shortest_path" else 0
+        return {
+            "ibtt_lengths": 32 * G + 4 * G,
+            "scan_rows": 4 * G + 8 * (G + 1),
+            "ibtt_serialize": 8 * e_total + 16 * G + qb + 8 * total_tokens,
+            "batch_extents": 4 * G + 8 * self.nb,
+            "scan_batches": 4 * self.nb + 8 * (self.nb + 1),
+            "pad_mask_batched": 8 * total_tokens + 9 * padded_cells,
+        }
