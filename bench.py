@@ -191,7 +191,7 @@ def run_gpu(args):
     vocab = zinc_vocab()
     dev_batch = synth.zinc_shaped(G, seed=rank, device=dev)           # rank r owns graphs [r*G, (r+1)*G)
     host_batch = dev_batch.to("cpu").pin_memory()
-    pipe = ZincIbttPipeline(host_batch, vocab, MAX_LEN, BATCH, dev)
+    pipe = ZincIbttPipeline(host_batch, vocab, MAX_LEN, BATCH, dev, fused=None if args.zinc_fused < 0 else bool(args.zinc_fused))
     pipe.use_device_batch(dev_batch)
 
     def barrier():
@@ -262,7 +262,7 @@ def run_gpu(args):
             kernels[name] = {"ms": avg, "algo_bytes": algo[name], "GBps": algo[name] / avg / 1e6,
                              "frac": algo[name] / avg / 1e6 / peak}
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
-        step_algo = algo["zinc_serialize"] + 9 * padded_cells     # SURVEY 8d "fused" figure for the whole step
+        step_algo = algo["zinc_serialize"] + 9 * padded_cells - 8 * total_tokens     # SURVEY 8d "fused" figure for the whole step
         step_s = ms / 1e3 / args.steps
         line = {
             "metric": METRIC, "value": graphs_all / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -304,6 +304,7 @@ def main():
     ap.add_argument("--graphs", type=int, default=1_000_000, help="graphs per GPU")
     ap.add_argument("--cpu-graphs-per-core", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--zinc-fused", type=int, default=-1, help="-1 auto, 0 three-kernel path, 1 fused single pass")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -27,20 +27,41 @@ __device__ __forceinline__ unsigned long long mask_bytes(int nvalid) {
 
 __device__ __forceinline__ void warp_collate_row(const int64_t* __restrict__ src, int len, int Lmax, int64_t pad,
                                                  int64_t* __restrict__ xrow, uint8_t* __restrict__ arow) {
-  warp_write_row(xrow, Lmax, [&](int p) -> int64_t { return p < len ? __ldcs(src + p) : pad; });
-  // mask row: scalar head up to 16-byte alignment, 16-byte interior, scalar tail
   const int lane = lane_id();
-  int head = (int)((16 - (reinterpret_cast<uintptr_t>(arow) & 15)) & 15);
-  if (head > Lmax) head = Lmax;
-  if (lane < head) arow[lane] = (uint8_t)(lane < len);
-  const int nvec = (Lmax - head) >> 4;
-  for (int j = lane; j < nvec; j += kWarp) {
-    const int p = head + 16 * j;
-    const int nv = len - p;
-    ulonglong2 m = make_ulonglong2(mask_bytes(nv), mask_bytes(nv - 8));
-    __stcs(reinterpret_cast<ulonglong2*>(arow + p), m);
+  // ---- X row: [0,len) copied, [len,Lmax) = pad; 16-byte stores on the aligned interior.
+  const int head = (int)((reinterpret_cast<uintptr_t>(xrow) >> 3) & 1);
+  if (head && lane == 0 && Lmax > 0) st_stream_i64(xrow, 0 < len ? __ldcs(src) : pad);
+  const int npair = (Lmax - head) >> 1;
+  int j = lane;
+  // two pairs per lane per trip: four independent 8-byte loads in flight before the stores
+  for (; j + kWarp < npair; j += 2 * kWarp) {
+    const int p0 = head + 2 * j, p1 = p0 + 2 * kWarp;
+    const int64_t a0 = p0 < len ? __ldcs(src + p0) : pad;
+    const int64_t b0 = p0 + 1 < len ? __ldcs(src + p0 + 1) : pad;
+    const int64_t a1 = p1 < len ? __ldcs(src + p1) : pad;
+    const int64_t b1 = p1 + 1 < len ? __ldcs(src + p1 + 1) : pad;
+    st_stream_i64x2(xrow + p0, a0, b0);
+    st_stream_i64x2(xrow + p1, a1, b1);
   }
-  const int tail = head + 16 * nvec;
+  if (j < npair) {
+    const int p0 = head + 2 * j;
+    const int64_t a0 = p0 < len ? __ldcs(src + p0) : pad;
+    const int64_t b0 = p0 + 1 < len ? __ldcs(src + p0 + 1) : pad;
+    st_stream_i64x2(xrow + p0, a0, b0);
+  }
+  const int tailx = head + 2 * npair;
+  if (tailx < Lmax && lane == 31) st_stream_i64(xrow + tailx, tailx < len ? __ldcs(src + tailx) : pad);
+  // ---- mask row: scalar head up to 16-byte alignment, 16-byte interior, scalar tail
+  int mh = (int)((16 - (reinterpret_cast<uintptr_t>(arow) & 15)) & 15);
+  if (mh > Lmax) mh = Lmax;
+  if (lane < mh) arow[lane] = (uint8_t)(lane < len);
+  const int nvec = (Lmax - mh) >> 4;
+  for (int q = lane; q < nvec; q += kWarp) {
+    const int p = mh + 16 * q;
+    const int nv = len - p;
+    __stcs(reinterpret_cast<ulonglong2*>(arow + p), make_ulonglong2(mask_bytes(nv), mask_bytes(nv - 8)));
+  }
+  const int tail = mh + 16 * nvec;
   if (tail + lane < Lmax && lane < 16) arow[tail + lane] = (uint8_t)(tail + lane < len);
 }
 
@@ -80,19 +101,40 @@ batch_extents_kernel(const int32_t* __restrict__ row_len, const int64_t* __restr
   }
 }
 
-__global__ void __launch_bounds__(kColThreads)
+__global__ void __launch_bounds__(kColThreads, 8)
 pad_mask_batched_kernel(const int64_t* __restrict__ tok, const int64_t* __restrict__ row_start,
                         const int32_t* __restrict__ row_len, const int64_t* __restrict__ batch_idx, int64_t G,
-                        int64_t B, const int32_t* __restrict__ lmax, const int64_t* __restrict__ xoff, int64_t pad,
-                        int64_t* __restrict__ X, uint8_t* __restrict__ attn) {
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = warp0; r < G; r += nwarps) {
-    const int64_t k = r / B;
-    const int64_t i = batch_idx ? __ldg(batch_idx + r) : r;
+                        int B, int64_t nb, const int32_t* __restrict__ lmax, const int64_t* __restrict__ xoff,
+                        int64_t pad, int64_t* __restrict__ X, uint8_t* __restrict__ attn) {
+  // one CTA per batch (grid-stride): batch extents are CTA-uniform, rows go round-robin to warps,
+  // each warp fetches the metadata of its NEXT row before copying the current one.
+  const int w = threadIdx.x >> 5;
+  for (int64_t k = blockIdx.x; k < nb; k += gridDim.x) {
     const int Lm = __ldg(lmax + k);
-    const int64_t base = __ldg(xoff + k) + (r - k * B) * Lm;
-    warp_collate_row(tok + __ldg(row_start + i), __ldg(row_len + i), Lm, pad, X + base, attn + base);
+    const int64_t base = __ldg(xoff + k);
+    const int64_t r0 = k * B;
+    const int rows = (int)((G - r0 < B) ? (G - r0) : B);
+    int rr = w;
+    int64_t i = 0, st = 0;
+    int len = 0;
+    if (rr < rows) {
+      i = batch_idx ? __ldg(batch_idx + r0 + rr) : r0 + rr;
+      len = __ldg(row_len + i);
+      st = __ldg(row_start + i);
+    }
+    while (rr < rows) {
+      const int nr = rr + kColWarps;
+      int64_t ni = 0, nst = 0;
+      int nlen = 0;
+      if (nr < rows) {
+        ni = batch_idx ? __ldg(batch_idx + r0 + nr) : r0 + nr;
+        nlen = __ldg(row_len + ni);
+        nst = __ldg(row_start + ni);
+      }
+      const int64_t o = base + (int64_t)rr * Lm;
+      warp_collate_row(tok + st, len, Lm, pad, X + o, attn + o);
+      rr = nr; i = ni; len = nlen; st = nst;
+    }
   }
 }
 
@@ -135,9 +177,11 @@ extern "C" int gtok_pad_mask_batched(const int64_t* tok, const int64_t* row_star
   if (G == 0) return GTOK_OK;
   GTOK_REQUIRE(tok && row_start && row_len && lmax && xoff && X && attn, GTOK_EINVAL, "pad_mask_batched: null pointer");
   GTOK_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0, GTOK_EINVAL, "pad_mask_batched: X must be 16-byte aligned");
-  const int64_t work = (G + kColWarps - 1) / kColWarps;
-  const int grid = persistent_grid(pad_mask_batched_kernel, kColThreads, 0, work);
-  pad_mask_batched_kernel<<<grid, kColThreads, 0, (cudaStream_t)stream>>>(tok, row_start, row_len, batch_idx, G, B, lmax, xoff, pad_id, X, attn);
+  GTOK_REQUIRE(B < (1ll << 31), GTOK_EINVAL, "pad_mask_batched: batch size too large");
+  const int64_t nb = (G + B - 1) / B;
+  // small batches: several CTAs per SM worth of batches per wave; large batches: one batch spans the CTA's warps anyway
+  const int grid = persistent_grid(pad_mask_batched_kernel, kColThreads, 0, nb);
+  pad_mask_batched_kernel<<<grid, kColThreads, 0, (cudaStream_t)stream>>>(tok, row_start, row_len, batch_idx, G, (int)B, nb, lmax, xoff, pad_id, X, attn);
   GTOK_CUDA_TRY(cudaGetLastError());
   return GTOK_OK;
 }

@@ -76,4 +76,50 @@ __device__ __forceinline__ void warp_write_row(int64_t* __restrict__ row, int L,
   if (tail < L && lane == 31) st_stream_i64(row + tail, (int64_t)tok(tail));
 }
 
+
+// ---- decoupled look-back (single-pass chained scan) -------------------------
+// One 64-bit word per tile carries {flag (top 2 bits) | value (62 bits)}, so flag
+// and value can never be observed out of order; relaxed gpu-scope accesses suffice.
+constexpr unsigned long long kFlagAgg = 1ull << 62;
+constexpr unsigned long long kFlagIncl = 2ull << 62;
+constexpr unsigned long long kValMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by ONE full warp of the tile's CTA.  Publishes `total` for `tile`, walks
+// back over predecessor tiles and returns the exclusive prefix (same value in all lanes).
+// Tiles must be numbered by an atomic ticket so predecessors are already running.
+__device__ __forceinline__ long long lookback_exclusive(unsigned long long* status, long long tile, long long total) {
+  const int t = lane_id();
+  if (t == 0) st_relaxed_u64(status + tile, (tile == 0 ? kFlagIncl : kFlagAgg) | (unsigned long long)total);
+  long long excl = 0;
+  long long j = tile - 1;
+  while (j >= 0) {
+    const long long idx = j - t;
+    unsigned long long w;
+    if (idx >= 0) {
+      do { w = ld_relaxed_u64(status + idx); } while ((w >> 62) == 0);
+    } else {
+      w = kFlagIncl;  // virtual tile -1: inclusive prefix 0
+    }
+    const unsigned incl_mask = __ballot_sync(kFull, (w >> 62) == 2);
+    const int stop = incl_mask ? (__ffs(incl_mask) - 1) : 31;
+    long long val = (t <= stop) ? (long long)(w & kValMask) : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(kFull, val, d);
+    excl += val;
+    if (incl_mask) break;
+    j -= 32;
+  }
+  if (t == 0 && tile != 0) st_relaxed_u64(status + tile, kFlagIncl | (unsigned long long)(excl + total));
+  return excl;
+}
+
 }  // namespace gtok

@@ -15,19 +15,6 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
-constexpr unsigned long long kFlagAgg = 1ull << 62;
-constexpr unsigned long long kFlagIncl = 2ull << 62;
-constexpr unsigned long long kValMask = (1ull << 62) - 1;
-
-__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 template <typename OutT>
 __global__ void __launch_bounds__(kScanThreads)
 scan_offsets_kernel(const int32_t* __restrict__ len, int64_t n, OutT* __restrict__ off,
@@ -75,30 +62,8 @@ scan_offsets_kernel(const int32_t* __restrict__ len, int64_t n, OutT* __restrict
 
   // publish the tile aggregate, then look back (warp 0)
   if (t < 32) {
-    if (t == 0) st_relaxed(status + tile, (tile == 0 ? kFlagIncl : kFlagAgg) | (unsigned long long)total);
-    long long excl = 0;
-    int64_t j = tile - 1;
-    while (j >= 0) {
-      const int64_t idx = j - t;
-      unsigned long long w;
-      if (idx >= 0) {
-        do { w = ld_relaxed(status + idx); } while ((w >> 62) == 0);
-      } else {
-        w = kFlagIncl;  // virtual tile -1: inclusive prefix 0
-      }
-      const unsigned incl_mask = __ballot_sync(kFull, (w >> 62) == 2);
-      const int stop = incl_mask ? (__ffs(incl_mask) - 1) : 31;
-      long long val = (t <= stop) ? (long long)(w & kValMask) : 0;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(kFull, val, d);
-      excl += val;
-      if (incl_mask) break;
-      j -= 32;
-    }
-    if (t == 0) {
-      if (tile != 0) st_relaxed(status + tile, kFlagIncl | (unsigned long long)(excl + total));
-      s_excl = excl;
-    }
+    const long long excl = lookback_exclusive(status, tile, total);
+    if (t == 0) s_excl = excl;
   }
   __syncthreads();
   long long run = s_excl + texcl;

@@ -13,14 +13,21 @@
 // same unordered pair (set() dedupe, zinc_dataset_indexbase.py:176-184), in column
 // order and in THAT column's (u, v) orientation.
 //
-// One warp per molecule.  Dedupe without sorting: each column inserts its packed
-// unordered pair into a per-warp shared-memory open-addressing table (atomicCAS
-// claims the slot for the key, atomicMin keeps the smallest column index); a
-// column survives iff it is its slot's minimum.  Survivors are compacted in
-// column order with ballot/popc, then the row is written position-centric with
-// 16-byte streaming stores (gtok_common.cuh: warp_write_row).
+// One warp per molecule, two code paths chosen by batch.max_nodes:
+//  * N <= 64 (every real molecule set): the "seen" set is an N x 64-bit adjacency
+//    bitmap in the warp's shared memory.  Columns are taken 32 at a time in order;
+//    __match_any_sync groups equal pairs inside the chunk (lowest lane = first
+//    occurrence), the bitmap answers "seen in an earlier chunk", survivors are
+//    ranked with ballot/popc and write their four tokens straight into a staged
+//    int32 row in shared memory; atoms are staged lane-per-atom; the row then
+//    leaves with aligned 16-byte streaming stores.  ~200 warp instructions per
+//    molecule (v1's generic position-centric path needed ~670 and was issue bound,
+//    profiles/r1a_v1_full.txt).  The lengths pass only needs the NUMBER of distinct
+//    pairs: one atomicOr per column, then a popcount of the bitmap.
+//  * N > 64: open-addressing hash in shared memory (atomicCAS claims the slot for
+//    the key, atomicMin keeps the smallest column index), position-centric write.
 // Algorithmic bytes / molecule: 8*Ed (edge_index) + 4*Ed (edge_attr) + 4N (x) +
-// 16 (offsets) + 8L.  This v1 reads edge_index twice (lengths pass + write pass).
+// 16 (offsets) + 8L.  The lengths pass re-reads edge_index (8*Ed).
 #include "gtok_common.cuh"
 
 namespace gtok {
@@ -145,6 +152,148 @@ zinc_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v, con
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// N <= 64 path
+// ---------------------------------------------------------------------------
+constexpr int kSmallN = 64;
+
+__device__ __forceinline__ void load_graph_header(const GtokGraphBatch& b, const int64_t* __restrict__ off, int64_t g,
+                                                  int lane, bool with_off, int64_t& n0, int& N, int64_t& e0, int& Ed,
+                                                  int64_t& o0, int& L) {
+  int64_t s = 0;
+  if (lane < 2) s = __ldg(b.node_off + g + lane);
+  else if (lane < 4) s = __ldg(b.edge_off + g + lane - 2);
+  else if (with_off && lane < 6) s = __ldg(off + g + lane - 4);
+  n0 = __shfl_sync(kFull, s, 0);
+  N = (int)(__shfl_sync(kFull, s, 1) - n0);
+  e0 = __shfl_sync(kFull, s, 2);
+  Ed = (int)(__shfl_sync(kFull, s, 3) - e0);
+  o0 = __shfl_sync(kFull, s, 4);
+  L = (int)(__shfl_sync(kFull, s, 5) - o0);
+}
+
+__global__ void __launch_bounds__(kZincThreads)
+zinc_small_lengths_kernel(const GtokGraphBatch b, int item_max, int ds_max, int32_t* __restrict__ len_out) {
+  __shared__ unsigned s_rows[kZincWarps][2 * kSmallN];
+  const int lane = lane_id();
+  unsigned* rows = s_rows[threadIdx.x >> 5];
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t g = warp0; g < b.num_graphs; g += nwarps) {
+    int64_t n0, e0, o0; int N, Ed, L;
+    load_graph_header(b, nullptr, g, lane, false, n0, N, e0, Ed, o0, L);
+    const int32_t* __restrict__ src = b.src + e0;
+    const int32_t* __restrict__ dst = b.dst + e0;
+    for (int i = lane; i < 2 * N; i += kWarp) rows[i] = 0u;
+    __syncwarp();
+    for (int i = lane; i < Ed; i += kWarp) {
+      const unsigned a = (unsigned)__ldg(src + i) & 63u, c = (unsigned)__ldg(dst + i) & 63u;
+      const unsigned mn = min(a, c), mx = max(a, c);
+      atomicOr(&rows[2 * mn + (mx >> 5)], 1u << (mx & 31));
+    }
+    __syncwarp();
+    int cnt = 0;
+    for (int i = lane; i < 2 * N; i += kWarp) cnt += __popc(rows[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(kFull, cnt, d);
+    int eos_pos;
+    if (lane == 0) len_out[g] = zinc_row_length(N, cnt, item_max, ds_max, &eos_pos);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kZincThreads, 8)
+zinc_small_serialize_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
+                            const int64_t* __restrict__ off, int64_t* __restrict__ out, int cap) {
+  extern __shared__ __align__(16) unsigned char z_smem[];
+  const int lane = lane_id();
+  const int w = threadIdx.x >> 5;
+  // per warp: 2*64 bitmap words, then the staged row (cap int32)
+  unsigned* rows = reinterpret_cast<unsigned*>(z_smem) + (size_t)w * (2 * kSmallN + cap);
+  int* stage = reinterpret_cast<int*>(rows + 2 * kSmallN);
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int32_t* __restrict__ node_tok = v.node_tok;
+  const int tbl = v.node_tok_len;
+  const unsigned lt = (1u << lane) - 1u;
+
+  for (int64_t g = warp0; g < b.num_graphs; g += nwarps) {
+    int64_t n0, e0, o0; int N, Ed, L;
+    load_graph_header(b, off, g, lane, true, n0, N, e0, Ed, o0, L);
+    const int32_t* __restrict__ src = b.src + e0;
+    const int32_t* __restrict__ dst = b.dst + e0;
+    const int32_t* __restrict__ attr = b.edge_attr ? b.edge_attr + e0 : nullptr;
+    const int32_t* __restrict__ x = b.x + n0;
+
+    for (int i = lane; i < 2 * N; i += kWarp) rows[i] = 0u;
+    if (lane == 0) stage[0] = v.tok_bos;
+    // atoms: lane per atom, positions 1+2i, 2+2i
+    for (int i = lane; i < N; i += kWarp) {
+      const int xi = __ldg(x + i);
+      const int p = 1 + 2 * i;
+      if (p < cap) stage[p] = v.tok_atom;
+      if (p + 1 < cap) stage[p + 1] = ((unsigned)xi < 9u) ? v.atom_tok[xi] : v.atom_oov;
+    }
+    __syncwarp();
+    // bonds: 32 columns at a time, in column order
+    const int bbase = 1 + 2 * N;
+    int Eu = 0;
+    for (int i0 = 0; i0 < Ed; i0 += kWarp) {
+      const int i = i0 + lane;
+      const bool valid = i < Ed;
+      int a = 0, c = 0, t = 0;
+      if (valid) {
+        a = __ldg(src + i);
+        c = __ldg(dst + i);
+        t = attr ? __ldg(attr + i) : 0;
+      }
+      const unsigned mn = (unsigned)min(a, c) & 63u, mx = (unsigned)max(a, c) & 63u;
+      const unsigned key = valid ? (mn << 6 | mx) : (0x10000u | (unsigned)lane);
+      const unsigned grp = __match_any_sync(kFull, key);
+      const unsigned word = 2 * mn + (mx >> 5), bit = 1u << (mx & 31);
+      const bool keep = valid && ((grp & lt) == 0u) && ((rows[word] & bit) == 0u);
+      __syncwarp();
+      if (keep) atomicOr(&rows[word], bit);
+      const unsigned m = __ballot_sync(kFull, keep);
+      if (keep) {
+        const int p = bbase + 4 * (Eu + __popc(m & lt));
+        if (p + 3 < cap) {
+          stage[p] = v.tok_bond;
+          stage[p + 1] = ((unsigned)(t - 1) < 4u) ? v.bond_tok[t - 1] : v.bond_oov;
+          stage[p + 2] = ((unsigned)a < (unsigned)tbl) ? __ldg(node_tok + a) : v.oov;
+          stage[p + 3] = ((unsigned)c < (unsigned)tbl) ? __ldg(node_tok + c) : v.oov;
+        } else {
+          if (p < cap) stage[p] = v.tok_bond;
+          if (p + 1 < cap) stage[p + 1] = ((unsigned)(t - 1) < 4u) ? v.bond_tok[t - 1] : v.bond_oov;
+          if (p + 2 < cap) stage[p + 2] = ((unsigned)a < (unsigned)tbl) ? __ldg(node_tok + a) : v.oov;
+        }
+      }
+      Eu += __popc(m);
+      __syncwarp();
+    }
+    int eos_pos;
+    zinc_row_length(N, Eu, v.item_max_len, v.ds_max_len, &eos_pos);
+    const int tbase = bbase + 4 * Eu;
+    if (lane < 3 && tbase + lane < cap) stage[tbase + lane] = lane == 0 ? v.tok_q : (lane == 1 ? v.tok_regression : v.tok_p);
+    __syncwarp();
+    if (lane == 0 && eos_pos >= 0 && eos_pos < cap) stage[eos_pos] = v.tok_eos;
+    __syncwarp();
+    // aligned 16-byte streaming write-out of the staged row
+    int64_t* __restrict__ row = out + o0;
+    const int head = (int)(o0 & 1);
+    if (head && lane == 0 && L > 0) st_stream_i64(row, (int64_t)stage[0]);
+    const int npair = (L - head) >> 1;
+    for (int j = lane; j < npair; j += kWarp) {
+      const int p = head + 2 * j;
+      st_stream_i64x2(row + p, (int64_t)stage[p], (int64_t)stage[p + 1]);
+    }
+    const int tail = head + 2 * npair;
+    if (tail < L && lane == 31) st_stream_i64(row + tail, (int64_t)stage[tail]);
+    __syncwarp();
+  }
+}
+
 static int zinc_check(const GtokGraphBatch* b, const GtokZincVocab* v, const char* who) {
   GTOK_REQUIRE(b != nullptr && v != nullptr, GTOK_EINVAL, "%s: null batch/vocab", who);
   GTOK_REQUIRE(b->num_graphs >= 0, GTOK_EINVAL, "%s: negative graph count", who);
@@ -171,9 +320,31 @@ static int zinc_launch(const GtokGraphBatch* b, const GtokZincVocab* v, const in
   return GTOK_OK;
 }
 
+static int zinc_small_launch(bool write, const GtokGraphBatch* b, const GtokZincVocab* v, const int64_t* off,
+                             int32_t* len_out, int64_t* out, cudaStream_t st) {
+  const int64_t work = (b->num_graphs + kZincWarps - 1) / kZincWarps;
+  if (!write) {
+    const int grid = persistent_grid(zinc_small_lengths_kernel, kZincThreads, 0, work);
+    zinc_small_lengths_kernel<<<grid, kZincThreads, 0, st>>>(*b, v->item_max_len, v->ds_max_len, len_out);
+    GTOK_CUDA_TRY(cudaGetLastError());
+    return GTOK_OK;
+  }
+  long long bound = 2ll * b->max_nodes + 4ll * b->max_entries + 4;
+  const long long lim = (long long)(v->item_max_len > v->ds_max_len ? v->item_max_len : v->ds_max_len) + 1;
+  if (bound > lim) bound = lim;
+  const int cap = (int)((bound + 4 + 3) & ~3ll);
+  const size_t smem = (size_t)kZincWarps * (2 * kSmallN + cap) * 4;
+  GTOK_CUDA_TRY(cudaFuncSetAttribute(zinc_small_serialize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = persistent_grid(zinc_small_serialize_kernel, kZincThreads, smem, work);
+  zinc_small_serialize_kernel<<<grid, kZincThreads, smem, st>>>(*b, *v, off, out, cap);
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}
+
 template <bool WRITE>
 static int zinc_dispatch(const GtokGraphBatch* b, const GtokZincVocab* v, const int64_t* off, int32_t* len_out,
                          int64_t* out, cudaStream_t st) {
+  if (b->max_nodes <= kSmallN && b->max_entries <= 256) return zinc_small_launch(WRITE, b, v, off, len_out, out, st);
   // static shared memory budget is 48 KB per CTA: 8 warps * (8 B * H + 2 B * MAXE)
   if (b->max_entries <= 128) return zinc_launch<256, 128, WRITE>(b, v, off, len_out, out, st);
   return zinc_launch<512, 256, WRITE>(b, v, off, len_out, out, st);

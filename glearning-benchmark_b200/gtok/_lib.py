@@ -41,7 +41,7 @@ class ZincVocabC(C.Structure):
     _fields_ = [("item_max_len", i32), ("ds_max_len", i32), ("tok_bos", i32), ("tok_eos", i32),
                 ("tok_atom", i32), ("tok_bond", i32), ("tok_q", i32), ("tok_regression", i32), ("tok_p", i32),
                 ("atom_tok", i32 * 9), ("atom_oov", i32), ("bond_tok", i32 * 4), ("bond_oov", i32),
-                ("oov", i32), ("node_tok_len", i32), ("node_tok", vp)]
+                ("oov", i32), ("node_tok_len", i32), ("node_tok", vp), ("max_token_id", i32), ("reserved_", i32)]
 
 
 class CsrBatchC(C.Structure):
@@ -70,6 +70,8 @@ PROTOTYPES = {
     "gtok_ibtt_serialize": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(IbttRulesC), vp, vp, vp]),
     "gtok_zinc_lengths": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(ZincVocabC), vp, vp]),
     "gtok_zinc_serialize": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(ZincVocabC), vp, vp, vp]),
+    "gtok_zinc_tokenize_workspace_bytes": (C.c_size_t, [i64]),
+    "gtok_zinc_tokenize": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(ZincVocabC), vp, vp, vp, i64, vp, C.c_size_t, vp]),
     "gtok_sent_tokenize": (C.c_int, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), C.POINTER(ChoiceC), vp, vp, i64, vp]),
     "gtok_pad_mask": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp]),
     "gtok_batch_extents": (C.c_int, [vp, vp, i64, i64, vp, vp, vp]),

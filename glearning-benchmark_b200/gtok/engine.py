@@ -138,12 +138,15 @@ def zinc_vocab_c(vocab: Dict[str, int], item_max_len: int, ds_max_len: int, tabl
         v.bond_tok[i] = g(b)
     v.atom_oov, v.bond_oov, v.oov = g("X"), g("unknown"), pad
     v.node_tok_len, v.node_tok = tbl.numel(), _ptr(tbl)
+    v.max_token_id = max(vocab.values())
     return v, tbl
 
 
 def tokenize_zinc(batch: GraphBatch, vocab: Dict[str, int], max_len: int, item_max_len: Optional[int] = None,
                   max_nodes: Optional[int] = None, max_entries: Optional[int] = None,
-                  out: Optional[torch.Tensor] = None) -> Ragged:
+                  out: Optional[torch.Tensor] = None, fused: Optional[bool] = None) -> Ragged:
+    """ZINC molecules -> ragged ids.  Molecule-shaped batches (<= 64 atoms, <= 256 columns) take the
+    single-pass fused kernel; anything else takes lengths -> scan -> serialize."""
     _require_cuda(batch.src)
     if batch.x is None:
         raise ValueError("ZINC tokenization needs batch.x (atom types)")
@@ -152,6 +155,25 @@ def tokenize_zinc(batch: GraphBatch, vocab: Dict[str, int], max_len: int, item_m
     bc = _batch_c(batch, max_nodes, max_entries)
     zv, tbl = zinc_vocab_c(vocab, max_len if item_max_len is None else item_max_len, max_len, bc.max_nodes, dev)
     lengths = torch.empty(G, dtype=torch.int32, device=dev)
+    can_fuse = bc.max_nodes <= 64 and bc.max_entries <= 256
+    if fused is None:
+        fused = can_fuse
+    if fused:
+        if not can_fuse:
+            raise ValueError("fused ZINC path needs <= 64 atoms and <= 256 edge_index columns per molecule")
+        n_total, e_total = batch.x.numel(), batch.src.numel()
+        bound = min(G * min(max_len, 2 * bc.max_nodes + 4 * bc.max_entries + 4), 2 * n_total + 4 * e_total + 4 * G)
+        if out is None:
+            out = torch.empty(bound + 2, dtype=torch.int64, device=dev)
+        off = torch.empty(G + 1, dtype=torch.int64, device=dev)
+        nbytes = lib.gtok_zinc_tokenize_workspace_bytes(G)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib.gtok_zinc_tokenize(C.byref(bc), C.byref(zv), _ptr(lengths), _ptr(off), _ptr(out), out.numel(),
+                                     _ptr(ws), nbytes, _stream()))
+        total = int(off[-1]) if G else 0
+        if total > out.numel():
+            raise ValueError("output buffer too small")
+        return Ragged(out[:total], off, lengths)
     check(lib.gtok_zinc_lengths(C.byref(bc), C.byref(zv), _ptr(lengths), _stream()))
     off = scan_offsets(lengths)
     total = int(off[-1]) if G else 0

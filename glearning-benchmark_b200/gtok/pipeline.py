@@ -130,7 +130,8 @@ class _PipelineBase:
 class ZincIbttPipeline(_PipelineBase):
     """BASELINE config 2: IBTT tokenization of ZINC-shaped molecules + collate."""
 
-    def __init__(self, host_batch: GraphBatch, vocab: Dict[str, int], max_len: int, batch_size: int, device):
+    def __init__(self, host_batch: GraphBatch, vocab: Dict[str, int], max_len: int, batch_size: int, device,
+                 fused: Optional[bool] = None):
         G = host_batch.num_graphs
         n = host_batch.num_nodes()
         e = host_batch.num_entries()
@@ -143,6 +144,11 @@ class ZincIbttPipeline(_PipelineBase):
         self.vocab = vocab
         self.pad_id = int(vocab["<pad>"])
         self.zv, self._tbl = engine.zinc_vocab_c(vocab, max_len, max_len, self.max_nodes, self.device)
+        self.fused = (self.max_nodes <= 64 and self.max_entries <= 256) if fused is None else bool(fused)
+        if self.fused:
+            self.kernel_launches_per_pass = 4
+            self.ws_bytes = max(self.ws_bytes, lib.gtok_zinc_tokenize_workspace_bytes(G))
+            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
 
     def _batch_c(self):
         d = self.dev_in
@@ -151,9 +157,15 @@ class ZincIbttPipeline(_PipelineBase):
                                 max(1, self.max_entries))
 
     def launch(self) -> None:
-        """The hot path on whatever dev_in points at: 6 kernels, no sync."""
+        """The hot path on whatever dev_in points at: 4 kernels (fused tokenizer) or 6, no sync."""
         bc = self._batch_c()
         st = _stream()
+        if self.fused:
+            self._timed("zinc_tokenize", lambda: check(lib.gtok_zinc_tokenize(
+                C.byref(bc), C.byref(self.zv), _ptr(self.lengths), _ptr(self.offsets), _ptr(self.tokens),
+                self.tokens.numel(), _ptr(self.ws), self.ws_bytes, st)))
+            self._collate(self.pad_id)
+            return
         self._timed("zinc_lengths", lambda: check(lib.gtok_zinc_lengths(C.byref(bc), C.byref(self.zv), _ptr(self.lengths), st)))
         self._timed("scan_rows", lambda: self._scan(self.lengths, self.G, self.offsets))
         self._timed("zinc_serialize", lambda: check(lib.gtok_zinc_serialize(
@@ -174,6 +186,7 @@ class ZincIbttPipeline(_PipelineBase):
         n_total = self.dev_in["x"].numel()
         e_total = self.dev_in["src"].numel()
         return {
+            "zinc_tokenize": 12 * e_total + 4 * n_total + 16 * G + 8 * total_tokens,
             "zinc_lengths": 8 * e_total + 16 * G + 4 * G,
             "scan_rows": 4 * G + 8 * (G + 1),
             "zinc_serialize": 12 * e_total + 4 * n_total + 16 * G + 8 * total_tokens,

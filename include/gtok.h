@@ -92,6 +92,9 @@ typedef struct GtokZincVocab {
   int32_t oov;           /* vocab["<pad>"] */
   int32_t node_tok_len;
   const int32_t* node_tok; /* [node_tok_len] id(str(k)) */
+  int32_t max_token_id;  /* upper bound on every id above incl. node_tok[] (0 = unknown); ids < 65536
+                            let the fused kernel stage rows as 16-bit in shared memory */
+  int32_t reserved_;
 } GtokZincVocab;
 
 /* Canonical undirected CSR of the same G graphs, what SENT walks every epoch:
@@ -162,6 +165,18 @@ GTOK_API int gtok_zinc_lengths(const GtokGraphBatch* batch, const GtokZincVocab*
                       int32_t* len_out, void* stream);
 GTOK_API int gtok_zinc_serialize(const GtokGraphBatch* batch, const GtokZincVocab* vocab,
                         const int64_t* off, int64_t* tok_out, void* stream);
+
+/* K2 fused  the same two reference functions in ONE pass over HBM: lengths, ragged
+ *      offsets (int64[G+1]) and rows are produced together (tiles of 32 molecules
+ *      staged in shared memory, decoupled look-back for the offsets).  Molecule
+ *      shapes only: batch.max_nodes <= 64 and batch.max_entries <= 256, otherwise
+ *      GTOK_EUNSUPPORTED (use the three calls above).  Rows that would end beyond
+ *      tok_capacity are not written (lengths/offsets still are), so the caller can
+ *      size tok_out from the bound 2N+4E+4G and check off_out[G] afterwards. */
+GTOK_API size_t gtok_zinc_tokenize_workspace_bytes(int64_t num_graphs);
+GTOK_API int gtok_zinc_tokenize(const GtokGraphBatch* batch, const GtokZincVocab* vocab, int32_t* len_out,
+                                int64_t* off_out, int64_t* tok_out, int64_t tok_capacity,
+                                void* ws, size_t ws_bytes, void* stream);
 
 /* K3   Graph2TrailTokenizer.__call__ (external AutoGraph; spec in
  *      oracle/sent_oracle.py) + remap_zinc_tokens + query append

@@ -148,13 +148,15 @@ def _zinc_batch(mols, dev):
                                  x_lists=[m["x"] for m in mols], attr_lists=[m["attr"] for m in mols]).to(dev)
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("max_len", [1024, 120, 121, 122, 64])
-def test_zinc_matches_reference_golden(dev, golden_zinc, max_len):
+def test_zinc_matches_reference_golden(dev, golden_zinc, max_len, fused):
+    """fused = single-pass tile kernel; not fused = lengths -> scan -> serialize (bitmap path)."""
     from gtok import engine
     gold = golden_zinc[f"L{max_len}"]
     vocab = gold["vocab"]
     gb = _zinc_batch(golden_zinc["mols"], dev)
-    rag = engine.tokenize_zinc(gb, vocab, max_len)
+    rag = engine.tokenize_zinc(gb, vocab, max_len, fused=fused)
     rows = rag.rows_cpu()
     assert [len(r) for r in rows] == gold["lengths"]
     assert sha_int64([r.numpy() for r in rows]) == gold["ids_sha256"]
@@ -170,20 +172,22 @@ def test_zinc_adversarial_vs_oracle(dev):
     rng = np.random.default_rng(9)
     vocab = O.zinc_fixed_vocab()
     vocab = O.zinc_extend_vocab(vocab, [str(k) for k in rng.permutation(30)] + ["X"])     # no 'unknown', ids >= 30 OOV
-    for big in (False, True):
+    wide = {t: (i if i < 22 else i + 70000) for t, i in vocab.items()}                  # ids >= 65536: 32-bit staging path
+    for big, nmax, fused in ((False, 45, True), (True, 45, True), (False, 45, False), (True, 64, False),
+                             (False, 100, None), (True, 300, None)):      # > 64 atoms: hash-table path
         mols = []
         for i in range(200):
-            n = int(rng.integers(1, 45))
+            n = int(rng.integers(1, nmax + 1))
             m = int(rng.integers(0, 200 if big else 100)) if i % 9 else 0
             s = rng.integers(0, n, m)
             d = rng.integers(0, n, m)
             mols.append({"n": n, "src": s.tolist(), "dst": d.tolist(), "x": rng.integers(-1, 12, n).tolist(),
                          "attr": rng.integers(0, 7, m).tolist()})
         gb = _zinc_batch(mols, dev)
-        for max_len in (1024, 77):
-            rows = engine.tokenize_zinc(gb, vocab, max_len).rows_cpu()
+        for max_len, voc in ((1024, vocab), (77, vocab), (1024, wide), (50, wide)):
+            rows = engine.tokenize_zinc(gb, voc, max_len, fused=fused).rows_cpu()
             for mo, got in zip(mols, rows):
-                want = O.zinc_ids(mo["x"], mo["src"], mo["dst"], mo["attr"], vocab, max_len, max_len)
+                want = O.zinc_ids(mo["x"], mo["src"], mo["dst"], mo["attr"], voc, max_len, max_len)
                 assert got.tolist() == want.tolist()
 
 
