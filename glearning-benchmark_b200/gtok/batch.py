@@ -103,6 +103,29 @@ class GraphBatch:
                           opt(self.edge_attr, e0, e1), opt(self.query_u, g0, g1),
                           opt(self.query_v, g0, g1), opt(self.y, g0, g1))
 
+    def select(self, idx: torch.Tensor) -> "GraphBatch":
+        """Gather the graphs idx[0], idx[1], ... into a new batch (any order, repeats allowed)."""
+        idx = idx.to(self.node_off.device, torch.int64)
+        n = (self.node_off[idx + 1] - self.node_off[idx])
+        e = (self.edge_off[idx + 1] - self.edge_off[idx])
+        node_off = torch.zeros(idx.numel() + 1, dtype=torch.int64, device=idx.device)
+        node_off[1:] = n.cumsum(0)
+        edge_off = torch.zeros(idx.numel() + 1, dtype=torch.int64, device=idx.device)
+        edge_off[1:] = e.cumsum(0)
+
+        def gather(off_src, off_dst, cnt, arr):
+            if arr is None:
+                return None
+            total = int(off_dst[-1])
+            seg = torch.repeat_interleave(torch.arange(idx.numel(), device=idx.device), cnt)
+            pos = torch.arange(total, device=idx.device) - off_dst[seg] + off_src[idx][seg]
+            return arr[pos]
+        opt = lambda t: None if t is None else t[idx]
+        return GraphBatch(node_off, edge_off, gather(self.edge_off, edge_off, e, self.src),
+                          gather(self.edge_off, edge_off, e, self.dst), gather(self.node_off, node_off, n, self.x),
+                          gather(self.edge_off, edge_off, e, self.edge_attr), opt(self.query_u), opt(self.query_v),
+                          opt(self.y))
+
     # ------------------------------------------------------------------
     @staticmethod
     def from_lists(num_nodes: Sequence[int], edge_lists: Sequence, x_lists=None, attr_lists=None,

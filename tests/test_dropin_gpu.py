@@ -1,0 +1,138 @@
+"""Drop-in surface on the GPU: the reference's own call sequences (trainer/train_ibtt.py:231-233,
+:361-402; trainer/train_agtt.py:246-302, :514-542) executed against the gtok package, compared
+with the golden vectors the reference produced and with the oracle."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import gt_examples, sha_int64
+from oracle import ibtt_oracle as O
+from oracle import sent_oracle as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+class _Mol:
+    pass
+
+
+def _fake_zinc(mols):
+    out = []
+    for m in mols:
+        d = _Mol()
+        d.x = torch.tensor(m["x"], dtype=torch.long).reshape(-1, 1)
+        d.edge_index = torch.tensor([m["src"], m["dst"]], dtype=torch.long)
+        d.edge_attr = torch.tensor(m["attr"], dtype=torch.long)
+        d.y = torch.tensor([m["y"]], dtype=torch.float32)
+        out.append(d)
+    return out
+
+
+@pytest.mark.parametrize("task,G,max_len,max_vocab", [("cycle_check", 1000, 600, 600), ("shortest_path", 200, 600, 60)])
+def test_ibtt_trainer_sequence_graph_token(golden_gt, task, G, max_len, max_vocab):
+    import graph_data_loader as g
+    gold = golden_gt[f"{task}_G{G}_L{max_len}_V{max_vocab}"]
+    _, texts, ex = gt_examples(task, G)
+    vocab, _ = g.build_vocab_from_texts([e["text"] for e in ex], max_tokens=max_vocab)      # train_ibtt.py:391
+    assert vocab == gold["vocab"]
+    ds = g.TokenDataset(ex, vocab, max_len)                                                  # :395
+    assert len(ds) == gold["num_kept"]
+    assert sha_int64([s.numpy() for s in ds.seqs]) == gold["ids_sha256"]
+    assert [int(l) for l in ds.labels] == gold["labels"]
+    seq, lab = ds[3]
+    assert seq.dtype == torch.long and lab.dtype == torch.long and not seq.is_cuda
+    pad_id = vocab["<pad>"]
+    for k, b0 in enumerate(range(0, len(ds), 128)):                                          # collate lambda :399
+        X, A, Y = g.collate([ds[i] for i in range(b0, min(b0 + 128, len(ds)))], pad_id)
+        assert X.is_cuda and A.dtype == torch.bool and Y.dtype == torch.long
+        assert sha_int64([X.cpu().numpy()]) == gold["batch_sha"][k][1]
+        assert sha_int64([Y.cpu().numpy()]) == gold["batch_sha"][k][3]
+    # shuffled batch + foreign (non-registered) rows take the upload path
+    idx = np.random.default_rng(0).permutation(len(ds))[:37]
+    X, A, Y = g.collate([ds[int(i)] for i in idx], pad_id)
+    Xw, Aw, _ = O.collate([ds.seqs[int(i)].numpy() for i in idx], [0] * 37, pad_id)
+    assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+    X2, A2, _ = g.collate([(ds.seqs[int(i)].clone(), ds.labels[int(i)]) for i in idx], pad_id)
+    assert torch.equal(X2, X) and torch.equal(A2, A)
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        g.TokenDataset([{"text": "not a graph at all", "label": 1}], vocab, 64)
+
+
+@pytest.mark.parametrize("max_len", [1024, 120])
+def test_ibtt_trainer_sequence_zinc(golden_zinc, max_len):
+    import graph_data_loader as g
+    gold = golden_zinc[f"L{max_len}"]
+    zds = g.ZINCTokenizationDataset(split="train", max_vocab=2000, max_len=max_len, zinc_dataset=_fake_zinc(golden_zinc["mols"]))
+    ex = [zds[i] for i in range(len(zds))]                                                   # train_ibtt.py:231
+    assert [e["text"] for e in ex[:3]] == gold["first_texts"]
+    vocab, _ = g.build_fixed_zinc_vocab()
+    dyn = []
+    for e in ex:
+        for t in e["text"].split():
+            if t not in vocab and t not in dyn:
+                dyn.append(t)
+    vocab = g.extend_vocab_with_dynamic_tokens(vocab, dyn)                                   # :372
+    assert vocab == gold["vocab"]
+    ds = g.TokenDataset(ex, vocab, max_len)
+    assert sha_int64([s.numpy() for s in ds.seqs]) == gold["ids_sha256"]
+    assert [int(l) for l in ds.labels] == gold["labels"]                                     # int(label) truncation, C4
+    X, A, Y = g.collate([ds[i] for i in range(8)], vocab["<pad>"])
+    assert X.cpu().tolist() == gold["collate8"]["X"] and Y.cpu().tolist() == gold["collate8"]["Y"]
+
+
+def test_agtt_tokenizer_shim_zinc(golden_zinc):
+    import graph_data_loader as g
+    from autograph.datamodules.data.tokenizer import Graph2TrailTokenizer
+    mols = golden_zinc["mols"][:64]
+    pyg = g.ZINCDatasetForAutoGraph(split="train", zinc_dataset=_fake_zinc(mols))
+    nt, et = g.get_zinc_num_types()
+    tok = Graph2TrailTokenizer(dataset_names=[], max_length=1024, truncation_length=1024, labeled_graph=True,
+                               undirected=True)                                              # train_agtt.py:514-520
+    nmax = max(pyg[i].num_nodes for i in range(len(pyg)))
+    tok.set_num_nodes(nmax)
+    tok.set_num_node_and_edge_types(nt, et)
+    cfg = S.SentConfig(6, tok.node_idx_offset, tok.edge_idx_offset, 1024, True)
+    first = []
+    for i, m in enumerate(mols):
+        t = tok(pyg[i])                                                                      # :250
+        assert t.dtype == torch.long and t.dim() == 1 and t[0] == 0 and t[-1] == 4
+        rp, col, ea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"])
+        want = S.sent_tokenize(m["n"], rp, col, cfg, S.PhiloxWords(0, i), x=m["x"], eattr=ea)
+        assert t.tolist() == want.tolist()
+        first.append(t.tolist())
+    again = [tok(pyg[i]).tolist() for i in range(len(mols))]                                 # next epoch: fresh trails
+    assert again != first
+    for i, m in enumerate(mols[:8]):
+        rp, col, ea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"])
+        assert again[i] == S.sent_tokenize(m["n"], rp, col, cfg, S.PhiloxWords(1, i), x=m["x"], eattr=ea).tolist()
+    assert Graph2TrailTokenizer.pad == 5
+
+
+def test_agtt_tokenizer_shim_graph_token(tmp_path):
+    import graph_data_loader as g
+    from autograph.datamodules.data.tokenizer import Graph2TrailTokenizer
+    recs, texts, _ = gt_examples("shortest_path", 40, seed=9)
+    d = tmp_path / "tasks_train" / "shortest_path" / "er" / "train"
+    d.mkdir(parents=True)
+    for i, t in enumerate(texts):
+        (d / f"{i:03d}.json").write_text(json.dumps({"text": t}))
+    ds = g.GraphTokenDatasetForAutoGraph(str(tmp_path), task="shortest_path", algorithm=["er"], split="train", seed=0)
+    tok = Graph2TrailTokenizer(dataset_names=[], max_length=600, truncation_length=600, labeled_graph=False, undirected=True)
+    tok.set_num_nodes(max(ds[i].num_nodes for i in range(len(ds))))
+    cfg = S.SentConfig(idx_offset=6, max_length=600)
+    kept = [r for r in recs if r["label"] != "INF"]
+    assert len(ds) == len(kept)
+    for i, r in enumerate(kept):
+        data = ds[i]
+        assert (data.query_u, data.query_v) == tuple(r["query"]) and data.num_nodes == r["n"]
+        rp, col, _ = S.canonical_csr(r["n"], [e[0] for e in r["edges"]], [e[1] for e in r["edges"]])
+        want = S.sent_tokenize(r["n"], rp, col, cfg, S.PhiloxWords(0, i))
+        assert tok(data).tolist() == want.tolist()
