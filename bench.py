@@ -236,15 +236,13 @@ def run_gpu(args):
     assert int(res.host_xoff[-1]) == padded_cells and int(res.host_lengths.sum()) == total_tokens
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([G, total_tokens], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # the one optional collective of the design: per-rank (graphs, tokens) -> global offsets
-        gathered = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(gathered, cnt)
-        cnt = torch.stack(gathered).sum(0)
     ms, e2e_ms = float(t[0]), float(t[1])
-    graphs_all, tokens_all = int(cnt[0]), int(cnt[1])
+    # the one optional collective of the design: per-rank (graphs, tokens) -> global offsets
+    from gtok import shard
+    info = shard.global_offsets(G, total_tokens, device=dev)
+    graphs_all, tokens_all = info["graphs"], info["tokens"]
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
