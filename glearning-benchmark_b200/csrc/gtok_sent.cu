@@ -328,6 +328,9 @@ static int sent_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const Gtok
   return GTOK_OK;
 }
 
+int sent_small_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
+                        int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
+
 }  // namespace gtok
 
 extern "C" int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cfg, const GtokChoice* choice,
@@ -349,6 +352,12 @@ extern "C" int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cf
   GTOK_REQUIRE(choice->stream == nullptr || choice->stream_off != nullptr, GTOK_EINVAL, "sent: choice stream without offsets");
   GTOK_REQUIRE((reinterpret_cast<uintptr_t>(tok_out) & 15) == 0, GTOK_EINVAL, "sent: tok_out must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // graphs of at most 64 nodes: one thread per graph on 64-bit adjacency masks (gtok_sent_small.cu)
+    bool handled = false;
+    const int rc = sent_small_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);
+    if (rc != GTOK_OK || handled) return rc;
+  }
   const bool staged = cfg->max_length <= 2048;
   if (cfg->labeled) {
     return staged ? sent_launch<true, true>(csr, cfg, choice, len_out, tok_out, stride, st)

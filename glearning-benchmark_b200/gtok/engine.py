@@ -266,6 +266,8 @@ class CsrBatch:
     query_v: Optional[torch.Tensor]
     max_nodes: int
     max_nnz: int
+    max_label: int = 0          # labels lie in [0, max_label]; 0 = unknown
+    adj64: Optional[torch.Tensor] = None   # int64[N_total] adjacency bit rows (graphs of <= 64 nodes)
 
     @property
     def num_graphs(self) -> int:
@@ -274,6 +276,19 @@ class CsrBatch:
     def input_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in
                    (self.node_off, self.rowptr, self.col, self.eattr, self.x) if t is not None)
+
+    def sent_input_bytes(self, labeled: bool) -> int:
+        """Bytes the SENT kernel has to read per pass (bit rows replace rowptr+col when present)."""
+        b = self.node_off.numel() * 8
+        if self.adj64 is not None:
+            b += self.adj64.numel() * 8
+            if labeled:
+                b += self.rowptr.numel() * 4
+        else:
+            b += self.rowptr.numel() * 4 + self.col.numel() * 4
+        if labeled:
+            b += self.x.numel() * 4 + self.eattr.numel() * 4
+        return b
 
 
 def build_csr(batch: GraphBatch) -> CsrBatch:
@@ -313,8 +328,19 @@ def build_csr(batch: GraphBatch) -> CsrBatch:
     col_local = (cols - batch.node_off[gnode[rows]]).to(torch.int32)
     eattr = None if attr is None else torch.cat([attr, attr])[o2].to(torch.int32)
     nnz_g = rowptr[batch.node_off[1:]] - rowptr[batch.node_off[:-1]]
+    max_label = 0
+    if batch.x is not None and eattr is not None and batch.x.numel() and eattr.numel():
+        lo = min(int(batch.x.min()), int(eattr.min()))
+        hi = max(int(batch.x.max()), int(eattr.max()))
+        max_label = hi if lo >= 0 else 0
+    max_nodes = int(n.max()) if G else 1
+    adj64 = None
+    if max_nodes <= 64:
+        # neighbours are unique, so the sum of distinct powers of two is the OR (bit 63 wraps to the sign bit)
+        adj64 = torch.zeros(Ntot, dtype=torch.int64, device=dev)
+        adj64.scatter_add_(0, rows, torch.ones_like(rows) << col_local.to(torch.int64))
     return CsrBatch(batch.node_off, rowptr.to(torch.int32), col_local, eattr, batch.x, batch.query_u, batch.query_v,
-                    int(n.max()) if G else 1, int(nnz_g.max()) if G else 0)
+                    max_nodes, int(nnz_g.max()) if G else 0, max_label, adj64)
 
 
 @dataclass
@@ -343,7 +369,8 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
         out = torch.empty((G, stride), dtype=torch.int64, device=dev)
     lengths = torch.empty(G, dtype=torch.int32, device=dev)
     cc = _lib.CsrBatchC(G, _ptr(csr.node_off), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.eattr), _ptr(csr.x),
-                        _ptr(csr.query_u), _ptr(csr.query_v), max(1, csr.max_nodes), max(0, csr.max_nnz))
+                        _ptr(csr.query_u), _ptr(csr.query_v), max(1, csr.max_nodes), max(0, csr.max_nnz),
+                        max(0, csr.max_label), 0, _ptr(csr.adj64))
     sc = _lib.SentCfgC(cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset, cfg.max_length, int(cfg.labeled),
                        cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query))
     ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))

@@ -111,6 +111,11 @@ typedef struct GtokCsrBatch {
   const int32_t* query_v;    /* [G] or NULL */
   int32_t max_nodes;         /* upper bound on nodes per graph (required, > 0) */
   int32_t max_nnz;           /* upper bound on CSR entries per graph (required, > 0) */
+  int32_t max_label;         /* every x[] and eattr[] value lies in [0, max_label]; 0 = unknown (the
+                                thread-per-graph kernel stages labels as 8/16-bit and needs the bound) */
+  int32_t reserved_;
+  const uint64_t* adj64;     /* [N_total] optional: bit v of adj64[node_off[g]+u] set iff {u,v} is an edge of graph g
+                                (only meaningful when max_nodes <= 64; enables the thread-per-graph SENT kernel) */
 } GtokCsrBatch;
 
 /* SENT configuration: the observable contract of AutoGraph's Graph2TrailTokenizer
