@@ -161,6 +161,85 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(s)}
 
 
+def peak_gbs():
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        return float(json.load(open(pk)).get("hbm_gbs", 6650.0))
+    return 6650.0
+
+
+def run_extras(dev, G, peak):
+    """The other BASELINE configs at the same size (device-resident inputs, CUDA events):
+    configs[0]-shape IBTT graph-token tokenization + collate, configs[2] SENT on graph-token graphs,
+    configs[3]-shape labeled SENT on ZINC-shaped graphs with the fused remap.  Not the headline line."""
+    import torch
+    from gtok import engine, synth
+    from gtok.pipeline import GraphTokenIbttPipeline
+
+    def timeit(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    out = {}
+    gb = synth.er_graph_token(G, seed=0, device=dev)
+    vocab = {t: i for i, t in enumerate(["<pad>", "<bos>", "<e>", "<n>", "<q>", "<p>", "<eos>", "yes", "no"])}
+    for k in range(49):
+        vocab[str(k)] = len(vocab)
+    vocab["has_cycle"] = len(vocab)
+    pipe = GraphTokenIbttPipeline(gb.to("cpu"), vocab, "cycle_check", 600, BATCH, dev)
+    pipe.use_device_batch(gb)
+    timeit(pipe.launch, 2, 3)
+    pipe.timers = []
+    ms = timeit(pipe.launch, 10, 0)
+    kern = {}
+    for n, a, b in pipe.timers:
+        kern.setdefault(n, []).append(a.elapsed_time(b))
+    pipe.timers = None
+    tot, cells = int(pipe.offsets[-1]), int(pipe.xoff[-1])
+    algo = pipe.algorithmic_bytes(tot, cells)
+    out["ibtt_graph_token"] = {
+        "workload": f"{G} ER graph-token graphs, cycle_check, max_len 600, batch {BATCH}: tokenize + collate",
+        "ms_per_step": ms, "graphs_per_s": G / ms * 1e3, "tokens_per_s": tot / ms * 1e3,
+        "kernels": {n: {"ms": sum(v) / len(v), "GBps": algo[n] / (sum(v) / len(v)) / 1e6,
+                        "frac": algo[n] / (sum(v) / len(v)) / 1e6 / peak} for n, v in kern.items()}}
+    del pipe
+
+    def sent(name, batch, cfg, stride, labeled, window):
+        csr = engine.build_csr(batch, balance_window=window)
+        buf = torch.empty((G, stride), dtype=torch.int64, device=dev)
+        step = [0]
+
+        def go():
+            step[0] += 1
+            engine.tokenize_sent(csr, cfg, seed=step[0], out=buf, stride=stride)     # fresh trails every pass
+        ms = timeit(go, 5, 2)
+        _, ln = engine.tokenize_sent(csr, cfg, seed=0, out=buf, stride=stride)
+        tot = int(ln.sum())
+        byt = csr.sent_input_bytes(labeled) + 8 * tot + 4 * G
+        out[name] = {"ms_per_step": ms, "graphs_per_s": G / ms * 1e3, "tokens_per_s": tot / ms * 1e3,
+                     "mean_len": tot / G, "algo_bytes": byt, "GBps": byt / ms / 1e6, "frac": byt / ms / 1e6 / peak}
+        del buf
+
+    sent("sent_graph_token", gb, engine.SentConfig(idx_offset=6, max_length=600), 600, False, 2048)
+    out["sent_graph_token"]["workload"] = f"{G} ER graph-token graphs, unlabeled SENT, max_length 600, Philox-seeded (BASELINE configs[2])"
+    zb = synth.zinc_shaped(G, seed=0, device=dev)
+    nmax = int(zb.num_nodes().max())
+    cfgz = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 9, max_length=384,
+                             labeled=True, remap_zinc=True)
+    sent("sent_zinc", zb, cfgz, 384, True, 0)
+    out["sent_zinc"]["workload"] = (f"{G} ZINC-shaped graphs, labeled SENT + fused remap_zinc_tokens, row capacity 384 "
+                                    "(no row reaches it) (BASELINE configs[3] shape, per-GPU shard)")
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -235,6 +314,9 @@ def run_gpu(args):
     e2e_ms = f0.elapsed_time(f1)
     assert int(res.host_xoff[-1]) == padded_cells and int(res.host_lengths.sum()) == total_tokens
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = run_extras(dev, args.graphs, peak_gbs())
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -288,6 +370,8 @@ def run_gpu(args):
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if extras is not None:
+            line["extras"] = extras
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -302,6 +386,7 @@ def main():
     ap.add_argument("--graphs", type=int, default=1_000_000, help="graphs per GPU")
     ap.add_argument("--cpu-graphs-per-core", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (graph-token IBTT, SENT)")
     ap.add_argument("--zinc-fused", type=int, default=-1, help="-1 auto, 0 three-kernel path, 1 fused single pass")
     args = ap.parse_args()
     if args.impl == "reference":

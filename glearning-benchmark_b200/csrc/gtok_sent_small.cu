@@ -104,16 +104,11 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
 
   for (int64_t g0 = wid0 * 32; g0 < G; g0 += nw * 32) {
     const int Tc = (int)((G - g0 < 32) ? (G - g0) : 32);
-    int64_t my_n0 = 0;
-    int my_N = 0;
-    if (lane < Tc) {
-      my_n0 = __ldg(c.node_off + g0 + lane);
-      my_N = (int)(__ldg(c.node_off + g0 + lane + 1) - my_n0);
-    }
     // ---- one thread walks one graph -----------------------------------------------------------
     if (lane < Tc) {
-      const int64_t g = g0 + lane;
-      const int N = my_N;
+      const int64_t g = c.order ? (int64_t)__ldg(c.order + g0 + lane) : g0 + lane;
+      const int64_t my_n0 = __ldg(c.node_off + g);
+      const int N = (int)(__ldg(c.node_off + g + 1) - my_n0);
       int64_t* __restrict__ row = out + g * stride;
       // pairwise output: rows are 16-byte aligned (even stride, aligned base)
       int pos = 0;

@@ -268,6 +268,7 @@ class CsrBatch:
     max_nnz: int
     max_label: int = 0          # labels lie in [0, max_label]; 0 = unknown
     adj64: Optional[torch.Tensor] = None   # int64[N_total] adjacency bit rows (graphs of <= 64 nodes)
+    order: Optional[torch.Tensor] = None   # int32[G] processing order (graphs sorted by work)
 
     @property
     def num_graphs(self) -> int:
@@ -291,7 +292,7 @@ class CsrBatch:
         return b
 
 
-def build_csr(batch: GraphBatch) -> CsrBatch:
+def build_csr(batch: GraphBatch, balance_window: int = 0) -> CsrBatch:
     """edge_index (any orientation, duplicates allowed) -> canonical undirected CSR.
     One-off ingest per dataset (what to_undirected/coalesce does inside AutoGraph per
     call); plain torch ops - plumbing, not the hot path.  The label of {u,v} is the
@@ -339,8 +340,15 @@ def build_csr(batch: GraphBatch) -> CsrBatch:
         # neighbours are unique, so the sum of distinct powers of two is the OR (bit 63 wraps to the sign bit)
         adj64 = torch.zeros(Ntot, dtype=torch.int64, device=dev)
         adj64.scatter_add_(0, rows, torch.ones_like(rows) << col_local.to(torch.int64))
+    order = None
+    if adj64 is not None and G and balance_window > 1:
+        # one thread walks one graph: give the 32 lanes of a warp graphs of similar work, but only reorder
+        # inside windows of consecutive graphs - a global sort scatters a warp's reads and rows over the whole
+        # buffers and was measured 10-30 % SLOWER than natural order
+        w = torch.arange(G, device=dev) // int(balance_window)
+        order = torch.argsort(w * (1 << 40) + n * 4096 + nnz_g, stable=True).to(torch.int32)
     return CsrBatch(batch.node_off, rowptr.to(torch.int32), col_local, eattr, batch.x, batch.query_u, batch.query_v,
-                    max_nodes, int(nnz_g.max()) if G else 0, max_label, adj64)
+                    max_nodes, int(nnz_g.max()) if G else 0, max_label, adj64, order)
 
 
 @dataclass
@@ -370,7 +378,7 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
     lengths = torch.empty(G, dtype=torch.int32, device=dev)
     cc = _lib.CsrBatchC(G, _ptr(csr.node_off), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.eattr), _ptr(csr.x),
                         _ptr(csr.query_u), _ptr(csr.query_v), max(1, csr.max_nodes), max(0, csr.max_nnz),
-                        max(0, csr.max_label), 0, _ptr(csr.adj64))
+                        max(0, csr.max_label), 0, _ptr(csr.adj64), _ptr(csr.order))
     sc = _lib.SentCfgC(cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset, cfg.max_length, int(cfg.labeled),
                        cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query))
     ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))

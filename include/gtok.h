@@ -116,6 +116,9 @@ typedef struct GtokCsrBatch {
   int32_t reserved_;
   const uint64_t* adj64;     /* [N_total] optional: bit v of adj64[node_off[g]+u] set iff {u,v} is an edge of graph g
                                 (only meaningful when max_nodes <= 64; enables the thread-per-graph SENT kernel) */
+  const int32_t* order;      /* [G] optional processing order (a permutation of 0..G-1, e.g. graphs sorted by
+                                size so the 32 graphs of a warp take similar time); rows are still written
+                                at their own index g */
 } GtokCsrBatch;
 
 /* SENT configuration: the observable contract of AutoGraph's Graph2TrailTokenizer

@@ -28,7 +28,7 @@ def test_version_and_struct_sizes():
     assert ctypes.sizeof(_lib.GraphBatchC) == 80
     assert ctypes.sizeof(_lib.IbttRulesC) == 48
     assert ctypes.sizeof(_lib.ZincVocabC) == 120
-    assert ctypes.sizeof(_lib.CsrBatchC) == 88
+    assert ctypes.sizeof(_lib.CsrBatchC) == 96
     assert ctypes.sizeof(_lib.SentCfgC) == 32
     assert ctypes.sizeof(_lib.ChoiceC) == 32
 

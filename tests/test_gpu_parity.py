@@ -355,3 +355,42 @@ def test_sent_sharding_invariance(dev):
         assert torch.equal(l, fl[r * 1024:(r + 1) * 1024])
         m = torch.arange(t.shape[1], device=dev)[None, :] < l[:, None]
         assert torch.equal(t[m], full[r * 1024:(r + 1) * 1024][m])
+
+
+# --------------------------------------------------------------------------- large graphs (BASELINE config 5)
+@pytest.mark.parametrize("N", [64, 65, 512, 4096])
+def test_large_graph_sweep_ibtt_sent_collate(dev, N):
+    """64..4096-node graphs, mean degree ~8, untruncated: IBTT rows, SENT rows (general warp-per-graph
+    kernel beyond 64 nodes) and the padded batch, all against the oracle."""
+    from gtok import engine, synth
+    G = 6 if N >= 512 else 24
+    gb = synth.er_sparse(G, N, mean_degree=8.0, seed=N)
+    vocab = {t: i for i, t in enumerate(O.SPECIAL)}
+    for k in range(N):
+        vocab[str((k * 7919) % N)] = len(vocab)            # scrambled, data-dependent ids
+    vocab["has_cycle"] = len(vocab)
+    E = int(gb.num_entries().max())
+    max_len = 3 * E + N + 5
+    rag = engine.tokenize_ibtt(gb.to(dev), vocab, "cycle_check", max_len)
+    rows = rag.rows_cpu()
+    seqs = []
+    for g in range(G):
+        n, s, d, _, _ = gb.graph(g)
+        want = O.ibtt_ids(n, s.numpy(), d.numpy(), "cycle_check", vocab, max_len)
+        assert rows[g].tolist() == want.tolist()
+        seqs.append(want)
+    X, A = engine.pad_mask(rag.tokens, rag.offsets, rag.lengths, 0)
+    Xw, Aw, _ = O.collate(seqs, [0] * G, 0)
+    assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+    # SENT, untruncated (bound: 2 + nodes + resets + members + brackets)
+    bound = 2 + 4 * N + E + 8
+    cfg = engine.SentConfig(idx_offset=6, max_length=bound)
+    csr = engine.build_csr(gb.to(dev))
+    tok, ln = engine.tokenize_sent(csr, cfg, seed=N)
+    tok, ln = tok.cpu(), ln.cpu().tolist()
+    ocfg = S.SentConfig(idx_offset=6, max_length=bound)
+    for g in range(G if N < 4096 else 2):
+        n, s, d, _, _ = gb.graph(g)
+        rp, col, _ = S.canonical_csr(n, s.tolist(), d.tolist())
+        want = S.sent_tokenize(n, rp, col, ocfg, S.PhiloxWords(N, g))
+        assert tok[g, :ln[g]].tolist() == want.tolist(), (N, g)

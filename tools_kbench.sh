@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick GPU iteration helper: parity tests for one family + per-kernel timings from bench.py
 python -m pytest tests -m gpu -q -x -k "${1:-zinc}" 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline ${2:-} > /tmp/b.json 2>/tmp/b.err || tail -5 /tmp/b.err
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras ${2:-} > /tmp/b.json 2>/tmp/b.err || tail -5 /tmp/b.err
 python - <<PY
 import json
 d=json.load(open("/tmp/b.json"))

@@ -9,6 +9,7 @@ from gtok.pipeline import GraphTokenIbttPipeline
 
 dev = torch.device("cuda:0")
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+BW = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 PEAK = 6444.4
 
 def timeit(fn, steps=10, warm=3):
@@ -41,7 +42,7 @@ for n, v in k.items():
 pipe.timers = None
 
 # ---- K3 unlabeled (config 3)
-csr = engine.build_csr(gb)
+csr = engine.build_csr(gb, balance_window=BW)
 cfg = engine.SentConfig(idx_offset=6, max_length=600)
 out = torch.empty((G, 600), dtype=torch.int64, device=dev)
 ms = timeit(lambda: engine.tokenize_sent(csr, cfg, seed=0, out=out, stride=600), steps=5, warm=2)
@@ -52,7 +53,7 @@ print(f"K3 sent ER unlabeled G={G} tokens={tot} avgL={tot/G:.1f} ms={ms:.3f} gra
 del out
 # ---- K3 labeled zinc (config 4 shape, 1M per GPU)
 zb = synth.zinc_shaped(G, seed=0, device=dev)
-zc = engine.build_csr(zb)
+zc = engine.build_csr(zb, balance_window=BW)
 cfgz = engine.SentConfig(idx_offset=6, node_idx_offset=6 + 37, edge_idx_offset=6 + 37 + 9, max_length=1024, labeled=True, remap_zinc=True)
 stride = 2 + 3 * 37 + 4 * 45 + 40
 stride = 384
