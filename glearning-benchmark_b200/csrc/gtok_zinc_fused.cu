@@ -25,6 +25,8 @@
 //     the next molecule's loads are issued before the current one is processed.
 // HBM traffic = algorithmic minimum: 12*Ed + 4N + 16 read, 8L + 12 written per molecule.
 // Molecules only (max_nodes <= 64, <= 256 columns); other shapes use gtok_zinc.cu.
+#include <stdlib.h>
+
 #include "gtok_common.cuh"
 
 namespace gtok {
@@ -352,10 +354,14 @@ static int zinc_fused_launch(const GtokGraphBatch* batch, const GtokZincVocab* v
   return GTOK_OK;
 }
 
+// gtok_zinc_tpm.cu
+int zinc_tpm_ragged(const GtokGraphBatch* batch, const GtokZincVocab* vocab, int32_t* len_out, int64_t* off_out,
+                    int64_t* tok_out, int64_t tok_capacity, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled);
+
 }  // namespace gtok
 
 extern "C" size_t gtok_zinc_tokenize_workspace_bytes(int64_t num_graphs) {
-  const int64_t tiles = (num_graphs + gtok::kFTile - 1) / gtok::kFTile;
+  const int64_t tiles = (num_graphs + 31) / 32;           // smallest tile any ZINC kernel uses
   return 16 + (size_t)(tiles > 0 ? tiles : 1) * 8;
 }
 
@@ -386,6 +392,15 @@ extern "C" int gtok_zinc_tokenize(const GtokGraphBatch* batch, const GtokZincVoc
                GTOK_EINVAL, "zinc_tokenize: tok_out and workspace must be 16-byte aligned");
   const size_t need = gtok_zinc_tokenize_workspace_bytes(batch->num_graphs);
   GTOK_REQUIRE(ws_bytes >= need, GTOK_EWORKSPACE, "zinc_tokenize: workspace %zu < %zu bytes", ws_bytes, need);
+  {
+    // v6 thread-per-molecule kernel first; GTOK_ZINC_IMPL=warp keeps the warp-per-molecule kernel (A/B runs)
+    static const bool force_warp = [] { const char* e = getenv("GTOK_ZINC_IMPL"); return e && e[0] == 'w'; }();
+    if (!force_warp) {
+      bool handled = false;
+      const int rc = zinc_tpm_ragged(batch, vocab, len_out, off_out, tok_out, tok_capacity, ws, ws_bytes, st, &handled);
+      if (rc != GTOK_OK || handled) return rc;
+    }
+  }
   if (vocab->max_token_id > 0 && vocab->max_token_id < 65536)
     return zinc_fused_launch<uint16_t>(batch, vocab, len_out, off_out, tok_out, tok_capacity, ws, need, st);
   return zinc_fused_launch<int32_t>(batch, vocab, len_out, off_out, tok_out, tok_capacity, ws, need, st);

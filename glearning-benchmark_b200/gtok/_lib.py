@@ -72,6 +72,9 @@ PROTOTYPES = {
     "gtok_zinc_serialize": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(ZincVocabC), vp, vp, vp]),
     "gtok_zinc_tokenize_workspace_bytes": (C.c_size_t, [i64]),
     "gtok_zinc_tokenize": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(ZincVocabC), vp, vp, vp, i64, vp, C.c_size_t, vp]),
+    "gtok_zinc_collate_workspace_bytes": (C.c_size_t, [i64, i64]),
+    "gtok_zinc_collate": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(ZincVocabC), i64, i64, vp, vp, vp, vp, vp, i64,
+                                    vp, C.c_size_t, vp]),
     "gtok_sent_tokenize": (C.c_int, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), C.POINTER(ChoiceC), vp, vp, i64, vp]),
     "gtok_pad_mask": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp]),
     "gtok_batch_extents": (C.c_int, [vp, vp, i64, i64, vp, vp, vp]),

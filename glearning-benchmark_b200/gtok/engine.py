@@ -251,6 +251,38 @@ def pad_mask_epoch(tokens: torch.Tensor, row_start: torch.Tensor, row_len: torch
     return PaddedEpoch(X, attn, xoff, lmax, B, G)
 
 
+def zinc_collate_epoch(batch: GraphBatch, vocab: Dict[str, int], max_len: int, batch_size: int,
+                       item_max_len: Optional[int] = None, max_nodes: Optional[int] = None,
+                       max_entries: Optional[int] = None, X: Optional[torch.Tensor] = None,
+                       attn: Optional[torch.Tensor] = None):
+    """K2+K4 in one pass: molecules -> every padded batch of the epoch (tokenize_molecule + TokenDataset +
+    collate, zinc_dataset_indexbase.py:143-227, data_loader.py:465-497); the ragged stream never exists.
+    -> (PaddedEpoch, lengths int32[G]).  batch_size: multiple of 32 in [32, 256]."""
+    _require_cuda(batch.src)
+    if batch.x is None:
+        raise ValueError("ZINC tokenization needs batch.x (atom types)")
+    dev = batch.device
+    G, B = batch.num_graphs, int(batch_size)
+    nb = (G + B - 1) // B
+    bc = _batch_c(batch, max_nodes, max_entries)
+    zv, tbl = zinc_vocab_c(vocab, max_len if item_max_len is None else item_max_len, max_len, bc.max_nodes, dev)
+    lengths = torch.empty(G, dtype=torch.int32, device=dev)
+    lmax = torch.empty(nb, dtype=torch.int32, device=dev)
+    xoff = torch.zeros(nb + 1, dtype=torch.int64, device=dev)
+    if X is None or attn is None:
+        cap = G * min(max_len, 2 * bc.max_nodes + 4 * bc.max_entries + 4) + 2
+        X = torch.empty(cap, dtype=torch.int64, device=dev)
+        attn = torch.empty(cap, dtype=torch.bool, device=dev)
+    nbytes = lib.gtok_zinc_collate_workspace_bytes(G, B)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.gtok_zinc_collate(C.byref(bc), C.byref(zv), B, int(vocab["<pad>"]), _ptr(lengths), _ptr(lmax), _ptr(xoff),
+                                _ptr(X), _ptr(attn), min(X.numel(), attn.numel()), _ptr(ws), nbytes, _stream()))
+    total = int(xoff[-1]) if G else 0
+    if total > min(X.numel(), attn.numel()):
+        raise ValueError("padded output buffers too small")
+    return PaddedEpoch(X[:total], attn[:total], xoff, lmax, B, G), lengths
+
+
 # ---------------------------------------------------------------------------
 # K3: SENT  (AutoGraph Graph2TrailTokenizer + train_agtt.py:171-273)
 # ---------------------------------------------------------------------------

@@ -175,8 +175,9 @@ GTOK_API int gtok_zinc_serialize(const GtokGraphBatch* batch, const GtokZincVoca
                         const int64_t* off, int64_t* tok_out, void* stream);
 
 /* K2 fused  the same two reference functions in ONE pass over HBM: lengths, ragged
- *      offsets (int64[G+1]) and rows are produced together (tiles of 32 molecules
- *      staged in shared memory, decoupled look-back for the offsets).  Molecule
+ *      offsets (int64[G+1]) and rows are produced together (CTA tiles of molecules
+ *      staged in shared memory, one thread per molecule for the first-seen dedupe,
+ *      decoupled look-back for the offsets).  Molecule
  *      shapes only: batch.max_nodes <= 64 and batch.max_entries <= 256, otherwise
  *      GTOK_EUNSUPPORTED (use the three calls above).  Rows that would end beyond
  *      tok_capacity are not written (lengths/offsets still are), so the caller can
@@ -185,6 +186,20 @@ GTOK_API size_t gtok_zinc_tokenize_workspace_bytes(int64_t num_graphs);
 GTOK_API int gtok_zinc_tokenize(const GtokGraphBatch* batch, const GtokZincVocab* vocab, int32_t* len_out,
                                 int64_t* off_out, int64_t* tok_out, int64_t tok_capacity,
                                 void* ws, size_t ws_bytes, void* stream);
+
+/* K2+K4 fused  tokenize_molecule + TokenDataset + collate in ONE pass (zinc_dataset_indexbase.py:143-227,
+ *      data_loader.py:465-497): molecules -> padded batches; the ragged token stream never exists in HBM.
+ *      Batch k = molecules [k*B, min(G,(k+1)*B)) in batch order, padded to ITS OWN Lmax_k with pad_id,
+ *      written row-major [rows_k, Lmax_k] at X + xoff[k] / attn + xoff[k] - the layout
+ *      gtok_pad_mask_batched produces.  Outputs: len_out int32[G], lmax_out int32[nb], xoff_out int64[nb+1],
+ *      X int64 / attn uint8 (torch.bool storage) with x_capacity cells each; a batch that would end beyond
+ *      x_capacity is not written (its extents still are), so the caller can size X from the bound
+ *      G * min(max_len, 2*max_nodes + 4*max_entries + 4) and check xoff_out[nb] afterwards.
+ *      B must be a multiple of 32 in [32, 256]; molecule shapes as for gtok_zinc_tokenize. */
+GTOK_API size_t gtok_zinc_collate_workspace_bytes(int64_t num_graphs, int64_t batch_size);
+GTOK_API int gtok_zinc_collate(const GtokGraphBatch* batch, const GtokZincVocab* vocab, int64_t batch_size,
+                               int64_t pad_id, int32_t* len_out, int32_t* lmax_out, int64_t* xoff_out, int64_t* X,
+                               uint8_t* attn, int64_t x_capacity, void* ws, size_t ws_bytes, void* stream);
 
 /* K3   Graph2TrailTokenizer.__call__ (external AutoGraph; spec in
  *      oracle/sent_oracle.py) + remap_zinc_tokens + query append

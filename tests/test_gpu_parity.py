@@ -191,6 +191,50 @@ def test_zinc_adversarial_vs_oracle(dev):
                 assert got.tolist() == want.tolist()
 
 
+@pytest.mark.parametrize("B", [32, 128, 256])
+def test_zinc_fused_collate_vs_oracle(dev, golden_zinc, B):
+    """molecules -> padded batches in one kernel == oracle tokenize + oracle collate, batch by batch;
+    golden molecules (every truncation case) and adversarial shapes, 16-bit and 32-bit staging."""
+    from gtok import engine
+    rng = np.random.default_rng(11)
+    sets = [(golden_zinc["mols"], golden_zinc["L1024"]["vocab"])]
+    vocab = O.zinc_extend_vocab(O.zinc_fixed_vocab(), [str(k) for k in rng.permutation(40)] + ["X"])
+    mols = []
+    for i in range(700):
+        n = int(rng.integers(1, 46))
+        m = int(rng.integers(0, 120)) if i % 9 else 0
+        mols.append({"n": n, "src": rng.integers(0, n, m).tolist(), "dst": rng.integers(0, n, m).tolist(),
+                     "x": rng.integers(-1, 12, n).tolist(), "attr": rng.integers(0, 7, m).tolist()})
+    sets.append((mols, vocab))
+    sets.append((mols[:333], {t: (i if i < 22 else i + 70000) for t, i in vocab.items()}))
+    for ms, voc in sets:
+        gb = _zinc_batch(ms, dev)
+        for max_len in (1024, 121, 64):
+            ep, lens = engine.zinc_collate_epoch(gb, voc, max_len, B)
+            want = [O.zinc_ids(m["x"], m["src"], m["dst"], m["attr"], voc, max_len, max_len) for m in ms]
+            assert lens.cpu().tolist() == [len(w) for w in want]
+            assert ep.num_batches == (len(ms) + B - 1) // B
+            for k in range(ep.num_batches):
+                Xw, Aw, _ = O.collate(want[k * B:(k + 1) * B], [0] * len(want[k * B:(k + 1) * B]), voc["<pad>"])
+                X, A = ep.batch(k)
+                assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw), (max_len, k)
+
+
+def test_zinc_fused_collate_equals_two_step_large(dev):
+    """200k ZINC-shaped molecules: the fused kernel's X/attn/extents are byte-identical to
+    gtok_zinc_tokenize followed by gtok_pad_mask_batched."""
+    from gtok import engine, synth
+    G = 200_000
+    gb = synth.zinc_shaped(G, seed=3, device=dev)
+    vocab = O.zinc_extend_vocab(O.zinc_fixed_vocab(), [str(k) for k in range(37)] + ["X", "unknown"])
+    rag = engine.tokenize_zinc(gb, vocab, 1024)
+    ep2 = engine.pad_mask_epoch(rag.tokens, rag.offsets, rag.lengths, vocab["<pad>"], 128)
+    ep1, lens = engine.zinc_collate_epoch(gb, vocab, 1024, 128)
+    assert torch.equal(lens, rag.lengths) and torch.equal(ep1.xoff, ep2.xoff) and torch.equal(ep1.lmax, ep2.lmax)
+    tot = int(ep2.xoff[-1])
+    assert torch.equal(ep1.X[:tot], ep2.X[:tot]) and torch.equal(ep1.attn[:tot], ep2.attn[:tot])
+
+
 def test_zinc_properties_large(dev):
     """1M ZINC-shaped molecules (BASELINE config 2 size): closed-form lengths, checksum of a
     strided sample against the oracle, structural invariants on every row start."""

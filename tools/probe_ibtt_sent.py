@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """GPU probe: throughput of K1 (graph-token IBTT) and K3 (SENT) on 1M-graph workloads."""
 import sys, os, json, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "glearning-benchmark_b200")]
 import torch
 from gtok import engine, synth

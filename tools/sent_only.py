@@ -1,5 +1,5 @@
 import sys, os
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "glearning-benchmark_b200")]
 import torch
 from gtok import engine, synth
