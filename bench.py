@@ -270,7 +270,8 @@ def run_gpu(args):
     vocab = zinc_vocab()
     dev_batch = synth.zinc_shaped(G, seed=rank, device=dev)           # rank r owns graphs [r*G, (r+1)*G)
     host_batch = dev_batch.to("cpu").pin_memory()
-    pipe = ZincIbttPipeline(host_batch, vocab, MAX_LEN, BATCH, dev, fused=None if args.zinc_fused < 0 else bool(args.zinc_fused))
+    pipe = ZincIbttPipeline(host_batch, vocab, MAX_LEN, BATCH, dev, fused=None if args.zinc_fused < 0 else bool(args.zinc_fused),
+                            mode=args.zinc_mode)
     pipe.use_device_batch(dev_batch)
 
     def barrier():
@@ -297,8 +298,26 @@ def run_gpu(args):
     for name, a, b in pipe.timers:
         kern.setdefault(name, []).append(a.elapsed_time(b))
     pipe.timers = None
-    total_tokens = int(pipe.offsets[-1])
+    total_tokens = int(pipe.lengths.sum())
     padded_cells = int(pipe.xoff[-1])
+
+    # ---- the same step as separate kernels (ragged ids kept, then K4 collate): per-kernel rooflines only
+    alt_kern = {}
+    if pipe.mode == "collate" and rank == 0:
+        alt = ZincIbttPipeline(host_batch, vocab, MAX_LEN, BATCH, dev, mode="ragged")
+        alt.use_device_batch(dev_batch)
+        for _ in range(3):
+            alt.launch()
+        torch.cuda.synchronize()
+        alt.timers = []
+        for _ in range(max(3, min(args.steps, 10))):
+            alt.launch()
+        torch.cuda.synchronize()
+        for name, a, b in alt.timers:
+            alt_kern.setdefault(name, []).append(a.elapsed_time(b))
+        assert int(alt.offsets[-1]) == total_tokens and int(alt.xoff[-1]) == padded_cells
+        assert torch.equal(alt.X[:padded_cells], pipe.X[:padded_cells]) and torch.equal(alt.attn[:padded_cells], pipe.attn[:padded_cells])
+        del alt
 
     # ---- end to end through the public call: pinned host graphs -> device batches + host metadata
     e2e_steps = max(3, min(args.steps, 10))
@@ -342,6 +361,15 @@ def run_gpu(args):
             kernels[name] = {"ms": avg, "algo_bytes": algo[name], "GBps": algo[name] / avg / 1e6,
                              "frac": algo[name] / avg / 1e6 / peak}
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        two_step = {}
+        for name, v in alt_kern.items():
+            avg = sum(v) / len(v)
+            two_step[name] = {"ms": avg, "algo_bytes": algo[name], "GBps": algo[name] / avg / 1e6,
+                              "frac": algo[name] / avg / 1e6 / peak}
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tj) and G == 1_000_000:
+            traffic = json.load(open(tj)).get(dom, {}).get("dram_bytes_per_launch")
         step_algo = algo["zinc_serialize"] + 9 * padded_cells - 8 * total_tokens     # SURVEY 8d "fused" figure for the whole step
         step_s = ms / 1e3 / args.steps
         line = {
@@ -350,7 +378,9 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "tokens_per_s": tokens_all / step_s,
             "config": {"workload": f"ibtt_zinc: {G} ZINC-shaped graphs per GPU (BASELINE configs[1]), max_len {MAX_LEN}, "
-                                   f"batch {BATCH}; tokenize (ragged int64) + pad/mask collate of every batch",
+                                   f"batch {BATCH}; tokenize + pad/mask collate of every batch" +
+                                   (" in ONE kernel (molecules -> X/attn; output byte-identical to the two-step path, "
+                                    "checked in this run)" if pipe.mode == "collate" else " (ragged int64 ids, then collate)"),
                        "graphs_per_gpu": G, "tokens_per_gpu": total_tokens, "padded_cells_per_gpu": padded_cells,
                        "l2": "inputs+outputs per step (~%.1f GB) far exceed the 126 MB L2; no flush needed" %
                              ((pipe.h2d_bytes() + 8 * total_tokens + 9 * padded_cells) / 1e9),
@@ -361,9 +391,10 @@ def run_gpu(args):
                     "note": "pinned host graph arrays copied H2D every step; row lengths + batch extents read back"},
             "gpu_launches": pipe.kernel_launches_per_pass * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                         "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                          "algo_bytes_per_launch": kernels[dom]["algo_bytes"]},
             "kernels": kernels,
+            "kernels_two_step": two_step,
             "step_roofline": {"algo_bytes": step_algo, "GBps": step_algo / step_s / 1e9, "frac": step_algo / step_s / 1e9 / peak,
                               "note": "fused-minimum bytes (graph reads + 9*B*Lmax writes) / whole-step time"},
             "clocks": sampler.summary(),
@@ -388,6 +419,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (graph-token IBTT, SENT)")
     ap.add_argument("--zinc-fused", type=int, default=-1, help="-1 auto, 0 three-kernel path, 1 fused single pass")
+    ap.add_argument("--zinc-mode", default="auto", choices=["auto", "collate", "ragged"],
+                    help="collate: molecules -> padded batches in one kernel; ragged: tokenizer + K4 collate kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -168,7 +168,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
         const int4* __restrict__ d4 = reinterpret_cast<const int4*>(g_dst);
         const int4* __restrict__ a4 = reinterpret_cast<const int4*>(g_attr);
         uint2* c2 = reinterpret_cast<uint2*>(s_col);
-#pragma unroll 2
+#pragma unroll 4
         for (long long j = j0 + lane; j < j1v; j += 32) {
           const int4 A = __ldcs(s4 + j);
           const int4 Cc = __ldcs(d4 + j);
@@ -356,7 +356,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
       if (two) fix_eos(j + 1, rb1);
       __syncwarp();
       if (base < 0) {
-        while (s_ready[par] != (unsigned)tile + 1u) __nanosleep(32);
+        while (s_ready[par] != (unsigned)tile + 1u) __nanosleep(128);
         __threadfence_block();
         base = s_base[par];
       }
@@ -366,7 +366,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
     }
     if (nv > 0) {
       if (base < 0) {
-        while (s_ready[par] != (unsigned)tile + 1u) __nanosleep(32);
+        while (s_ready[par] != (unsigned)tile + 1u) __nanosleep(128);
         __threadfence_block();
         base = s_base[par];
       }

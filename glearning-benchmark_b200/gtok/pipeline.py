@@ -131,7 +131,12 @@ class ZincIbttPipeline(_PipelineBase):
     """BASELINE config 2: IBTT tokenization of ZINC-shaped molecules + collate."""
 
     def __init__(self, host_batch: GraphBatch, vocab: Dict[str, int], max_len: int, batch_size: int, device,
-                 fused: Optional[bool] = None):
+                 fused: Optional[bool] = None, mode: str = "auto"):
+        """mode: "collate"  one kernel, molecules -> padded batches (gtok_zinc_collate; the ragged stream is
+                            never materialised), the default when the shapes allow it;
+                 "ragged"   gtok_zinc_tokenize (ragged ids, kept for TokenDataset.seqs) + the K4 collate kernels;
+                 "auto"     "collate" if batch_size is a multiple of 32 <= 256 and molecules are <= 64 atoms /
+                            <= 256 columns, else "ragged".  `fused=False` forces the three-kernel tokenizer."""
         G = host_batch.num_graphs
         n = host_batch.num_nodes()
         e = host_batch.num_entries()
@@ -144,10 +149,18 @@ class ZincIbttPipeline(_PipelineBase):
         self.vocab = vocab
         self.pad_id = int(vocab["<pad>"])
         self.zv, self._tbl = engine.zinc_vocab_c(vocab, max_len, max_len, self.max_nodes, self.device)
-        self.fused = (self.max_nodes <= 64 and self.max_entries <= 256) if fused is None else bool(fused)
+        small = self.max_nodes <= 64 and self.max_entries <= 256
+        self.fused = small if fused is None else bool(fused)
+        can_collate = small and self.fused and batch_size % 32 == 0 and 32 <= batch_size <= 256
+        if mode == "auto":
+            mode = "collate" if can_collate else "ragged"
+        if mode == "collate" and not can_collate:
+            raise ValueError("fused tokenize+collate needs molecule shapes and a batch size that is a multiple of 32 <= 256")
+        self.mode = mode
         if self.fused:
-            self.kernel_launches_per_pass = 4
-            self.ws_bytes = max(self.ws_bytes, lib.gtok_zinc_tokenize_workspace_bytes(G))
+            self.kernel_launches_per_pass = 1 if mode == "collate" else 4
+            self.ws_bytes = max(self.ws_bytes, lib.gtok_zinc_tokenize_workspace_bytes(G),
+                                lib.gtok_zinc_collate_workspace_bytes(G, batch_size))
             self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
 
     def _batch_c(self):
@@ -160,6 +173,11 @@ class ZincIbttPipeline(_PipelineBase):
         """The hot path on whatever dev_in points at: 4 kernels (fused tokenizer) or 6, no sync."""
         bc = self._batch_c()
         st = _stream()
+        if self.mode == "collate":
+            self._timed("zinc_collate", lambda: check(lib.gtok_zinc_collate(
+                C.byref(bc), C.byref(self.zv), self.B, self.pad_id, _ptr(self.lengths), _ptr(self.lmax), _ptr(self.xoff),
+                _ptr(self.X), _ptr(self.attn), min(self.X.numel(), self.attn.numel()), _ptr(self.ws), self.ws_bytes, st)))
+            return
         if self.fused:
             self._timed("zinc_tokenize", lambda: check(lib.gtok_zinc_tokenize(
                 C.byref(bc), C.byref(self.zv), _ptr(self.lengths), _ptr(self.offsets), _ptr(self.tokens),
@@ -186,6 +204,7 @@ class ZincIbttPipeline(_PipelineBase):
         n_total = self.dev_in["x"].numel()
         e_total = self.dev_in["src"].numel()
         return {
+            "zinc_collate": 12 * e_total + 4 * n_total + 16 * G + 9 * padded_cells + 4 * G,
             "zinc_tokenize": 12 * e_total + 4 * n_total + 16 * G + 8 * total_tokens,
             "zinc_lengths": 8 * e_total + 16 * G + 4 * G,
             "scan_rows": 4 * G + 8 * (G + 1),

@@ -6,6 +6,6 @@ python - <<PY
 import json
 d=json.load(open("/tmp/b.json"))
 print("value",round(d["value"]/1e6,1),"Mgraphs/s  ms/step",round(d["ms_per_step"],4),"e2e",round(d["e2e"]["value"]/1e6,1))
-for k,v in d["kernels"].items(): print(f"  {k:18s} {v['ms']:.4f} ms  {v['GBps']:7.0f} GB/s  frac {v['frac']:.3f}")
+for k,v in list(d["kernels"].items())+list(d.get("kernels_two_step",{}).items()): print(f"  {k:18s} {v['ms']:.4f} ms  {v['GBps']:7.0f} GB/s  frac {v['frac']:.3f}")
 print("  step_roofline", round(d["step_roofline"]["frac"],3), d["clocks"])
 PY

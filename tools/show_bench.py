@@ -1,0 +1,16 @@
+#!/usr/bin/env python
+"""Pretty-print a bench.py JSON line: python tools/show_bench.py gpurun_out/bench_X.json"""
+import json
+import sys
+d = json.load(open(sys.argv[1]))
+print("value", round(d["value"] / 1e6, 1), "Mgraphs/s  ms/step", round(d["ms_per_step"], 4), " e2e", round(d["e2e"]["value"] / 1e6, 1),
+      "Mgraphs/s  launches", d["gpu_launches"])
+for k, v in list(d["kernels"].items()) + list(d.get("kernels_two_step", {}).items()):
+    print(f"  {k:18s} {v['ms']:.4f} ms  {v['GBps']:7.0f} GB/s  frac {v['frac']:.3f}")
+print("  roofline", d["roofline"])
+print("  step_roofline", round(d["step_roofline"]["frac"], 3), d["clocks"])
+print("  cpu_baseline", d.get("cpu_baseline"))
+for k, v in (d.get("extras") or {}).items():
+    print(f"  extra {k}: {v.get('ms_per_step'):.3f} ms/step  {v.get('graphs_per_s', 0) / 1e6:.0f} Mgraphs/s  frac {v.get('frac')}")
+    for kk, vv in (v.get("kernels") or {}).items():
+        print(f"      {kk:18s} {vv['ms']:.4f} ms  {vv['GBps']:7.0f} GB/s  frac {vv['frac']:.3f}")
