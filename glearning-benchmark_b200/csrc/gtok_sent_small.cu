@@ -30,7 +30,7 @@ constexpr int kSmallThreads = 128;
 constexpr int kSmallWarps = kSmallThreads / 32;
 
 __device__ __forceinline__ void philox10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
-                                         unsigned k1, unsigned (&o)[4]) {
+                                         unsigned k1, unsigned& o0, unsigned& o1, unsigned& o2, unsigned& o3) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -38,7 +38,7 @@ __device__ __forceinline__ void philox10(unsigned c0, unsigned c1, unsigned c2, 
     c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+  o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
 // trainer/train_agtt.py:193-242 (branch order preserved; oracle: remap_zinc_token)
@@ -69,22 +69,43 @@ __device__ __forceinline__ int select64(unsigned long long m, int k) {
 }
 
 struct SmallLayout {
-  int o_vis, o_ord;   // byte offsets inside a warp slice
+  int o_vis, o_ord, o_ring;   // byte offsets inside a warp slice
   int warp_bytes;
 };
 
+constexpr int kRing = 64;      // ring slots per lane (tokens leave 16 at a time = four full 32-byte sectors)
+
 }  // namespace
 
-static SmallLayout small_layout(int nmax, bool labeled) {
+static SmallLayout small_layout(int nmax, bool labeled, int ring_elem) {
   SmallLayout L;
   int o = 0;
-  L.o_vis = o; o += 32 * nmax;                 // u8 [v][lane]  node -> visit index
-  L.o_ord = o; o += labeled ? 32 * nmax : 0;   // u8 [k][lane]  visit index -> node
+  L.o_vis = o; o += 32 * nmax;                 // u8  [v][lane]  node -> visit index
+  L.o_ord = o; o += labeled ? 32 * nmax : 0;   // u8  [k][lane]  visit index -> node
+  o = (o + 15) & ~15;
+  L.o_ring = o; o += kRing * 32 * ring_elem;   // [slot][lane] pending tokens (16-bit when every token fits)
   L.warp_bytes = (o + 15) & ~15;
   return L;
 }
 
-template <bool LABELED>
+// One lockstep loop per warp (lane j <-> graph j); every iteration is one EVENT (arrival at a node) and
+// takes exactly one pick, so the Philox block refresh falls on the same iteration for all lanes.  All 32
+// lanes stay in the loop until the slowest graph is done, which gives two warp-synchronous service points
+// per iteration.  History (profiles/r1g..r1n): the first thread-per-graph version ran 1900 warp instructions
+// per graph at 7 of 32 lanes active; what changed:
+//   * emit() is a shared-memory store into a per-lane ring ([slot][lane], conflict free) at each of its ten
+//     call sites instead of a bounds check + remap + parity branch + global store;
+//   * flush point: when ANY lane has 32 tokens pending, EVERY lane with 16 or more stores 16 (eight 16-byte
+//     stores = four full sectors) - the flush code runs a handful of times per 32 graphs with most lanes
+//     active (lane-by-lane flushing was 31 % of all instructions);
+//   * restart service: a stuck lane needs the visited nodes that still have an unvisited neighbour, i.e. the
+//     neighbours of its FRONTIER (unvisited nodes adjacent to the visited set, kept incrementally as
+//     reach & ~visited).  The warp serves each stuck lane together: lane i loads adjacency rows i and i+32 of
+//     that graph if they are in the frontier, two REDUX.OR give the union - no dependent load chain
+//     (the per-lane scan was 13 % of all stall samples);
+//   * one select64 site (the pick among unvisited neighbours and the restart pick share it); a bracket with
+//     one member (the common case) skips the visit-index ordering.
+template <bool LABELED, typename RingT>
 __global__ void __launch_bounds__(kSmallThreads)
 sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch, const SmallLayout lay,
                   int32_t* __restrict__ len_out, int64_t* __restrict__ out, int64_t stride) {
@@ -92,8 +113,9 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
   const int lane = lane_id();
   const int w = threadIdx.x >> 5;
   unsigned char* base = s_smem + (size_t)w * lay.warp_bytes;
-  unsigned char* vis = base + lay.o_vis;
-  unsigned char* ord = base + lay.o_ord;
+  unsigned char* vis = base + lay.o_vis + lane;
+  unsigned char* ord = base + lay.o_ord + lane;
+  RingT* ring = reinterpret_cast<RingT*>(base + lay.o_ring) + lane;
   const unsigned long long* __restrict__ adj64 = reinterpret_cast<const unsigned long long*>(c.adj64);
 
   const int64_t G = c.num_graphs;
@@ -101,121 +123,163 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int Lcap = cfg.max_length;
   const unsigned k0 = (unsigned)(ch.seed & 0xffffffffu), k1 = (unsigned)(ch.seed >> 32);
+  const bool remap = cfg.remap_zinc != 0;
+  const int idx_off = cfg.idx_offset, node_off = cfg.node_idx_offset, edge_off = cfg.edge_idx_offset;
 
   for (int64_t g0 = wid0 * 32; g0 < G; g0 += nw * 32) {
     const int Tc = (int)((G - g0 < 32) ? (G - g0) : 32);
-    // ---- one thread walks one graph -----------------------------------------------------------
-    if (lane < Tc) {
-      const int64_t g = c.order ? (int64_t)__ldg(c.order + g0 + lane) : g0 + lane;
-      const int64_t my_n0 = __ldg(c.node_off + g);
-      const int N = (int)(__ldg(c.node_off + g + 1) - my_n0);
-      int64_t* __restrict__ row = out + g * stride;
-      // pairwise output: rows are 16-byte aligned (even stride, aligned base)
-      int pos = 0;
-      long long held = 0;
-      auto emit = [&](int t) {
-        if (pos < Lcap) {
-          const long long v = cfg.remap_zinc ? remap_zinc_tok(t, cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset) : t;
-          if (pos & 1) st_stream_i64x2(row + pos - 1, held, v);
-          else held = v;
-        }
-        ++pos;
-      };
-      // random words
-      const uint64_t gid = (uint64_t)(ch.graph_id_base + g);
-      unsigned blk[4] = {0, 0, 0, 0};
-      unsigned d = 0;
-      int64_t s_off = 0;
-      unsigned s_len = 0;
-      if (ch.stream) {
-        s_off = __ldg(ch.stream_off + g);
-        s_len = (unsigned)(__ldg(ch.stream_off + g + 1) - s_off);
-      }
-      auto pick = [&](int cnt) -> int {
-        unsigned r;
-        if (ch.stream) {
-          r = d < s_len ? __ldg(ch.stream + s_off + d) : 0u;
-        } else {
-          if ((d & 3u) == 0u) philox10((unsigned)gid, (unsigned)(gid >> 32), d >> 2, 0u, k0, k1, blk);
-          const unsigned w01 = (d & 1u) ? blk[1] : blk[0], w23 = (d & 1u) ? blk[3] : blk[2];
-          r = (d & 2u) ? w23 : w01;
-        }
-        ++d;
-        return (int)__umulhi(r, (unsigned)cnt);
-      };
-      const unsigned long long* __restrict__ arow = adj64 + my_n0;
-      auto adj = [&](int r) -> unsigned long long { return __ldg(arow + r); };
-      auto edge_label = [&](int u, int v) -> int {     // label of CSR entry (u -> v): rank of v inside row u
-        const unsigned long long below = adj(u) & ((1ull << v) - 1ull);
-        return cfg.edge_idx_offset + __ldg(c.eattr + __ldg(c.rowptr + my_n0 + u) + __popcll(below)) + cfg.edge_label_shift;
-      };
+    const bool valid = lane < Tc;
+    const int64_t g = valid ? (c.order ? (int64_t)__ldg(c.order + g0 + lane) : g0 + lane) : g0;
+    const int64_t my_n0 = __ldg(c.node_off + g);
+    const int N = valid ? (int)(__ldg(c.node_off + g + 1) - my_n0) : 0;
+    const unsigned long long* __restrict__ arow = adj64 + my_n0;
+    int64_t* __restrict__ row = out + g * stride;                // rows are 16-byte aligned (even stride, aligned base)
 
-      emit(SOS);
-      if (N > 0) {
-        const unsigned long long nodemask = N >= 64 ? ~0ull : ((1ull << N) - 1ull);
-        unsigned long long visited = 0ull;
-        int nvis = 0, prev = -1;
-        int cur = pick(N);
-        while (pos < Lcap) {
-          const unsigned long long a_cur = adj(cur);
-          if (!((visited >> cur) & 1ull)) {
-            const int k = nvis++;
-            vis[cur * 32 + lane] = (unsigned char)k;
-            if (LABELED) ord[k * 32 + lane] = (unsigned char)cur;
-            emit(cfg.idx_offset + k);
-            if (LABELED) emit(cfg.node_idx_offset + __ldg(c.x + my_n0 + cur));
-            unsigned long long M = a_cur & visited;
-            if (prev >= 0) M &= ~(1ull << prev);
-            visited |= 1ull << cur;
-            if (M) {
+    int pos = 0, flushed = 0;                                    // tokens emitted / tokens already in HBM (multiple of 16)
+    auto emit = [&](int t) {
+      if (pos < Lcap) ring[(pos & (kRing - 1)) * 32] = (RingT)t;  // tokens past max_length are never stored
+      ++pos;
+    };
+    auto tok = [&](int p) -> long long {                         // pending token p, post-processed
+      const int t = (int)ring[(p & (kRing - 1)) * 32];
+      return remap ? remap_zinc_tok(t, idx_off, node_off, edge_off) : t;
+    };
+    auto flush16 = [&]() {                                       // 16 tokens = four full 32-byte sectors of the row
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) st_stream_i64x2(row + flushed + i, tok(flushed + i), tok(flushed + i + 1));
+      flushed += 16;
+    };
+    auto flush_guard = [&]() {                                   // inside a long bracket: never let the ring wrap (rare)
+      if (pos - flushed >= kRing - 8 && flushed + 16 <= Lcap) flush16();
+    };
+    auto edge_label = [&](int u, int v, unsigned long long au) -> int {   // label of CSR entry (u -> v): rank of v inside row u
+      const unsigned long long below = au & ((1ull << v) - 1ull);
+      return edge_off + __ldg(c.eattr + __ldg(c.rowptr + my_n0 + u) + __popcll(below)) + cfg.edge_label_shift;
+    };
+
+    // random words
+    const uint64_t gid = (uint64_t)(ch.graph_id_base + g);
+    unsigned b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    unsigned d = 0;
+    int64_t s_off = 0;
+    unsigned s_len = 0;
+    if (ch.stream && valid) {
+      s_off = __ldg(ch.stream_off + g);
+      s_len = (unsigned)(__ldg(ch.stream_off + g + 1) - s_off);
+    }
+    auto pick = [&](int cnt) -> int {
+      unsigned r;
+      if (ch.stream) {
+        r = d < s_len ? __ldg(ch.stream + s_off + d) : 0u;
+      } else {
+        if ((d & 3u) == 0u) philox10((unsigned)gid, (unsigned)(gid >> 32), d >> 2, 0u, k0, k1, b0, b1, b2, b3);
+        const unsigned w01 = (d & 1u) ? b1 : b0, w23 = (d & 1u) ? b3 : b2;
+        r = (d & 2u) ? w23 : w01;
+      }
+      ++d;
+      return (int)__umulhi(r, (unsigned)cnt);
+    };
+
+    if (valid) emit(SOS);
+    const unsigned long long nodemask = N >= 64 ? ~0ull : ((1ull << N) - 1ull);
+    unsigned long long visited = 0ull, reach = 0ull;
+    int nvis = 0, prev = -1, cur = 0;
+    bool done = N == 0 || pos >= Lcap;
+    if (!done) cur = pick(N);
+    while (true) {
+      // ---- arrive at cur ---------------------------------------------------------------------
+      unsigned long long a_cur = 0ull, C = 0ull;
+      bool stuck = false;
+      if (!done) {
+        a_cur = __ldg(arow + cur);
+        if (!((visited >> cur) & 1ull)) {
+          const int k = nvis++;
+          vis[cur * 32] = (unsigned char)k;
+          if (LABELED) ord[k * 32] = (unsigned char)cur;
+          emit(idx_off + k);
+          if (LABELED) emit(node_off + __ldg(c.x + my_n0 + cur));
+          unsigned long long M = a_cur & visited;
+          if (prev >= 0) M &= ~(1ull << prev);
+          visited |= 1ull << cur;
+          reach |= a_cur;
+          if (M) {
+            emit(LADJ);
+            if ((M & (M - 1)) == 0ull) {                          // one member (the common case): no ordering needed
+              const int u = __ffsll((long long)M) - 1;
+              if (LABELED) emit(edge_label(cur, u, a_cur));
+              emit(idx_off + (int)vis[u * 32]);
+            } else {
               unsigned long long V = 0ull;
-              while (M) {
+              do {
                 const int u = __ffsll((long long)M) - 1;
                 M &= M - 1;
-                V |= 1ull << vis[u * 32 + lane];
-              }
-              emit(LADJ);
-              while (V) {
+                V |= 1ull << vis[u * 32];
+              } while (M);
+              do {
                 const int jv = __ffsll((long long)V) - 1;
                 V &= V - 1;
-                if (LABELED) emit(edge_label(cur, (int)ord[jv * 32 + lane]));
-                emit(cfg.idx_offset + jv);
-              }
-              emit(RADJ);
+                if (LABELED) emit(edge_label(cur, (int)ord[jv * 32], a_cur));
+                emit(idx_off + jv);
+                flush_guard();
+              } while (V);
             }
-          } else {
-            emit(cfg.idx_offset + (int)vis[cur * 32 + lane]);     // head of a new segment at a visited node
+            emit(RADJ);
           }
-          const unsigned long long C = a_cur & ~visited;
-          if (C) {
-            const int nxt = select64(C, pick(__popcll(C)));
-            if (LABELED) emit(edge_label(cur, nxt));
-            prev = cur;
-            cur = nxt;
-          } else {
-            if (nvis == N) break;
-            unsigned long long U = ~visited & nodemask, acc = 0ull;
-            unsigned long long t = U;
-            while (t) {
-              const int wv = __ffsll((long long)t) - 1;
-              t &= t - 1;
-              acc |= adj(wv);
-            }
-            const unsigned long long R1 = acc & visited;
-            const unsigned long long R = R1 ? R1 : U;
-            emit(RESET);
-            cur = select64(R, pick(__popcll(R)));
-            prev = -1;
+        } else {
+          emit(idx_off + (int)vis[cur * 32]);                    // head of a new segment at a visited node
+        }
+        C = a_cur & ~visited;
+        if (!C) {
+          if (nvis == N) done = true;
+          else stuck = true;
+        }
+      }
+      // ---- restart service (warp-synchronous) ------------------------------------------------------
+      unsigned long long sel = C;
+      {
+        const unsigned long long myF = reach & ~visited;
+        unsigned need = __ballot_sync(kFull, stuck);
+        while (need) {
+          const int j = __ffs(need) - 1;
+          need &= need - 1;
+          const unsigned long long Fj = __shfl_sync(kFull, myF, j);
+          const unsigned long long rj = __shfl_sync(kFull, (unsigned long long)reinterpret_cast<uintptr_t>(arow), j);
+          const unsigned long long* __restrict__ rowj = reinterpret_cast<const unsigned long long*>((uintptr_t)rj);
+          unsigned long long part = 0ull;
+          if ((Fj >> lane) & 1ull) part = __ldg(rowj + lane);
+          if ((Fj >> (lane + 32)) & 1ull) part |= __ldg(rowj + lane + 32);
+          const unsigned lo = __reduce_or_sync(kFull, (unsigned)part);
+          const unsigned hi = __reduce_or_sync(kFull, (unsigned)(part >> 32));
+          if (lane == j) {
+            const unsigned long long R1 = (((unsigned long long)hi << 32) | lo) & visited;
+            sel = R1 ? R1 : (~visited & nodemask);                // no visited node can continue: any unvisited node
           }
         }
       }
+      // ---- leave: one pick per event ---------------------------------------------------------------
+      if (!done) {
+        if (stuck) emit(RESET);
+        const int nxt = select64(sel, pick(__popcll(sel)));
+        if (LABELED && !stuck) emit(edge_label(cur, nxt, a_cur));
+        prev = stuck ? -1 : cur;
+        cur = nxt;
+        if (pos >= Lcap) done = true;
+      }
+      // ---- flush point (warp-synchronous) ----------------------------------------------------------
+      if (__any_sync(kFull, pos - flushed >= 32) && pos - flushed >= 16 && flushed + 16 <= Lcap) flush16();
+      if (__all_sync(kFull, done)) break;
+    }
+    if (valid) {
       emit(EOS);
-      int L = pos < Lcap ? pos : Lcap;
-      if (L & 1) st_stream_i64(row + L - 1, held);          // flush the unpaired last token
+      const int L0 = pos < Lcap ? pos : Lcap;
+      // drain: whole pairs, then the unpaired last token
+      for (int p = flushed; p + 1 < L0; p += 2) st_stream_i64x2(row + p, tok(p), tok(p + 1));
+      if (L0 & 1) st_stream_i64(row + L0 - 1, tok(L0 - 1));
+      int L = L0;
       if (cfg.append_query) {
-        row[L] = cfg.idx_offset + N;
-        row[L + 1] = cfg.idx_offset + __ldg(c.query_u + g);
-        row[L + 2] = cfg.idx_offset + __ldg(c.query_v + g);
+        row[L] = idx_off + N;
+        row[L + 1] = idx_off + __ldg(c.query_u + g);
+        row[L + 2] = idx_off + __ldg(c.query_v + g);
         L += 3;
       }
       len_out[g] = L;
@@ -229,9 +293,20 @@ int sent_small_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const Gto
                         int64_t* out, int64_t stride, cudaStream_t st, bool* handled) {
   *handled = false;
   if (c->max_nodes > 64 || (stride & 1) || c->adj64 == nullptr) return GTOK_OK;
-  const SmallLayout lay = small_layout(c->max_nodes, cfg->labeled != 0);
+  // largest token before the remap: node index / node label / edge label (needs the label bound)
+  long long tmax = (long long)cfg->idx_offset + 64;
+  bool narrow = tmax < 65536;
+  if (cfg->labeled) {
+    const long long lab = c->max_label > 0 ? c->max_label : (1ll << 40);
+    const long long a = (long long)cfg->node_idx_offset + lab, b = (long long)cfg->edge_idx_offset + lab + cfg->edge_label_shift;
+    narrow = narrow && a < 65536 && b < 65536 && cfg->node_idx_offset >= 0 && cfg->edge_idx_offset + cfg->edge_label_shift >= 0;
+  }
+  narrow = narrow && cfg->idx_offset >= 0;
+  const SmallLayout lay = small_layout(c->max_nodes, cfg->labeled != 0, narrow ? 2 : 4);
   const size_t smem = (size_t)kSmallWarps * lay.warp_bytes;
-  auto k = cfg->labeled ? sent_small_kernel<true> : sent_small_kernel<false>;
+  void (*k)(GtokCsrBatch, GtokSentCfg, GtokChoice, SmallLayout, int32_t*, int64_t*, int64_t);
+  if (cfg->labeled) k = narrow ? sent_small_kernel<true, uint16_t> : sent_small_kernel<true, int32_t>;
+  else k = narrow ? sent_small_kernel<false, uint16_t> : sent_small_kernel<false, int32_t>;
   GTOK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t warps = (c->num_graphs + 31) / 32;
   const int grid = persistent_grid(k, kSmallThreads, smem, (warps + kSmallWarps - 1) / kSmallWarps);
