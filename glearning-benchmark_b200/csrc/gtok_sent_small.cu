@@ -69,9 +69,11 @@ __device__ __forceinline__ int select64(unsigned long long m, int k) {
 }
 
 struct SmallLayout {
-  int o_vis, o_ord, o_ring;   // byte offsets inside a warp slice
+  int o_vis, o_rem, o_ord, o_ring;   // byte offsets inside a warp slice
   int warp_bytes;
 };
+
+constexpr int kRemapTable = 1024;  // tokens below this go through a shared-memory remap table
 
 constexpr int kRing = 64;      // ring slots per lane (tokens leave 16 at a time = four full 32-byte sectors)
 
@@ -81,6 +83,7 @@ static SmallLayout small_layout(int nmax, bool labeled, int ring_elem) {
   SmallLayout L;
   int o = 0;
   L.o_vis = o; o += 32 * nmax;                 // u8  [v][lane]  node -> visit index
+  L.o_rem = o; o += 32 * nmax;                 // u8  [v][lane]  unvisited neighbours left (visited nodes only)
   L.o_ord = o; o += labeled ? 32 * nmax : 0;   // u8  [k][lane]  visit index -> node
   o = (o + 15) & ~15;
   L.o_ring = o; o += kRing * 32 * ring_elem;   // [slot][lane] pending tokens (16-bit when every token fits)
@@ -98,11 +101,11 @@ static SmallLayout small_layout(int nmax, bool labeled, int ring_elem) {
 //   * flush point: when ANY lane has 32 tokens pending, EVERY lane with 16 or more stores 16 (eight 16-byte
 //     stores = four full sectors) - the flush code runs a handful of times per 32 graphs with most lanes
 //     active (lane-by-lane flushing was 31 % of all instructions);
-//   * restart service: a stuck lane needs the visited nodes that still have an unvisited neighbour, i.e. the
-//     neighbours of its FRONTIER (unvisited nodes adjacent to the visited set, kept incrementally as
-//     reach & ~visited).  The warp serves each stuck lane together: lane i loads adjacency rows i and i+32 of
-//     that graph if they are in the frontier, two REDUX.OR give the union - no dependent load chain
-//     (the per-lane scan was 13 % of all stall samples);
+//   * restart in O(1): a stuck lane needs the visited nodes that still have an unvisited neighbour.  Every
+//     visited node keeps a counter of unvisited neighbours (u8 in shared memory) and a bit in `open`; a node's
+//     first visit already enumerates its visited neighbours (trail predecessor + bracket members), so each
+//     edge costs one decrement, and the restart set is just `open` - no adjacency scan (the scan, per lane or
+//     served by the whole warp, was 15-20 % of instructions and the top stall);
 //   * one select64 site (the pick among unvisited neighbours and the restart pick share it); a bracket with
 //     one member (the common case) skips the visit-index ordering.
 template <bool LABELED, typename RingT>
@@ -114,6 +117,7 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
   const int w = threadIdx.x >> 5;
   unsigned char* base = s_smem + (size_t)w * lay.warp_bytes;
   unsigned char* vis = base + lay.o_vis + lane;
+  unsigned char* rem = base + lay.o_rem + lane;
   unsigned char* ord = base + lay.o_ord + lane;
   RingT* ring = reinterpret_cast<RingT*>(base + lay.o_ring) + lane;
   const unsigned long long* __restrict__ adj64 = reinterpret_cast<const unsigned long long*>(c.adj64);
@@ -125,6 +129,12 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
   const unsigned k0 = (unsigned)(ch.seed & 0xffffffffu), k1 = (unsigned)(ch.seed >> 32);
   const bool remap = cfg.remap_zinc != 0;
   const int idx_off = cfg.idx_offset, node_off = cfg.node_idx_offset, edge_off = cfg.edge_idx_offset;
+  __shared__ unsigned short s_remap[kRemapTable];
+  if (remap) {
+    for (int t = threadIdx.x; t < kRemapTable; t += blockDim.x)
+      s_remap[t] = (unsigned short)remap_zinc_tok(t, idx_off, node_off, edge_off);
+    __syncthreads();
+  }
 
   for (int64_t g0 = wid0 * 32; g0 < G; g0 += nw * 32) {
     const int Tc = (int)((G - g0 < 32) ? (G - g0) : 32);
@@ -142,7 +152,8 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
     };
     auto tok = [&](int p) -> long long {                         // pending token p, post-processed
       const int t = (int)ring[(p & (kRing - 1)) * 32];
-      return remap ? remap_zinc_tok(t, idx_off, node_off, edge_off) : t;
+      if (!remap) return t;
+      return (unsigned)t < (unsigned)kRemapTable ? (int)s_remap[t] : remap_zinc_tok(t, idx_off, node_off, edge_off);
     };
     auto flush16 = [&]() {                                       // 16 tokens = four full 32-byte sectors of the row
 #pragma unroll
@@ -152,9 +163,10 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
     auto flush_guard = [&]() {                                   // inside a long bracket: never let the ring wrap (rare)
       if (pos - flushed >= kRing - 8 && flushed + 16 <= Lcap) flush16();
     };
-    auto edge_label = [&](int u, int v, unsigned long long au) -> int {   // label of CSR entry (u -> v): rank of v inside row u
+    // label of CSR entry (cur -> v): rank of v inside cur's row; rp = rowptr of cur, fetched together with its adjacency
+    auto edge_label = [&](int rp, int v, unsigned long long au) -> int {
       const unsigned long long below = au & ((1ull << v) - 1ull);
-      return edge_off + __ldg(c.eattr + __ldg(c.rowptr + my_n0 + u) + __popcll(below)) + cfg.edge_label_shift;
+      return edge_off + __ldg(c.eattr + rp + __popcll(below)) + cfg.edge_label_shift;
     };
 
     // random words
@@ -182,88 +194,79 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
 
     if (valid) emit(SOS);
     const unsigned long long nodemask = N >= 64 ? ~0ull : ((1ull << N) - 1ull);
-    unsigned long long visited = 0ull, reach = 0ull;
+    unsigned long long visited = 0ull, open = 0ull;     // open: visited nodes that still have an unvisited neighbour
     int nvis = 0, prev = -1, cur = 0;
     bool done = N == 0 || pos >= Lcap;
     if (!done) cur = pick(N);
+    unsigned long long a_nxt = 0ull;                    // adjacency row of the node we are about to arrive at
+    int rp_nxt = 0;                                      // (fetched as soon as the node is chosen)
+    if (!done) {
+      a_nxt = __ldg(arow + cur);
+      if (LABELED) rp_nxt = __ldg(c.rowptr + my_n0 + cur);
+    }
     while (true) {
       // ---- arrive at cur ---------------------------------------------------------------------
-      unsigned long long a_cur = 0ull, C = 0ull;
-      bool stuck = false;
       if (!done) {
-        a_cur = __ldg(arow + cur);
+        const unsigned long long a_cur = a_nxt;
+        const int rp_cur = rp_nxt;
         if (!((visited >> cur) & 1ull)) {
           const int k = nvis++;
           vis[cur * 32] = (unsigned char)k;
           if (LABELED) ord[k * 32] = (unsigned char)cur;
           emit(idx_off + k);
           if (LABELED) emit(node_off + __ldg(c.x + my_n0 + cur));
-          unsigned long long M = a_cur & visited;
-          if (prev >= 0) M &= ~(1ull << prev);
+          unsigned long long Mall = a_cur & visited;              // visited neighbours = bracket members + the trail
+          if (prev >= 0) Mall &= ~(1ull << prev);                 // predecessor (already accounted for when we left it)
           visited |= 1ull << cur;
-          reach |= a_cur;
-          if (M) {
+          const unsigned long long C0 = a_cur & ~visited;
+          rem[cur * 32] = (unsigned char)__popcll(C0);
+          if (C0) open |= 1ull << cur;
+          unsigned long long V = 0ull;                            // bracket members in visit-index space
+          while (Mall) {
+            const int u = __ffsll((long long)Mall) - 1;
+            Mall &= Mall - 1;
+            const int r = (int)rem[u * 32] - 1;                   // cur is no longer an unvisited neighbour of u
+            rem[u * 32] = (unsigned char)r;
+            if (r == 0) open &= ~(1ull << u);
+            V |= 1ull << vis[u * 32];
+          }
+          if (V) {
             emit(LADJ);
-            if ((M & (M - 1)) == 0ull) {                          // one member (the common case): no ordering needed
-              const int u = __ffsll((long long)M) - 1;
-              if (LABELED) emit(edge_label(cur, u, a_cur));
-              emit(idx_off + (int)vis[u * 32]);
-            } else {
-              unsigned long long V = 0ull;
-              do {
-                const int u = __ffsll((long long)M) - 1;
-                M &= M - 1;
-                V |= 1ull << vis[u * 32];
-              } while (M);
-              do {
-                const int jv = __ffsll((long long)V) - 1;
-                V &= V - 1;
-                if (LABELED) emit(edge_label(cur, (int)ord[jv * 32], a_cur));
-                emit(idx_off + jv);
-                flush_guard();
-              } while (V);
-            }
+            do {
+              const int jv = __ffsll((long long)V) - 1;
+              V &= V - 1;
+              if (LABELED) emit(edge_label(rp_cur, (int)ord[jv * 32], a_cur));
+              emit(idx_off + jv);
+              flush_guard();
+            } while (V);
             emit(RADJ);
           }
         } else {
           emit(idx_off + (int)vis[cur * 32]);                    // head of a new segment at a visited node
         }
-        C = a_cur & ~visited;
-        if (!C) {
-          if (nvis == N) done = true;
-          else stuck = true;
-        }
-      }
-      // ---- restart service (warp-synchronous) ------------------------------------------------------
-      unsigned long long sel = C;
-      {
-        const unsigned long long myF = reach & ~visited;
-        unsigned need = __ballot_sync(kFull, stuck);
-        while (need) {
-          const int j = __ffs(need) - 1;
-          need &= need - 1;
-          const unsigned long long Fj = __shfl_sync(kFull, myF, j);
-          const unsigned long long rj = __shfl_sync(kFull, (unsigned long long)reinterpret_cast<uintptr_t>(arow), j);
-          const unsigned long long* __restrict__ rowj = reinterpret_cast<const unsigned long long*>((uintptr_t)rj);
-          unsigned long long part = 0ull;
-          if ((Fj >> lane) & 1ull) part = __ldg(rowj + lane);
-          if ((Fj >> (lane + 32)) & 1ull) part |= __ldg(rowj + lane + 32);
-          const unsigned lo = __reduce_or_sync(kFull, (unsigned)part);
-          const unsigned hi = __reduce_or_sync(kFull, (unsigned)(part >> 32));
-          if (lane == j) {
-            const unsigned long long R1 = (((unsigned long long)hi << 32) | lo) & visited;
-            sel = R1 ? R1 : (~visited & nodemask);                // no visited node can continue: any unvisited node
+        // ---- leave: one pick per event -------------------------------------------------------------
+        const unsigned long long C = a_cur & ~visited;
+        if (!C && nvis == N) {
+          done = true;
+        } else {
+          unsigned long long sel = C;
+          if (!C) {                                               // stuck: restart at an open node, else at any unvisited node
+            sel = open ? open : (~visited & nodemask);
+            emit(RESET);
           }
+          const int nsel = __popcll(sel);
+          const int nxt = select64(sel, pick(nsel));
+          a_nxt = __ldg(arow + nxt);
+          if (LABELED) rp_nxt = __ldg(c.rowptr + my_n0 + nxt);
+          if (C) {                                                // trail step: nxt stops being an unvisited neighbour of cur
+            rem[cur * 32] = (unsigned char)(nsel - 1);            // (nsel == |C| == the counter's current value)
+            if (nsel == 1) open &= ~(1ull << cur);
+            if (LABELED) emit(edge_label(rp_cur, nxt, a_cur));
+          }
+          prev = C ? cur : -1;
+          cur = nxt;
+          if (pos >= Lcap) done = true;
         }
-      }
-      // ---- leave: one pick per event ---------------------------------------------------------------
-      if (!done) {
-        if (stuck) emit(RESET);
-        const int nxt = select64(sel, pick(__popcll(sel)));
-        if (LABELED && !stuck) emit(edge_label(cur, nxt, a_cur));
-        prev = stuck ? -1 : cur;
-        cur = nxt;
-        if (pos >= Lcap) done = true;
       }
       // ---- flush point (warp-synchronous) ----------------------------------------------------------
       if (__any_sync(kFull, pos - flushed >= 32) && pos - flushed >= 16 && flushed + 16 <= Lcap) flush16();
