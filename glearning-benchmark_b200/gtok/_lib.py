@@ -64,6 +64,8 @@ PROTOTYPES = {
     "gtok_version": (C.c_int, []),
     "gtok_last_error": (C.c_char_p, []),
     "gtok_device_sm_count": (C.c_int, []),
+    "gtok_widen_i32": (C.c_int, [vp, i32, i64, vp, vp]),
+    "gtok_counts_to_offsets": (C.c_int, [vp, i32, i64, vp, vp, vp, C.c_size_t, vp]),
     "gtok_ibtt_lengths": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(IbttRulesC), vp, vp]),
     "gtok_scan_workspace_bytes": (C.c_size_t, [i64]),
     "gtok_scan_offsets": (C.c_int, [vp, i64, vp, vp, C.c_size_t, vp]),

@@ -178,3 +178,57 @@ class GraphBatch:
             qv = torch.as_tensor([int(d.query_v) for d in data_list], dtype=torch.int32)
         y = torch.cat([d.y.reshape(-1)[:1] for d in data_list]) if has("y") else None
         return GraphBatch(node_off, edge_off, ei[0].contiguous(), ei[1].contiguous(), x, ea, qu, qv, y)
+
+
+def _narrowest(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Lossless narrowing of a non-negative integer array: uint8 if every value fits, else int16-as-uint16
+    (stored in torch.int16 storage and reinterpreted on the device), else int32."""
+    if t is None:
+        return None
+    if t.numel() == 0:
+        return t.to(torch.uint8)
+    lo, hi = int(t.min()), int(t.max())
+    if lo >= 0 and hi < 256:
+        return t.to(torch.uint8)
+    if lo >= 0 and hi < 65536:
+        return (t.to(torch.int32) & 0xFFFF).to(torch.int16)       # bit pattern of the uint16 value
+    return t.to(torch.int32)
+
+
+@dataclass
+class PackedGraphBatch:
+    """Compact host-side wire format of a GraphBatch: per-graph COUNTS instead of int64 offsets and the
+    narrowest lossless unsigned type per array.  gtok_widen_i32 / gtok_counts_to_offsets (include/gtok.h)
+    restore the resident int32 layout on the device.  For ZINC-shaped molecules this is 0.17 KB per graph
+    over PCIe instead of 0.68 KB (the reference's own int64 tensors would be 1.3 KB)."""
+    node_cnt: torch.Tensor
+    entry_cnt: torch.Tensor
+    src: torch.Tensor
+    dst: torch.Tensor
+    x: Optional[torch.Tensor] = None
+    edge_attr: Optional[torch.Tensor] = None
+    query_u: Optional[torch.Tensor] = None
+    query_v: Optional[torch.Tensor] = None
+    num_nodes_total: int = 0
+    num_entries_total: int = 0
+
+    ARRAYS = ("node_cnt", "entry_cnt", "src", "dst", "x", "edge_attr", "query_u", "query_v")
+
+    @property
+    def num_graphs(self) -> int:
+        return int(self.node_cnt.numel())
+
+    @staticmethod
+    def from_batch(b: GraphBatch) -> "PackedGraphBatch":
+        return PackedGraphBatch(_narrowest(b.num_nodes()), _narrowest(b.num_entries()), _narrowest(b.src),
+                                _narrowest(b.dst), _narrowest(b.x), _narrowest(b.edge_attr), _narrowest(b.query_u),
+                                _narrowest(b.query_v), int(b.node_off[-1]) if b.num_graphs else 0,
+                                int(b.edge_off[-1]) if b.num_graphs else 0)
+
+    def pin_memory(self) -> "PackedGraphBatch":
+        kw = {n: (None if getattr(self, n) is None else getattr(self, n).pin_memory()) for n in self.ARRAYS}
+        return PackedGraphBatch(num_nodes_total=self.num_nodes_total, num_entries_total=self.num_entries_total, **kw)
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in self.ARRAYS
+                   if getattr(self, n) is not None)

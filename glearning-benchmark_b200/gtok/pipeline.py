@@ -18,7 +18,7 @@ import torch
 
 from . import _lib, engine
 from ._lib import lib, check
-from .batch import GraphBatch
+from .batch import GraphBatch, PackedGraphBatch
 from .engine import _ptr, _stream
 
 
@@ -83,6 +83,28 @@ class _PipelineBase:
                "x": host.x, "edge_attr": host.edge_attr, "query_u": host.query_u, "query_v": host.query_v}
         for k, dst in self.dev_in.items():
             dst.copy_(src[k], non_blocking=True)
+
+    def upload_packed(self, host: PackedGraphBatch) -> None:
+        """compact pinned host arrays -> narrow device staging -> gtok_widen_i32 / gtok_counts_to_offsets into the
+        resident int32 layout (all async on the current stream)."""
+        st = _stream()
+        if getattr(self, "_wire", None) is None or self._wire_key != tuple(
+                (n, getattr(host, n).dtype, getattr(host, n).numel()) for n in host.ARRAYS if getattr(host, n) is not None):
+            self._wire = {n: torch.empty_like(getattr(host, n), device=self.device) for n in host.ARRAYS
+                          if getattr(host, n) is not None}
+            self._wire_key = tuple((n, getattr(host, n).dtype, getattr(host, n).numel()) for n in host.ARRAYS
+                                   if getattr(host, n) is not None)
+            self._cnt_tmp = torch.empty(max(1, self.G), dtype=torch.int32, device=self.device)
+        self._h2d_packed = host.nbytes()
+        for n, d in self._wire.items():
+            d.copy_(getattr(host, n), non_blocking=True)
+        w = self._wire
+        for cnt, off in (("node_cnt", "node_off"), ("entry_cnt", "edge_off")):
+            check(lib.gtok_counts_to_offsets(_ptr(w[cnt]), w[cnt].element_size(), self.G, _ptr(self.dev_in[off]),
+                                             _ptr(self._cnt_tmp), _ptr(self.ws), self.ws_bytes, st))
+        for n in ("src", "dst", "x", "edge_attr", "query_u", "query_v"):
+            if n in self.dev_in and n in w:
+                check(lib.gtok_widen_i32(_ptr(w[n]), w[n].element_size(), w[n].numel(), _ptr(self.dev_in[n]), st))
 
     def use_device_batch(self, dev_batch: GraphBatch) -> None:
         """Point the pipeline at arrays already resident in HBM (no copy)."""
@@ -190,9 +212,13 @@ class ZincIbttPipeline(_PipelineBase):
             C.byref(bc), C.byref(self.zv), _ptr(self.offsets), _ptr(self.tokens), st)))
         self._collate(self.pad_id)
 
-    def run(self, host_batch: GraphBatch) -> EpochResult:
-        """Public end-to-end call: pinned host graphs in, device batches + host row metadata out."""
-        self.upload(host_batch)
+    def run(self, host_batch) -> EpochResult:
+        """Public end-to-end call: pinned host graphs in (GraphBatch, or the compact PackedGraphBatch wire
+        format), device batches + host row metadata out."""
+        if isinstance(host_batch, PackedGraphBatch):
+            self.upload_packed(host_batch)
+        else:
+            self.upload(host_batch)
         self.launch()
         self.download()
         torch.cuda.current_stream().synchronize()
@@ -247,8 +273,11 @@ class GraphTokenIbttPipeline(_PipelineBase):
             C.byref(bc), C.byref(self.rules), _ptr(self.offsets), _ptr(self.tokens), st)))
         self._collate(self.pad_id)
 
-    def run(self, host_batch: GraphBatch) -> EpochResult:
-        self.upload(host_batch)
+    def run(self, host_batch) -> EpochResult:
+        if isinstance(host_batch, PackedGraphBatch):
+            self.upload_packed(host_batch)
+        else:
+            self.upload(host_batch)
         self.launch()
         self.download()
         torch.cuda.current_stream().synchronize()

@@ -148,6 +148,18 @@ GTOK_API const char* gtok_last_error(void);
 /* HOST: number of SMs of the current device, or a negative GTOK_E*. */
 GTOK_API int gtok_device_sm_count(void);
 
+/* Ingest  compact host->device wire format.  The reference holds graphs as int64 PyG tensors on the host
+ *      (zinc_dataset_autograph.py:51-73, graph_token_dataset_autograph.py:378-394); the engine's resident
+ *      layout is the int32 GtokGraphBatch above.  The host side ships each array in the narrowest lossless
+ *      unsigned type (local node ids, atom/bond types and per-graph counts of molecule-sized graphs fit 8/16
+ *      bits) and these two calls restore the resident layout on the device:
+ *      gtok_widen_i32: in[n] of elem_bytes (1 = uint8, 2 = uint16, 4 = int32 copy) -> out int32[n];
+ *      gtok_counts_to_offsets: per-graph counts -> int64[G+1] exclusive offsets (tmp_i32 int32[G] scratch,
+ *      ws as for gtok_scan_offsets).  All buffers 16-byte aligned. */
+GTOK_API int gtok_widen_i32(const void* in, int32_t elem_bytes, int64_t n, int32_t* out, void* stream);
+GTOK_API int gtok_counts_to_offsets(const void* counts, int32_t elem_bytes, int64_t num_items, int64_t* off_out,
+                                    int32_t* tmp_i32, void* ws, size_t ws_bytes, void* stream);
+
 /* K1a  lengths of TokenDataset sequences for graph-token graphs:
  *      min(max_len, 3E + N + 5|7)  (data_loader.py:471-484 applied to the
  *      serializer grammar).  len_out int32[G]. */

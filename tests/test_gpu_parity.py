@@ -255,6 +255,39 @@ def test_zinc_properties_large(dev):
         assert rag.row(g).cpu().tolist() == want.tolist()
 
 
+def test_ingest_widen_and_packed_pipeline(dev):
+    """compact wire format: widen kernels restore the int32 layout bit for bit, and the pipeline fed with a
+    PackedGraphBatch produces the same batches as with the int32 GraphBatch."""
+    from gtok import synth
+    from gtok._lib import lib, check
+    from gtok.batch import PackedGraphBatch
+    from gtok.engine import _ptr, _stream
+    from gtok.pipeline import ZincIbttPipeline
+    rng = np.random.default_rng(5)
+    for n, hi, dt in ((0, 10, torch.uint8), (1, 255, torch.uint8), (1000003, 255, torch.uint8), (77, 65535, torch.int16),
+                      (524288 + 5, 65535, torch.int16), (1234, 1 << 30, torch.int32)):
+        v = torch.from_numpy(rng.integers(0, hi + 1, n).astype(np.int64))
+        src = ((v & 0xFFFF).to(torch.int16) if dt == torch.int16 else v.to(dt)).to(dev)
+        out = torch.full((n + 8,), -7, dtype=torch.int32, device=dev)
+        check(lib.gtok_widen_i32(_ptr(src), src.element_size(), n, _ptr(out), _stream()))
+        assert torch.equal(out[:n].cpu().to(torch.int64), v) and bool((out[n:] == -7).all())
+    gb = synth.zinc_shaped(5000, seed=4)
+    vocab = O.zinc_extend_vocab(O.zinc_fixed_vocab(), [str(k) for k in range(37)] + ["X", "unknown"])
+    pk = PackedGraphBatch.from_batch(gb)
+    assert pk.src.dtype == torch.uint8 and pk.node_cnt.dtype == torch.uint8 and pk.nbytes() * 3 < gb.input_bytes()
+    for mode in ("collate", "ragged"):
+        pipe = ZincIbttPipeline(gb, vocab, 1024, 128, dev, mode=mode)
+        a = pipe.run(gb.pin_memory())
+        Xa, Aa, la = a.padded.X.clone(), a.padded.attn.clone(), a.host_lengths.clone()
+        tot = int(a.host_xoff[-1])
+        pipe.dev_in["src"].zero_()
+        pipe.dev_in["node_off"].zero_()
+        b = pipe.run(pk.pin_memory())
+        assert int(b.host_xoff[-1]) == tot and torch.equal(b.host_lengths, la)
+        assert torch.equal(b.padded.X[:tot], Xa[:tot]) and torch.equal(b.padded.attn[:tot], Aa[:tot])
+        assert torch.equal(pipe.dev_in["node_off"].cpu(), gb.node_off) and torch.equal(pipe.dev_in["edge_off"].cpu(), gb.edge_off)
+
+
 # --------------------------------------------------------------------------- K4
 def test_collate_permuted_batches(dev):
     from gtok import engine
