@@ -77,6 +77,44 @@ __device__ __forceinline__ void warp_write_row(int64_t* __restrict__ row, int L,
 }
 
 
+// One warp writes one row of a padded batch: X[0..Lmax) = tok(p) for p < len else pad, attn[0..Lmax) =
+// (p < len), both with 16-byte streaming stores on the aligned interior (collate, data_loader.py:488-497).
+// tok(p) must be callable for any 0 <= p < len by any lane.
+__device__ __forceinline__ unsigned long long mask8(int nvalid) {   // low `nvalid` bytes (0..8) = 0x01
+  if (nvalid <= 0) return 0ull;
+  if (nvalid >= 8) return 0x0101010101010101ull;
+  return 0x0101010101010101ull >> (8 * (8 - nvalid));
+}
+template <typename F>
+__device__ __forceinline__ void warp_pad_row(int len, int Lmax, int64_t pad, int64_t* __restrict__ xrow,
+                                             uint8_t* __restrict__ arow, F tok) {
+  const int lane = lane_id();
+  const int head = (int)((reinterpret_cast<uintptr_t>(xrow) >> 3) & 1);
+  if (head && lane == 0 && Lmax > 0) st_stream_i64(xrow, 0 < len ? (int64_t)tok(0) : pad);
+  const int npair = (Lmax - head) >> 1;
+  const int nfull = (len - head) >> 1;                   // pairs that lie entirely inside the row
+  for (int j = lane; j < npair; j += kWarp) {
+    const int p = head + 2 * j;
+    int64_t a = pad, b = pad;
+    if (j < nfull) { a = (int64_t)tok(p); b = (int64_t)tok(p + 1); }
+    else if (p < len) a = (int64_t)tok(p);
+    st_stream_i64x2(xrow + p, a, b);
+  }
+  const int tailx = head + 2 * npair;
+  if (tailx < Lmax && lane == 31) st_stream_i64(xrow + tailx, tailx < len ? (int64_t)tok(tailx) : pad);
+  int mh = (int)((16 - (reinterpret_cast<uintptr_t>(arow) & 15)) & 15);
+  if (mh > Lmax) mh = Lmax;
+  if (lane < mh) arow[lane] = (uint8_t)(lane < len);
+  const int nvec = (Lmax - mh) >> 4;
+  for (int q = lane; q < nvec; q += kWarp) {
+    const int p = mh + 16 * q;
+    const int nv = len - p;
+    __stcs(reinterpret_cast<ulonglong2*>(arow + p), make_ulonglong2(mask8(nv), mask8(nv - 8)));
+  }
+  const int tail = mh + 16 * nvec;
+  if (tail + lane < Lmax && lane < 16) arow[tail + lane] = (uint8_t)(tail + lane < len);
+}
+
 // ---- decoupled look-back (single-pass chained scan) -------------------------
 // One 64-bit word per tile carries {flag (top 2 bits) | value (62 bits)}, so flag
 // and value can never be observed out of order; relaxed gpu-scope accesses suffice.

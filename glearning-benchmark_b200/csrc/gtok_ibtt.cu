@@ -92,6 +92,106 @@ ibtt_serialize_kernel(GtokGraphBatch b, GtokIbttRules r, const int64_t* __restri
   }
 }
 
+// K1+K4 fused: graph-token graphs -> padded batches, the ragged stream never exists.  One CTA per batch
+// (grid-stride), one warp per row; batch extents come from the closed-form lengths (gtok_ibtt_lengths ->
+// gtok_batch_extents -> gtok_scan_offsets, 16 bytes per graph), so there is no inter-CTA dependency.
+// Rows that fit the warp's shared-memory row buffer are built segment-wise (lane <-> edge: 3 tokens, lane <->
+// node: 1 token) and streamed out with pad fill + mask; longer rows use the closed form per position.
+constexpr int kIcThreads = 256;
+constexpr int kIcWarps = kIcThreads / 32;
+
+template <int TASK, typename StageT>
+__global__ void __launch_bounds__(kIcThreads)
+ibtt_collate_kernel(GtokGraphBatch b, GtokIbttRules r, const int64_t* __restrict__ batch_idx, int64_t G, int B,
+                    int64_t nb, const int32_t* __restrict__ lmax, const int64_t* __restrict__ xoff, int64_t pad,
+                    int row_cap, int tbl_cap, int64_t* __restrict__ X, uint8_t* __restrict__ attn) {
+  extern __shared__ __align__(16) unsigned char ic_smem[];
+  StageT* s_tbl = reinterpret_cast<StageT*>(ic_smem);                     // node_tok[] (first tbl_cap entries)
+  const int lane = lane_id(), w = threadIdx.x >> 5;
+  StageT* rb = reinterpret_cast<StageT*>(ic_smem + (((size_t)tbl_cap * sizeof(StageT) + 15) & ~(size_t)15)) +
+               (size_t)w * row_cap;
+  const int32_t* __restrict__ node_tok = r.node_tok;
+  const int tbl = r.node_tok_len;
+  const int oov = r.oov;
+  const int qlen = TASK == GTOK_TASK_CYCLE_CHECK ? 5 : 7;
+  for (int i = threadIdx.x; i < tbl_cap; i += kIcThreads) s_tbl[i] = (StageT)(i < tbl ? __ldg(node_tok + i) : oov);
+  __syncthreads();
+  auto node = [&](int k) -> int {
+    if ((unsigned)k < (unsigned)tbl_cap) return (int)s_tbl[k];
+    return ((unsigned)k < (unsigned)tbl) ? __ldg(node_tok + k) : oov;
+  };
+
+  for (int64_t k = blockIdx.x; k < nb; k += gridDim.x) {
+    const int Lm = __ldg(lmax + k);
+    const int64_t base = __ldg(xoff + k);
+    const int64_t r0 = k * B;
+    const int rows = (int)((G - r0 < B) ? (G - r0) : B);
+    for (int rr = w; rr < rows; rr += kIcWarps) {
+      const int64_t g = batch_idx ? __ldg(batch_idx + r0 + rr) : r0 + rr;
+      int64_t s = 0;
+      if (lane < 2) s = __ldg(b.node_off + g + lane);
+      else if (lane < 4) s = __ldg(b.edge_off + g + lane - 2);
+      const int64_t n0 = __shfl_sync(kFull, s, 0), n1 = __shfl_sync(kFull, s, 1);
+      const int64_t e0 = __shfl_sync(kFull, s, 2), e1 = __shfl_sync(kFull, s, 3);
+      const int N = (int)(n1 - n0), E = (int)(e1 - e0), E3 = 3 * E;
+      const long long full = 3ll * E + N + qlen;
+      const int L = (int)(full < r.max_len ? full : r.max_len);
+      const int32_t* __restrict__ src = b.src + e0;
+      const int32_t* __restrict__ dst = b.dst + e0;
+      int qu = 0, qv = 0;
+      if (TASK == GTOK_TASK_SHORTEST_PATH) {
+        qu = __ldg(b.query_u + g);
+        qv = __ldg(b.query_v + g);
+      }
+      const int64_t o = base + (int64_t)rr * Lm;
+      if (full <= row_cap) {
+        // ---- build the untruncated row in shared memory, segment by segment -------------------------
+        if (lane == 0) rb[0] = (StageT)r.tok_bos;
+        for (int e = lane; e < E; e += kWarp) {
+          rb[1 + 3 * e] = (StageT)node(__ldcs(src + e));
+          rb[2 + 3 * e] = (StageT)node(__ldcs(dst + e));
+          rb[3 + 3 * e] = (StageT)r.tok_e;
+        }
+        if (lane == 0) rb[E3 + 1] = (StageT)r.tok_n;
+        for (int i = lane; i < N; i += kWarp) rb[E3 + 2 + i] = (StageT)node(i);
+        if (lane == 0) {
+          int t = E3 + 2 + N;
+          rb[t++] = (StageT)r.tok_q;
+          rb[t++] = (StageT)r.tok_task;
+          if (TASK == GTOK_TASK_SHORTEST_PATH) { rb[t++] = (StageT)node(qu); rb[t++] = (StageT)node(qv); }
+          rb[t] = (StageT)r.tok_p;
+        }
+        __syncwarp();
+        const StageT* __restrict__ rbc = rb;
+        warp_pad_row(L, Lm, pad, X + o, attn + o, [&](int p) -> int { return (int)rbc[p]; });
+        __syncwarp();                                     // row buffer drained before the next row overwrites it
+      } else {
+        auto tok = [&](int p) -> int {                    // closed form per position (same as ibtt_serialize_kernel)
+          if (p == 0) return r.tok_bos;
+          if (p <= E3) {
+            const int e = (int)(__umulhi((unsigned)(p - 1), 0xAAAAAAABu) >> 1);
+            const int rem = (p - 1) - 3 * e;
+            if (rem == 2) return r.tok_e;
+            return node(rem == 0 ? __ldg(src + e) : __ldg(dst + e));
+          }
+          const int t = p - E3 - 1;
+          if (t == 0) return r.tok_n;
+          if (t <= N) return node(t - 1);
+          const int u = t - N - 1;
+          if (u == 0) return r.tok_q;
+          if (u == 1) return r.tok_task;
+          if (TASK == GTOK_TASK_SHORTEST_PATH) {
+            if (u == 2) return node(qu);
+            if (u == 3) return node(qv);
+          }
+          return r.tok_p;
+        };
+        warp_pad_row(L, Lm, pad, X + o, attn + o, tok);
+      }
+    }
+  }
+}
+
 static int check_batch(const GtokGraphBatch* b, const char* who) {
   GTOK_REQUIRE(b != nullptr, GTOK_EINVAL, "%s: null batch", who);
   GTOK_REQUIRE(b->num_graphs >= 0, GTOK_EINVAL, "%s: negative graph count", who);
@@ -149,6 +249,47 @@ extern "C" int gtok_ibtt_serialize(const GtokGraphBatch* batch, const GtokIbttRu
     const int grid = persistent_grid(ibtt_serialize_kernel<GTOK_TASK_SHORTEST_PATH>, kIbttThreads, 0, work);
     ibtt_serialize_kernel<GTOK_TASK_SHORTEST_PATH><<<grid, kIbttThreads, 0, st>>>(*batch, *rules, off, tok_out);
   }
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}
+
+extern "C" int gtok_ibtt_collate(const GtokGraphBatch* batch, const GtokIbttRules* rules, const int64_t* batch_idx,
+                                 int64_t num_rows, int64_t batch_size, const int32_t* lmax, const int64_t* xoff,
+                                 int64_t pad_id, int64_t* X, uint8_t* attn, void* stream) {
+  using namespace gtok;
+  int rc = check_batch(batch, "ibtt_collate");
+  if (rc) return rc;
+  rc = check_rules(rules, batch);
+  if (rc) return rc;
+  GTOK_REQUIRE(num_rows >= 0 && batch_size > 0 && batch_size < (1ll << 31), GTOK_EINVAL, "ibtt_collate: need num_rows >= 0, 0 < batch_size < 2^31");
+  if (num_rows == 0) return GTOK_OK;
+  GTOK_REQUIRE(batch->num_graphs > 0, GTOK_EINVAL, "ibtt_collate: rows requested from an empty batch");
+  GTOK_REQUIRE(lmax && xoff && X && attn, GTOK_EINVAL, "ibtt_collate: null pointer");
+  GTOK_REQUIRE(batch->src && batch->dst, GTOK_EINVAL, "ibtt_collate: null src/dst");
+  GTOK_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0, GTOK_EINVAL, "ibtt_collate: X must be 16-byte aligned");
+  const int64_t nb = (num_rows + batch_size - 1) / batch_size;
+  // shared memory: node table (up to 4096 entries) + one row buffer per warp; rows longer than the buffer use the closed form
+  int maxid = rules->tok_bos;
+  const int ids[6] = {rules->tok_e, rules->tok_n, rules->tok_q, rules->tok_p, rules->tok_task, rules->oov};
+  for (int i = 0; i < 6; ++i) maxid = ids[i] > maxid ? ids[i] : maxid;
+  const bool narrow = maxid < 65536 && rules->max_token_id > 0 && rules->max_token_id < 65536;
+  const int esz = narrow ? 2 : 4;
+  const int tbl_cap = rules->node_tok_len < 4096 ? rules->node_tok_len : 4096;
+  int row_cap = rules->max_len + 8;
+  if (row_cap > 2048) row_cap = 2048;
+  row_cap = (row_cap + 7) & ~7;
+  const size_t smem = (((size_t)tbl_cap * esz + 15) & ~(size_t)15) + (size_t)kIcWarps * row_cap * esz;
+  cudaStream_t st = (cudaStream_t)stream;
+  void (*k)(GtokGraphBatch, GtokIbttRules, const int64_t*, int64_t, int, int64_t, const int32_t*, const int64_t*, int64_t,
+            int, int, int64_t*, uint8_t*);
+  if (rules->task == GTOK_TASK_CYCLE_CHECK)
+    k = narrow ? ibtt_collate_kernel<GTOK_TASK_CYCLE_CHECK, uint16_t> : ibtt_collate_kernel<GTOK_TASK_CYCLE_CHECK, int32_t>;
+  else
+    k = narrow ? ibtt_collate_kernel<GTOK_TASK_SHORTEST_PATH, uint16_t> : ibtt_collate_kernel<GTOK_TASK_SHORTEST_PATH, int32_t>;
+  GTOK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = persistent_grid(k, kIcThreads, smem, nb);
+  k<<<grid, kIcThreads, smem, st>>>(*batch, *rules, batch_idx, num_rows, (int)batch_size, nb, lmax, xoff, pad_id, row_cap,
+                                    tbl_cap, X, attn);
   GTOK_CUDA_TRY(cudaGetLastError());
   return GTOK_OK;
 }

@@ -34,7 +34,7 @@ class GraphBatchC(C.Structure):
 class IbttRulesC(C.Structure):
     _fields_ = [("task", i32), ("max_len", i32), ("tok_bos", i32), ("tok_e", i32), ("tok_n", i32),
                 ("tok_q", i32), ("tok_p", i32), ("tok_task", i32), ("oov", i32), ("node_tok_len", i32),
-                ("node_tok", vp)]
+                ("node_tok", vp), ("max_token_id", i32), ("reserved_", i32)]
 
 
 class ZincVocabC(C.Structure):
@@ -70,6 +70,7 @@ PROTOTYPES = {
     "gtok_scan_workspace_bytes": (C.c_size_t, [i64]),
     "gtok_scan_offsets": (C.c_int, [vp, i64, vp, vp, C.c_size_t, vp]),
     "gtok_ibtt_serialize": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(IbttRulesC), vp, vp, vp]),
+    "gtok_ibtt_collate": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(IbttRulesC), vp, i64, i64, vp, vp, i64, vp, vp, vp]),
     "gtok_zinc_lengths": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(ZincVocabC), vp, vp]),
     "gtok_zinc_serialize": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(ZincVocabC), vp, vp, vp]),
     "gtok_zinc_tokenize_workspace_bytes": (C.c_size_t, [i64]),

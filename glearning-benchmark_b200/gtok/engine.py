@@ -96,7 +96,7 @@ def ibtt_rules(vocab: Dict[str, int], task: str, max_len: int, table_size: int, 
     else:
         raise ValueError(f"unsupported graph-token task {task!r}")
     r = _lib.IbttRulesC(tcode, int(max_len), g("<bos>"), g("<e>"), g("<n>"), g("<q>"), g("<p>"), ttok, pad,
-                        tbl.numel(), _ptr(tbl))
+                        tbl.numel(), _ptr(tbl), max(vocab.values()), 0)
     return r, tbl      # keep tbl alive as long as r is used
 
 
@@ -119,6 +119,37 @@ def tokenize_ibtt(batch: GraphBatch, vocab: Dict[str, int], task: str, max_len: 
         raise ValueError("output buffer too small")
     check(lib.gtok_ibtt_serialize(C.byref(bc), C.byref(rules), _ptr(off), _ptr(out), _stream()))
     return Ragged(out[:total], off, lengths)
+
+
+def ibtt_collate_epoch(batch: GraphBatch, vocab: Dict[str, int], task: str, max_len: int, batch_size: int,
+                       batch_idx: Optional[torch.Tensor] = None, max_nodes: Optional[int] = None,
+                       X: Optional[torch.Tensor] = None, attn: Optional[torch.Tensor] = None):
+    """K1+K4 in one pass: graph-token graphs -> every padded batch of an epoch (serializer + TokenDataset +
+    collate); batch_idx = the epoch's row order (DataLoader shuffle), None = dataset order.
+    -> (PaddedEpoch, lengths int32[G] in dataset order)."""
+    _require_cuda(batch.src, batch_idx)
+    dev = batch.device
+    G = batch.num_graphs
+    rows = int(batch_idx.numel()) if batch_idx is not None else G
+    B = int(batch_size)
+    nb = (rows + B - 1) // B
+    if max_nodes is None:
+        max_nodes = int(batch.num_nodes().max()) if G else 0
+    bc = _batch_c(batch, max_nodes, 1)
+    rules, tbl = ibtt_rules(vocab, task, max_len, max(1, max_nodes), dev)
+    lengths = torch.empty(G, dtype=torch.int32, device=dev)
+    check(lib.gtok_ibtt_lengths(C.byref(bc), C.byref(rules), _ptr(lengths), _stream()))
+    lmax = torch.empty(nb, dtype=torch.int32, device=dev)
+    cells = torch.empty(nb, dtype=torch.int32, device=dev)
+    check(lib.gtok_batch_extents(_ptr(lengths), _ptr(batch_idx), rows, B, _ptr(lmax), _ptr(cells), _stream()))
+    xoff = scan_offsets(cells)
+    if X is None or attn is None:
+        total = int(xoff[-1]) if nb else 0
+        X = torch.empty(total, dtype=torch.int64, device=dev)
+        attn = torch.empty(total, dtype=torch.bool, device=dev)
+    check(lib.gtok_ibtt_collate(C.byref(bc), C.byref(rules), _ptr(batch_idx), rows, B, _ptr(lmax), _ptr(xoff),
+                                int(vocab["<pad>"]), _ptr(X), _ptr(attn), _stream()))
+    return PaddedEpoch(X, attn, xoff, lmax, B, rows), lengths
 
 
 # ---------------------------------------------------------------------------

@@ -244,8 +244,12 @@ class ZincIbttPipeline(_PipelineBase):
 class GraphTokenIbttPipeline(_PipelineBase):
     """BASELINE config 1/5: IBTT tokenization of graph-token graphs + collate."""
 
-    def __init__(self, host_batch: GraphBatch, vocab: Dict[str, int], task: str, max_len: int, batch_size: int, device):
+    def __init__(self, host_batch: GraphBatch, vocab: Dict[str, int], task: str, max_len: int, batch_size: int, device,
+                 mode: str = "collate"):
+        """mode "collate": lengths -> batch extents -> scan -> gtok_ibtt_collate (graphs -> padded batches, the ragged
+        stream never exists); "ragged": lengths -> scan -> serialize (ragged ids kept) -> K4 collate kernels."""
         G = host_batch.num_graphs
+        self.mode = mode
         n = host_batch.num_nodes()
         e = host_batch.num_entries()
         self.max_nodes = int(n.max()) if G else 1
@@ -256,6 +260,7 @@ class GraphTokenIbttPipeline(_PipelineBase):
         fields = ["query"] if task == "shortest_path" else []
         super().__init__(G, n_total, e_total, tok_cap + 2, G * row_bound + 2, batch_size, device, fields)
         self.task = task
+        self.kernel_launches_per_pass = 4 if mode == "collate" else 6
         self.pad_id = int(vocab["<pad>"])
         self.rules, self._tbl = engine.ibtt_rules(vocab, task, max_len, self.max_nodes, self.device)
 
@@ -268,6 +273,14 @@ class GraphTokenIbttPipeline(_PipelineBase):
         bc = self._batch_c()
         st = _stream()
         self._timed("ibtt_lengths", lambda: check(lib.gtok_ibtt_lengths(C.byref(bc), C.byref(self.rules), _ptr(self.lengths), st)))
+        if self.mode == "collate":
+            self._timed("batch_extents", lambda: check(lib.gtok_batch_extents(
+                _ptr(self.lengths), None, self.G, self.B, _ptr(self.lmax), _ptr(self.cells), st)))
+            self._timed("scan_batches", lambda: self._scan(self.cells, self.nb, self.xoff))
+            self._timed("ibtt_collate", lambda: check(lib.gtok_ibtt_collate(
+                C.byref(bc), C.byref(self.rules), None, self.G, self.B, _ptr(self.lmax), _ptr(self.xoff), self.pad_id,
+                _ptr(self.X), _ptr(self.attn), st)))
+            return
         self._timed("scan_rows", lambda: self._scan(self.lengths, self.G, self.offsets))
         self._timed("ibtt_serialize", lambda: check(lib.gtok_ibtt_serialize(
             C.byref(bc), C.byref(self.rules), _ptr(self.offsets), _ptr(self.tokens), st)))
@@ -288,6 +301,7 @@ class GraphTokenIbttPipeline(_PipelineBase):
         e_total = self.dev_in["src"].numel()
         qb = 8 * G if self.task == "shortest_path" else 0
         return {
+            "ibtt_collate": 8 * e_total + 32 * G + qb + 9 * padded_cells,
             "ibtt_lengths": 32 * G + 4 * G,
             "scan_rows": 4 * G + 8 * (G + 1),
             "ibtt_serialize": 8 * e_total + 16 * G + qb + 8 * total_tokens,

@@ -78,6 +78,9 @@ typedef struct GtokIbttRules {
   int32_t oov;           /* vocab["<pad>"]: id of any token missing from the vocab */
   int32_t node_tok_len;
   const int32_t* node_tok; /* [node_tok_len] node_tok[k] = vocab.get(str(k), oov) */
+  int32_t max_token_id;  /* upper bound on every id above incl. node_tok[] (0 = unknown); ids < 65536 let
+                            gtok_ibtt_collate stage rows as 16-bit in shared memory */
+  int32_t reserved_;
 } GtokIbttRules;
 
 /* ZINC molecular rule set (zinc_dataset_indexbase.py:143-227 + zinc_vocab.py:35-78). */
@@ -178,6 +181,16 @@ GTOK_API int gtok_scan_offsets(const int32_t* len, int64_t num_items, int64_t* o
  *      tok_out int64[off[G]], row g at tok_out[off[g] .. off[g+1]). */
 GTOK_API int gtok_ibtt_serialize(const GtokGraphBatch* batch, const GtokIbttRules* rules,
                         const int64_t* off, int64_t* tok_out, void* stream);
+
+/* K1+K4 fused  the graph-token serializer + TokenDataset + collate in one pass (external grammar +
+ *      data_loader.py:465-497): row r of the epoch is graph batch_idx[r] (or r when batch_idx is NULL - this
+ *      is the DataLoader's per-epoch shuffle), batch k = rows [k*B, min(num_rows,(k+1)*B)), written row-major
+ *      [rows_k, lmax[k]] at X + xoff[k] / attn + xoff[k] with pad_id beyond each row's length.  lmax / xoff
+ *      come from gtok_ibtt_lengths -> gtok_batch_extents -> gtok_scan_offsets (closed-form lengths: no token
+ *      is generated twice and the ragged stream never exists in HBM). */
+GTOK_API int gtok_ibtt_collate(const GtokGraphBatch* batch, const GtokIbttRules* rules, const int64_t* batch_idx,
+                               int64_t num_rows, int64_t batch_size, const int32_t* lmax, const int64_t* xoff,
+                               int64_t pad_id, int64_t* X, uint8_t* attn, void* stream);
 
 /* K2a/K2b  ZINCTokenizationDataset.tokenize_molecule + __getitem__ truncation +
  *      TokenDataset (zinc_dataset_indexbase.py:143-227, data_loader.py:465-486). */

@@ -107,6 +107,54 @@ def test_ibtt_random_shapes_vs_oracle(dev):
                 assert got.tolist() == want.tolist()
 
 
+@pytest.mark.parametrize("task", ["cycle_check", "shortest_path"])
+def test_ibtt_fused_collate_vs_oracle(dev, task):
+    """graphs -> padded batches in one kernel == reference-style encode + collate, in dataset order and under a
+    shuffled epoch order (batch_idx), with truncation, OOV node ids and a vocabulary beyond 16 bits."""
+    from gtok import engine
+    recs, texts, ex = gt_examples(task, 700, seed=5)
+    vocab, _ = O.vocab_from_texts(texts, max_tokens=40)          # small cap: many node ids fall out of the vocab
+    wide = {t: (i if i < 9 else i + 70000) for t, i in vocab.items()}
+    gb = _gb_from_recs(recs, task == "shortest_path").to(dev)
+    rng = np.random.default_rng(3)
+    perm = torch.from_numpy(rng.permutation(len(recs))[:613]).to(dev)
+    for voc, max_len, B, idx in ((vocab, 600, 128, None), (vocab, 100, 37, perm), (wide, 600, 64, perm), (vocab, 3000, 1, None)):
+        want = [np.asarray(O.encode_text(t, voc, max_len), dtype=np.int64) for t in texts]
+        ep, lens = engine.ibtt_collate_epoch(gb, voc, task, max_len, B, batch_idx=idx)
+        assert lens.cpu().tolist() == [len(w_) for w_ in want]
+        order = list(range(len(recs))) if idx is None else idx.cpu().tolist()
+        for k in range(ep.num_batches):
+            rows = [want[i] for i in order[k * B:(k + 1) * B]]
+            Xw, Aw, _ = O.collate(rows, [0] * len(rows), voc["<pad>"])
+            X, A = ep.batch(k)
+            assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw), (max_len, B, k)
+
+
+def test_ibtt_fused_collate_equals_two_step_large(dev):
+    """200k ER graphs + three 4096-node graphs (rows longer than the shared-memory row buffer: closed-form path):
+    byte-identical to gtok_ibtt_serialize followed by gtok_pad_mask_batched."""
+    from gtok import engine, synth
+    from gtok.batch import GraphBatch
+    vocab = {t: i for i, t in enumerate(["<pad>", "<bos>", "<e>", "<n>", "<q>", "<p>", "<eos>", "yes", "no"])}
+    for k in range(4096):
+        vocab[str(k)] = len(vocab)
+    vocab["has_cycle"] = len(vocab)
+    gb = synth.er_graph_token(200_000, seed=2, device=dev)
+    rag = engine.tokenize_ibtt(gb, vocab, "cycle_check", 600)
+    ep2 = engine.pad_mask_epoch(rag.tokens, rag.offsets, rag.lengths, vocab["<pad>"], 128)
+    ep1, lens = engine.ibtt_collate_epoch(gb, vocab, "cycle_check", 600, 128)
+    assert torch.equal(lens, rag.lengths) and torch.equal(ep1.xoff, ep2.xoff) and torch.equal(ep1.lmax, ep2.lmax)
+    assert torch.equal(ep1.X, ep2.X) and torch.equal(ep1.attn, ep2.attn)
+    rng = np.random.default_rng(0)
+    big = GraphBatch.from_lists([4096, 17, 4096, 4096], [list(map(tuple, rng.integers(0, 4096, (m, 2)).tolist())) if n > 17 else
+                                                        [(0, 1), (3, 16)] for n, m in ((4096, 9000), (17, 2), (4096, 1), (4096, 16000))]).to(dev)
+    rag = engine.tokenize_ibtt(big, vocab, "cycle_check", 100000)
+    ep2 = engine.pad_mask_epoch(rag.tokens, rag.offsets, rag.lengths, vocab["<pad>"], 2)
+    ep1, lens = engine.ibtt_collate_epoch(big, vocab, "cycle_check", 100000, 2)
+    assert torch.equal(lens, rag.lengths) and torch.equal(ep1.xoff, ep2.xoff)
+    assert torch.equal(ep1.X, ep2.X) and torch.equal(ep1.attn, ep2.attn)
+
+
 def test_ibtt_empty_batch(dev):
     from gtok import engine
     from gtok.batch import GraphBatch

@@ -33,7 +33,7 @@ pipe.timers = []
 ms = timeit(pipe.launch)
 k = {}
 for n, a, b in pipe.timers: k.setdefault(n, []).append(a.elapsed_time(b))
-tot, cells = int(pipe.offsets[-1]), int(pipe.xoff[-1])
+tot, cells = int(pipe.lengths.sum()), int(pipe.xoff[-1])
 algo = pipe.algorithmic_bytes(tot, cells)
 print(f"K1 ibtt graph-token G={G} tokens={tot} ms/step={ms:.3f} graphs/s={G/ms*1e3/1e6:.1f}M tokens/s={tot/ms*1e3/1e9:.1f}G")
 for n, v in k.items():

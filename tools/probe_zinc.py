@@ -54,7 +54,7 @@ def ragged():
 ms = timeit(ragged)
 tot = int(off[-1])
 byt = 12 * e_total + 4 * n_total + 16 * G + 8 * tot
-print(f"zinc_tokenize (ragged) impl={os.environ.get('GTOK_ZINC_IMPL', 'tpm')} tile={os.environ.get('GTOK_ZINC_TILE', '128')} pf={os.environ.get('GTOK_ZINC_PREFETCH', '128')}: "
+print(f"zinc_tokenize (ragged) impl={os.environ.get('GTOK_ZINC_IMPL', 'tpm')} tile={os.environ.get('GTOK_ZINC_TILE', '128')}: "
       f"{ms:.4f} ms  {G / ms / 1e3:.0f} Mgraphs/s  {byt / ms / 1e6:.0f} GB/s  frac {byt / ms / 1e6 / PEAK:.3f}")
 
 nb = (G + B - 1) // B
