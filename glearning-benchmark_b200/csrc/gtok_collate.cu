@@ -138,6 +138,25 @@ pad_mask_batched_kernel(const int64_t* __restrict__ tok, const int64_t* __restri
   }
 }
 
+// Few, large batches (large-graph sweep: 8 batches of 1024 rows of 50k tokens): one CTA per batch would leave
+// most SMs idle, so rows are dealt to ALL warps of the grid instead; each warp looks up its batch's extents.
+__global__ void __launch_bounds__(kColThreads, 8)
+pad_mask_rows_kernel(const int64_t* __restrict__ tok, const int64_t* __restrict__ row_start,
+                     const int32_t* __restrict__ row_len, const int64_t* __restrict__ batch_idx, int64_t G, int B,
+                     const int32_t* __restrict__ lmax, const int64_t* __restrict__ xoff, int64_t pad,
+                     int64_t* __restrict__ X, uint8_t* __restrict__ attn) {
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < G; r += nwarps) {
+    const int64_t k = r / B;
+    const int rr = (int)(r - k * B);
+    const int Lm = __ldg(lmax + k);
+    const int64_t i = batch_idx ? __ldg(batch_idx + r) : r;
+    const int64_t o = __ldg(xoff + k) + (int64_t)rr * Lm;
+    warp_collate_row(tok + __ldg(row_start + i), __ldg(row_len + i), Lm, pad, X + o, attn + o);
+  }
+}
+
 }  // namespace gtok
 
 extern "C" int gtok_pad_mask(const int64_t* tok, const int64_t* row_start, const int32_t* row_len,
@@ -180,8 +199,14 @@ extern "C" int gtok_pad_mask_batched(const int64_t* tok, const int64_t* row_star
   GTOK_REQUIRE(B < (1ll << 31), GTOK_EINVAL, "pad_mask_batched: batch size too large");
   const int64_t nb = (G + B - 1) / B;
   // small batches: several CTAs per SM worth of batches per wave; large batches: one batch spans the CTA's warps anyway
-  const int grid = persistent_grid(pad_mask_batched_kernel, kColThreads, 0, nb);
-  pad_mask_batched_kernel<<<grid, kColThreads, 0, (cudaStream_t)stream>>>(tok, row_start, row_len, batch_idx, G, (int)B, nb, lmax, xoff, pad_id, X, attn);
+  const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 8;      // resident CTAs of this kernel
+  if (nb >= cap) {
+    const int grid = persistent_grid(pad_mask_batched_kernel, kColThreads, 0, nb);
+    pad_mask_batched_kernel<<<grid, kColThreads, 0, (cudaStream_t)stream>>>(tok, row_start, row_len, batch_idx, G, (int)B, nb, lmax, xoff, pad_id, X, attn);
+  } else {
+    const int grid = persistent_grid(pad_mask_rows_kernel, kColThreads, 0, (G + kColWarps - 1) / kColWarps);
+    pad_mask_rows_kernel<<<grid, kColThreads, 0, (cudaStream_t)stream>>>(tok, row_start, row_len, batch_idx, G, (int)B, lmax, xoff, pad_id, X, attn);
+  }
   GTOK_CUDA_TRY(cudaGetLastError());
   return GTOK_OK;
 }

@@ -99,12 +99,13 @@ ibtt_serialize_kernel(GtokGraphBatch b, GtokIbttRules r, const int64_t* __restri
 // node: 1 token) and streamed out with pad fill + mask; longer rows use the closed form per position.
 constexpr int kIcThreads = 256;
 constexpr int kIcWarps = kIcThreads / 32;
+constexpr int kIcSpan = 4096;           // cells per work item when rows can be long
 
 template <int TASK, typename StageT>
 __global__ void __launch_bounds__(kIcThreads)
 ibtt_collate_kernel(GtokGraphBatch b, GtokIbttRules r, const int64_t* __restrict__ batch_idx, int64_t G, int B,
                     int64_t nb, const int32_t* __restrict__ lmax, const int64_t* __restrict__ xoff, int64_t pad,
-                    int row_cap, int tbl_cap, int64_t* __restrict__ X, uint8_t* __restrict__ attn) {
+                    int row_cap, int tbl_cap, int spans, int64_t* __restrict__ X, uint8_t* __restrict__ attn) {
   extern __shared__ __align__(16) unsigned char ic_smem[];
   StageT* s_tbl = reinterpret_cast<StageT*>(ic_smem);                     // node_tok[] (first tbl_cap entries)
   const int lane = lane_id(), w = threadIdx.x >> 5;
@@ -121,13 +122,22 @@ ibtt_collate_kernel(GtokGraphBatch b, GtokIbttRules r, const int64_t* __restrict
     return ((unsigned)k < (unsigned)tbl) ? __ldg(node_tok + k) : oov;
   };
 
-  for (int64_t k = blockIdx.x; k < nb; k += gridDim.x) {
+  // rows are dealt to all warps of the grid (consecutive rows -> consecutive warps), so a few huge batches
+  // (large-graph sweep) still fill the machine; each warp looks up its batch's extents
+  // Rows longer than kIcSpan cells are cut into `spans` independent work items (the closed form needs no
+  // neighbour), so a handful of 50k-token rows still occupies every warp.
+  const int64_t nwarps = (int64_t)gridDim.x * kIcWarps;
+  const int64_t items = G * spans;
+  for (int64_t item = (int64_t)blockIdx.x * kIcWarps + w; item < items; item += nwarps) {
+    const int64_t row = spans == 1 ? item : item / spans;
+    const int span = spans == 1 ? 0 : (int)(item - row * spans);
+    const int64_t k = row / B;
+    const int rr = (int)(row - k * B);
     const int Lm = __ldg(lmax + k);
+    if ((int64_t)span * kIcSpan >= Lm && span > 0) continue;
     const int64_t base = __ldg(xoff + k);
-    const int64_t r0 = k * B;
-    const int rows = (int)((G - r0 < B) ? (G - r0) : B);
-    for (int rr = w; rr < rows; rr += kIcWarps) {
-      const int64_t g = batch_idx ? __ldg(batch_idx + r0 + rr) : r0 + rr;
+    {
+      const int64_t g = batch_idx ? __ldg(batch_idx + row) : row;
       int64_t s = 0;
       if (lane < 2) s = __ldg(b.node_off + g + lane);
       else if (lane < 4) s = __ldg(b.edge_off + g + lane - 2);
@@ -144,7 +154,7 @@ ibtt_collate_kernel(GtokGraphBatch b, GtokIbttRules r, const int64_t* __restrict
         qv = __ldg(b.query_v + g);
       }
       const int64_t o = base + (int64_t)rr * Lm;
-      if (full <= row_cap) {
+      if (spans == 1 && full <= row_cap) {
         // ---- build the untruncated row in shared memory, segment by segment -------------------------
         if (lane == 0) rb[0] = (StageT)r.tok_bos;
         for (int e = lane; e < E; e += kWarp) {
@@ -186,7 +196,14 @@ ibtt_collate_kernel(GtokGraphBatch b, GtokIbttRules r, const int64_t* __restrict
           }
           return r.tok_p;
         };
-        warp_pad_row(L, Lm, pad, X + o, attn + o, tok);
+        if (spans == 1) {
+          warp_pad_row(L, Lm, pad, X + o, attn + o, tok);
+        } else {
+          const int p0 = span * kIcSpan;
+          const int plen = (span == spans - 1 || Lm - p0 < kIcSpan) ? Lm - p0 : kIcSpan;   // the last item takes the rest
+          const int vlen = L - p0 < 0 ? 0 : (L - p0 < plen ? L - p0 : plen);
+          warp_pad_row(vlen, plen, pad, X + o + p0, attn + o + p0, [&](int p) -> int { return tok(p0 + p); });
+        }
       }
     }
   }
@@ -281,15 +298,17 @@ extern "C" int gtok_ibtt_collate(const GtokGraphBatch* batch, const GtokIbttRule
   const size_t smem = (((size_t)tbl_cap * esz + 15) & ~(size_t)15) + (size_t)kIcWarps * row_cap * esz;
   cudaStream_t st = (cudaStream_t)stream;
   void (*k)(GtokGraphBatch, GtokIbttRules, const int64_t*, int64_t, int, int64_t, const int32_t*, const int64_t*, int64_t,
-            int, int, int64_t*, uint8_t*);
+            int, int, int, int64_t*, uint8_t*);
   if (rules->task == GTOK_TASK_CYCLE_CHECK)
     k = narrow ? ibtt_collate_kernel<GTOK_TASK_CYCLE_CHECK, uint16_t> : ibtt_collate_kernel<GTOK_TASK_CYCLE_CHECK, int32_t>;
   else
     k = narrow ? ibtt_collate_kernel<GTOK_TASK_SHORTEST_PATH, uint16_t> : ibtt_collate_kernel<GTOK_TASK_SHORTEST_PATH, int32_t>;
   GTOK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = persistent_grid(k, kIcThreads, smem, nb);
+  int spans = rules->max_len > 2 * kIcSpan ? (rules->max_len + kIcSpan - 1) / kIcSpan : 1;
+  if (spans > 64) spans = 64;
+  const int grid = persistent_grid(k, kIcThreads, smem, (num_rows * spans + kIcWarps - 1) / kIcWarps);
   k<<<grid, kIcThreads, smem, st>>>(*batch, *rules, batch_idx, num_rows, (int)batch_size, nb, lmax, xoff, pad_id, row_cap,
-                                    tbl_cap, X, attn);
+                                    tbl_cap, spans, X, attn);
   GTOK_CUDA_TRY(cudaGetLastError());
   return GTOK_OK;
 }
