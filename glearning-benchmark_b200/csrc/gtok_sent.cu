@@ -59,25 +59,30 @@ __device__ __forceinline__ int remap_zinc(int t, int idx_off, int node_off, int 
 }
 
 struct SentSmemLayout {
-  int rp, stage, ea, ent, bits, vis, rem, col, total;  // byte offsets inside one warp's slice
+  int rp, stage, ea, ent, bits, openb, visb, vis, rem, col, total;  // byte offsets inside one warp's slice
 };
 
-static SentSmemLayout sent_layout(int nmax, int zmax, int lcap, bool labeled, bool staged) {
+// csr_global: rowptr / col / eattr stay in HBM (read through L1/L2) - for graphs whose CSR would leave room for
+// only a couple of warps per SM (a 4096-node, 32k-entry graph needs 100 KB staged, 18 KB this way).
+static SentSmemLayout sent_layout(int nmax, int zmax, int lcap, bool labeled, bool staged, bool csr_global) {
   SentSmemLayout L;
   int o = 0;
-  L.rp = o;    o += 4 * (nmax + 1);
+  const int nwords = (nmax + 31) / 32;
+  L.rp = o;    o += csr_global ? 0 : 4 * (nmax + 1);
   L.stage = o; o += staged ? 4 * lcap : 0;
-  L.ea = o;    o += labeled ? 4 * zmax : 0;
+  L.ea = o;    o += (labeled && !csr_global) ? 4 * zmax : 0;
   L.ent = o;   o += labeled ? 4 * nmax : 0;
-  L.bits = o;  o += 4 * ((nmax + 31) / 32);
+  L.bits = o;  o += 4 * nwords;
+  L.openb = o; o += 4 * nwords;     // visited nodes that still have an unvisited neighbour
+  L.visb = o;  o += 4 * nwords;     // visited nodes
   L.vis = o;   o += 2 * nmax;
   L.rem = o;   o += 2 * nmax;
-  L.col = o;   o += 2 * zmax;
+  L.col = o;   o += csr_global ? 0 : 2 * zmax;
   L.total = (o + 15) & ~15;
   return L;
 }
 
-template <bool LABELED, bool STAGED>
+template <bool LABELED, bool STAGED, bool CSRG>
 __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch,
                             const SentSmemLayout lay, int32_t* __restrict__ len_out, int64_t* __restrict__ out,
                             int64_t stride) {
@@ -90,6 +95,8 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
   int* ea = reinterpret_cast<int*>(base + lay.ea);
   int* ent = reinterpret_cast<int*>(base + lay.ent);
   unsigned* bits = reinterpret_cast<unsigned*>(base + lay.bits);
+  unsigned* openb = reinterpret_cast<unsigned*>(base + lay.openb);
+  unsigned* visb = reinterpret_cast<unsigned*>(base + lay.visb);
   short* vis = reinterpret_cast<short*>(base + lay.vis);
   unsigned short* rem = reinterpret_cast<unsigned short*>(base + lay.rem);
   unsigned short* col = reinterpret_cast<unsigned short*>(base + lay.col);
@@ -107,16 +114,26 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
 
     // ---- stage the graph (coalesced) -----------------------------------
     const int z0 = __ldg(c.rowptr + n0);
-    for (int i = lane; i <= N; i += kWarp) rp[i] = __ldg(c.rowptr + n0 + i) - z0;
+    const int32_t* __restrict__ g_rp = c.rowptr + n0;
+    const int32_t* __restrict__ g_col = c.col + z0;
+    const int32_t* __restrict__ g_ea = LABELED ? c.eattr + z0 : nullptr;
+    auto RP = [&](int i) -> int { return CSRG ? __ldg(g_rp + i) - z0 : rp[i]; };
+    auto COL = [&](int e) -> int { return CSRG ? __ldg(g_col + e) : (int)col[e]; };
+    auto EA = [&](int e) -> int { return CSRG ? __ldg(g_ea + e) : ea[e]; };
+    if (!CSRG) for (int i = lane; i <= N; i += kWarp) rp[i] = __ldg(g_rp + i) - z0;
     for (int i = lane; i < N; i += kWarp) { vis[i] = -1; }
+    for (int i = lane; i < ((N + 31) >> 5); i += kWarp) { openb[i] = 0u; visb[i] = 0u; }
     __syncwarp();
-    const int Z = rp[N];
-    for (int i = lane; i < Z; i += kWarp) {
-      col[i] = (unsigned short)__ldg(c.col + z0 + i);
-      if (LABELED) ea[i] = __ldg(c.eattr + z0 + i);
+    if (!CSRG) {
+      const int Z = rp[N];
+      for (int i = lane; i < Z; i += kWarp) {
+        col[i] = (unsigned short)__ldg(g_col + i);
+        if (LABELED) ea[i] = __ldg(g_ea + i);
+      }
     }
-    for (int i = lane; i < N; i += kWarp) rem[i] = (unsigned short)(rp[i + 1] - rp[i]);
+    for (int i = lane; i < N; i += kWarp) rem[i] = (unsigned short)(RP(i + 1) - RP(i));
     __syncwarp();
+    int nopen = 0;                     // popcount of openb (warp-uniform)
 
     // ---- random words ----------------------------------------------------
     const uint64_t gid = (uint64_t)(ch.graph_id_base + g);
@@ -146,29 +163,42 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
         else row[pos] = cfg.remap_zinc ? remap_zinc(t, cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset) : t;
       }
     };
-    // k-th (0-based) node in [0,N) satisfying pred, ascending id; cnt_total known > k
-    auto locate = [&](auto pred, int k) -> int {
+    // k-th (0-based) set bit of an N-bit bitmap (or of its complement), ascending node id; the caller knows
+    // there are more than k.  128 words for 4096 nodes = 4 trips (the O(N) scans over vis[]/rem[] this replaces
+    // were most of the time on large graphs).
+    auto locate = [&](const unsigned* bm, bool invert, int k) -> int {
+      const int nwords = (N + 31) >> 5;
       int seen = 0, found = -1;
-      for (int v0 = 0; v0 < N && found < 0; v0 += kWarp) {
-        const int v = v0 + lane;
-        const bool f = v < N && pred(v);
-        const unsigned m = __ballot_sync(kFull, f);
-        const int cch = __popc(m);
-        if (k < seen + cch) {
-          const unsigned sel = __ballot_sync(kFull, f && (__popc(m & ((1u << lane) - 1)) == k - seen));
-          found = v0 + __ffs(sel) - 1;
+      for (int w0 = 0; w0 < nwords && found < 0; w0 += kWarp) {
+        const int wi = w0 + lane;
+        unsigned word = wi < nwords ? bm[wi] : 0u;
+        if (invert) {
+          word = wi < nwords ? ~word : 0u;
+          if (wi == nwords - 1 && (N & 31)) word &= (1u << (N & 31)) - 1u;
         }
-        seen += cch;
+        const int cw = __popc(word);
+        int incl = cw;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+          const int o = __shfl_up_sync(kFull, incl, dd);
+          if (lane >= dd) incl += o;
+        }
+        const int excl = seen + incl - cw;
+        const bool mine = k >= excl && k < excl + cw;
+        const unsigned who = __ballot_sync(kFull, mine);
+        if (who) {
+          int pos = -1;
+          if (mine) {
+            int kk = k - excl;
+            unsigned t = word;
+            while (kk--) t &= t - 1;
+            pos = (wi << 5) + __ffs(t) - 1;
+          }
+          found = __shfl_sync(kFull, pos, __ffs(who) - 1);
+        }
+        seen += __shfl_sync(kFull, incl, 31);
       }
       return found;
-    };
-    auto count = [&](auto pred) -> int {
-      int tot = 0;
-      for (int v0 = 0; v0 < N; v0 += kWarp) {
-        const int v = v0 + lane;
-        tot += __popc(__ballot_sync(kFull, v < N && pred(v)));
-      }
-      return tot;
     };
 
     int len = 0;
@@ -178,7 +208,7 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
       int nvis = 0, prev = -1;
       int cur = pick(N);
       while (len < Lcap) {
-        const int lo = rp[cur], hi = rp[cur + 1];
+        const int lo = RP(cur), hi = RP(cur + 1);
         const int vc = vis[cur];
         if (vc < 0) {
           // ---- first visit: node token [+ label], then bracketed neighbourhood set
@@ -187,22 +217,38 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
           for (int i = lane; i < nwords; i += kWarp) bits[i] = 0u;
           if (lane == 0) {
             vis[cur] = (short)nv;
+            visb[cur >> 5] |= 1u << (cur & 31);
             put(len, cfg.idx_offset + nv);
             if (LABELED) put(len + 1, cfg.node_idx_offset + __ldg(c.x + n0 + cur));
           }
           len += per;
           ++nvis;
           __syncwarp();
-          for (int e = lo + lane; e < hi; e += kWarp) {
-            const int u = col[e];
-            const int vu = vis[u];
-            rem[u] = (unsigned short)(rem[u] - 1);
-            if (vu >= 0 && u != prev && u != cur) {
-              atomicOr(&bits[vu >> 5], 1u << (vu & 31));
-              if (LABELED) ent[vu] = e;
+          int closed = 0;
+          for (int e0 = lo; e0 < hi; e0 += kWarp) {
+            const int e = e0 + lane;
+            bool z = false;
+            if (e < hi) {
+              const int u = COL(e);
+              const int vu = vis[u];
+              const int r = (int)rem[u] - 1;                    // cur stops being an unvisited neighbour of u
+              rem[u] = (unsigned short)r;
+              if (vu >= 0 && u != cur) {
+                if (r == 0) { z = true; atomicAnd(&openb[u >> 5], ~(1u << (u & 31))); }
+                if (u != prev) {
+                  atomicOr(&bits[vu >> 5], 1u << (vu & 31));
+                  if (LABELED) ent[vu] = e;
+                }
+              }
             }
+            closed += __popc(__ballot_sync(kFull, z));
           }
+          nopen -= closed;
           __syncwarp();
+          if (rem[cur] > 0) {                                   // cur joins the restart candidates
+            if (lane == 0) openb[cur >> 5] |= 1u << (cur & 31);
+            ++nopen;
+          }
           int M = 0;
           for (int w0 = 0; w0 < nwords; w0 += kWarp) {
             unsigned word = (w0 + lane < nwords) ? bits[w0 + lane] : 0u;
@@ -220,7 +266,7 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
               const int vi = ((w0 + lane) << 5) + bpos;
               const int pos = len + 1 + j * per;
               if (LABELED) {
-                put(pos, cfg.edge_idx_offset + ea[ent[vi]] + cfg.edge_label_shift);
+                put(pos, cfg.edge_idx_offset + EA(ent[vi]) + cfg.edge_label_shift);
                 put(pos + 1, cfg.idx_offset + vi);
               } else {
                 put(pos, cfg.idx_offset + vi);
@@ -245,7 +291,7 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
           int seen = 0, ne = -1;
           for (int e0 = lo; e0 < hi && ne < 0; e0 += kWarp) {
             const int e = e0 + lane;
-            const bool f = e < hi && vis[col[e]] < 0;
+            const bool f = e < hi && vis[COL(e)] < 0;
             const unsigned m = __ballot_sync(kFull, f);
             const int cch = __popc(m);
             if (k < seen + cch) {
@@ -255,20 +301,17 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
             seen += cch;
           }
           if (LABELED) {
-            if (lane == 0) put(len, cfg.edge_idx_offset + ea[ne] + cfg.edge_label_shift);
+            if (lane == 0) put(len, cfg.edge_idx_offset + EA(ne) + cfg.edge_label_shift);
             len += 1;
           }
           prev = cur;
-          cur = col[ne];
+          cur = COL(ne);
         } else {
           if (nvis == N) break;
           // ---- restart: visited nodes with unvisited neighbours, else unvisited nodes
-          auto p1 = [&](int v) { return vis[v] >= 0 && rem[v] > 0; };
-          auto p2 = [&](int v) { return vis[v] < 0; };
-          const int c1 = count(p1);
           int nxt;
-          if (c1 > 0) nxt = locate(p1, pick(c1));
-          else nxt = locate(p2, pick(N - nvis));
+          if (nopen > 0) nxt = locate(openb, false, pick(nopen));
+          else nxt = locate(visb, true, pick(N - nvis));
           if (lane == 0) put(len, RESET);
           len += 1;
           cur = nxt;
@@ -306,11 +349,11 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
   }
 }
 
-template <bool LABELED, bool STAGED>
+template <bool LABELED, bool STAGED, bool CSRG>
 static int sent_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
                        int64_t* out, int64_t stride, cudaStream_t st) {
-  const SentSmemLayout lay = sent_layout(c->max_nodes, c->max_nnz, cfg->max_length, LABELED, STAGED);
-  auto k = sent_kernel<LABELED, STAGED>;
+  const SentSmemLayout lay = sent_layout(c->max_nodes, c->max_nnz, cfg->max_length, LABELED, STAGED, CSRG);
+  auto k = sent_kernel<LABELED, STAGED, CSRG>;
   int dev = 0, max_optin = 0;
   GTOK_CUDA_TRY(cudaGetDevice(&dev));
   GTOK_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -359,10 +402,16 @@ extern "C" int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cf
     if (rc != GTOK_OK || handled) return rc;
   }
   const bool staged = cfg->max_length <= 2048;
+  // keep the CSR in HBM when staging it would leave fewer than ~8 warps per SM
+  const bool csrg = sent_layout(csr->max_nodes, csr->max_nnz, cfg->max_length, cfg->labeled != 0, staged, false).total > 24 * 1024;
   if (cfg->labeled) {
-    return staged ? sent_launch<true, true>(csr, cfg, choice, len_out, tok_out, stride, st)
-                  : sent_launch<true, false>(csr, cfg, choice, len_out, tok_out, stride, st);
+    if (csrg) return staged ? sent_launch<true, true, true>(csr, cfg, choice, len_out, tok_out, stride, st)
+                            : sent_launch<true, false, true>(csr, cfg, choice, len_out, tok_out, stride, st);
+    return staged ? sent_launch<true, true, false>(csr, cfg, choice, len_out, tok_out, stride, st)
+                  : sent_launch<true, false, false>(csr, cfg, choice, len_out, tok_out, stride, st);
   }
-  return staged ? sent_launch<false, true>(csr, cfg, choice, len_out, tok_out, stride, st)
-                : sent_launch<false, false>(csr, cfg, choice, len_out, tok_out, stride, st);
+  if (csrg) return staged ? sent_launch<false, true, true>(csr, cfg, choice, len_out, tok_out, stride, st)
+                          : sent_launch<false, false, true>(csr, cfg, choice, len_out, tok_out, stride, st);
+  return staged ? sent_launch<false, true, false>(csr, cfg, choice, len_out, tok_out, stride, st)
+                : sent_launch<false, false, false>(csr, cfg, choice, len_out, tok_out, stride, st);
 }
