@@ -2,7 +2,7 @@
 """Pretty-print a bench.py JSON line: python tools/show_bench.py gpurun_out/bench_X.json"""
 import json
 import sys
-d = json.load(open(sys.argv[1]))
+d = [json.loads(l) for l in open(sys.argv[1]) if l.startswith('{')][-1]
 print("value", round(d["value"] / 1e6, 1), "Mgraphs/s  ms/step", round(d["ms_per_step"], 4), " e2e", round(d["e2e"]["value"] / 1e6, 1),
       "Mgraphs/s  launches", d["gpu_launches"])
 for k, v in list(d["kernels"].items()) + list(d.get("kernels_two_step", {}).items()):
