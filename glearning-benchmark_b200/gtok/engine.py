@@ -121,6 +121,67 @@ def tokenize_ibtt(batch: GraphBatch, vocab: Dict[str, int], task: str, max_len: 
     return Ragged(out[:total], off, lengths)
 
 
+SPECIAL = ["<pad>", "<bos>", "<e>", "<n>", "<q>", "<p>", "<eos>", "yes", "no"]      # data_loader.py:10
+
+
+def vocab_from_graphs(batch: GraphBatch, task: str, label_tokens: Sequence[str], min_freq: int = 1,
+                      max_tokens: Optional[int] = None):
+    """build_vocab_from_texts (data_loader.py:451-463) without the texts: identical (vocab, itos) to running the
+    reference on the graph-token serialization of `batch` with label token label_tokens[g] ("yes"/"no",
+    "len3", "INF", ...).  The O(total tokens) Counter pass runs on the GPU (K5 gtok_vocab_histogram); the host
+    sorts <= max_nodes + |labels| + 1 entries by (-count, first occurrence) like Counter.most_common()."""
+    _require_cuda(batch.src)
+    G = batch.num_graphs
+    if len(label_tokens) != G:
+        raise ValueError("one label token per graph expected")
+    if task == "cycle_check":
+        tcode, tword, qtok = _lib.TASK_CYCLE_CHECK, "has_cycle", 3
+    elif task == "shortest_path":
+        tcode, tword, qtok = _lib.TASK_SHORTEST_PATH, "shortest_distance", 5
+    else:
+        raise ValueError(f"unsupported graph-token task {task!r}")
+    dev = batch.device
+    bins = int(batch.num_nodes().max()) if G else 0
+    if task == "shortest_path" and G:
+        bins = max(bins, int(batch.query_u.max()) + 1, int(batch.query_v.max()) + 1)
+    if G:
+        bins = max(bins, int(batch.src.max()) + 1 if batch.src.numel() else 0, int(batch.dst.max()) + 1 if batch.dst.numel() else 0)
+    counts = torch.empty(bins, dtype=torch.int64, device=dev)
+    first = torch.empty(bins, dtype=torch.int64, device=dev)
+    bc = _batch_c(batch, max(1, bins), 1)
+    check(lib.gtok_vocab_histogram(C.byref(bc), tcode, bins, _ptr(counts), _ptr(first), _stream()))
+    counts_h, first_h = counts.cpu().tolist(), first.cpu().tolist()
+    n_h, e_h = batch.num_nodes().cpu(), batch.num_entries().cpu()
+    items = []                                                    # (token, count, first-occurrence key)
+    for k in range(bins):
+        if counts_h[k] > 0:
+            items.append((str(k), counts_h[k], first_h[k] & 0xFFFFFFFFFFFFFFFF))
+    if G:
+        pos_q = (3 * e_h + n_h + 2)                               # position of <q> in text g
+        items.append((tword, G, (0 << 32) | int(pos_q[0] + 1)))
+        seen = {}
+        for g, lt in enumerate(label_tokens):                     # O(G) strings, not O(tokens)
+            c = seen.get(lt)
+            if c is None:
+                seen[lt] = [1, (g << 32) | int(pos_q[g] + qtok)]
+            else:
+                c[0] += 1
+        items += [(t, c[0], c[1]) for t, c in seen.items()]
+    items.sort(key=lambda it: (-it[1], it[2]))
+    vocab = {tok: i for i, tok in enumerate(SPECIAL)}
+    nxt = len(vocab)
+    for tok, c, _ in items:
+        if tok in vocab:
+            continue
+        if c < min_freq:
+            break
+        vocab[tok] = nxt
+        nxt += 1
+        if max_tokens and nxt >= max_tokens:
+            break
+    return vocab, {i: t for t, i in vocab.items()}
+
+
 def ibtt_collate_epoch(batch: GraphBatch, vocab: Dict[str, int], task: str, max_len: int, batch_size: int,
                        batch_idx: Optional[torch.Tensor] = None, max_nodes: Optional[int] = None,
                        X: Optional[torch.Tensor] = None, attn: Optional[torch.Tensor] = None):

@@ -163,6 +163,15 @@ GTOK_API int gtok_widen_i32(const void* in, int32_t elem_bytes, int64_t n, int32
 GTOK_API int gtok_counts_to_offsets(const void* counts, int32_t elem_bytes, int64_t num_items, int64_t* off_out,
                                     int32_t* tmp_i32, void* ws, size_t ws_bytes, void* stream);
 
+/* K5   token statistics for build_vocab_from_texts (data_loader.py:451-463) computed from the graphs instead
+ *      of from their serialized texts: for every node index k < num_bins, counts[k] = occurrences of the
+ *      string str(k) over all graph-token texts (edge endpoints + node list + query nodes) and first[k] =
+ *      (graph << 32 | token position) of its first occurrence (UINT64_MAX if it never occurs) - the key that
+ *      reproduces Counter.most_common()'s first-seen tie-break.  The remaining tokens (<e>, TASK words,
+ *      labels) have closed-form counts; the host finishes the vocabulary on <= num_bins + a few entries. */
+GTOK_API int gtok_vocab_histogram(const GtokGraphBatch* batch, int32_t task, int32_t num_bins, uint64_t* counts,
+                                  uint64_t* first, void* stream);
+
 /* K1a  lengths of TokenDataset sequences for graph-token graphs:
  *      min(max_len, 3E + N + 5|7)  (data_loader.py:471-484 applied to the
  *      serializer grammar).  len_out int32[G]. */

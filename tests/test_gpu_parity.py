@@ -155,6 +155,30 @@ def test_ibtt_fused_collate_equals_two_step_large(dev):
     assert torch.equal(ep1.X, ep2.X) and torch.equal(ep1.attn, ep2.attn)
 
 
+@pytest.mark.parametrize("task", ["cycle_check", "shortest_path"])
+def test_vocab_from_graphs_matches_reference_order(dev, golden_gt, task):
+    """K5: the vocabulary built from the graphs (GPU histogram + first-occurrence keys) is the dict
+    build_vocab_from_texts returns on their texts - same ids, same tie-breaks, same max_tokens / min_freq cuts."""
+    from gtok import engine
+    for G, seed in ((1000, 0), (300, 7)):
+        recs, texts, ex = gt_examples(task, G, seed=seed)
+        gb = _gb_from_recs(recs, task == "shortest_path").to(dev)
+        labs = [t.split()[t.split().index("<p>") + 1] for t in texts]
+        for max_tokens, min_freq in ((None, 1), (600, 1), (40, 1), (25, 1), (None, 900), (2000, 50)):
+            want, witos = O.vocab_from_texts(texts, min_freq=min_freq, max_tokens=max_tokens)
+            got, gitos = engine.vocab_from_graphs(gb, task, labs, min_freq=min_freq, max_tokens=max_tokens)
+            assert got == want and gitos == witos, (G, max_tokens, min_freq)
+    for t_, G, max_len, max_vocab in GT_CASES:                    # the reference's own build_vocab_from_texts output
+        if t_ != task:
+            continue
+        gold = golden_gt[f"{t_}_G{G}_L{max_len}_V{max_vocab}"]
+        recs, texts, ex = gt_examples(task, G)
+        gb = _gb_from_recs(recs, task == "shortest_path").to(dev)
+        labs = [t.split()[t.split().index("<p>") + 1] for t in texts]
+        got, _ = engine.vocab_from_graphs(gb, task, labs, max_tokens=max_vocab)
+        assert got == gold["vocab"]
+
+
 def test_ibtt_empty_batch(dev):
     from gtok import engine
     from gtok.batch import GraphBatch
