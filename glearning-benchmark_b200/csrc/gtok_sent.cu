@@ -373,6 +373,8 @@ static int sent_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const Gtok
 
 int sent_small_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
                         int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
+int sent_mid_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
+                      int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
 
 }  // namespace gtok
 
@@ -398,7 +400,10 @@ extern "C" int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cf
   {
     // graphs of at most 64 nodes: one thread per graph on 64-bit adjacency masks (gtok_sent_small.cu)
     bool handled = false;
-    const int rc = sent_small_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);
+    int rc = sent_small_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);
+    if (rc != GTOK_OK || handled) return rc;
+    // 65..256 nodes: the same scheme on 2 or 4 mask words (gtok_sent_mid.cu)
+    rc = sent_mid_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);
     if (rc != GTOK_OK || handled) return rc;
   }
   const bool staged = cfg->max_length <= 2048;

@@ -19,54 +19,11 @@
 // rows of adj64 / x / rowptr, so the L1 lines they pull are shared.
 // Random words and every decision are exactly those of the oracle (Philox-4x32-10 keyed by the
 // seed, counter = (global graph id, decision >> 2), or the explicit choice stream).
-#include "gtok_common.cuh"
+#include "gtok_sent_common.cuh"
 
 namespace gtok {
 
 namespace {
-
-constexpr int SOS = 0, RESET = 1, LADJ = 2, RADJ = 3, EOS = 4;
-constexpr int kSmallThreads = 128;
-constexpr int kSmallWarps = kSmallThreads / 32;
-
-__device__ __forceinline__ void philox10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
-                                         unsigned k1, unsigned& o0, unsigned& o1, unsigned& o2, unsigned& o3) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  o0 = c0; o1 = c1; o2 = c2; o3 = c3;
-}
-
-// trainer/train_agtt.py:193-242 (branch order preserved; oracle: remap_zinc_token)
-__device__ __forceinline__ int remap_zinc_tok(int t, int idx_off, int node_off, int edge_off) {
-  if (t == 0) return 0;
-  if (t == 1 || t == 2 || t == 3 || t == 5) return 2;
-  if (t == 4) return 1;
-  if (t >= node_off && t < edge_off) { const int a = t - node_off; return (a >= 0 && a < 9) ? 8 + a : 22 + t; }
-  if (t >= edge_off) { const int b = t - edge_off + 1; return (b >= 1 && b <= 4) ? 17 + (b - 1) : 22 + t; }
-  if (t >= idx_off && t < node_off) return 22 + (t - idx_off);
-  return 22 + t;
-}
-
-// k-th (0-based) set bit; popc(m) > k.  (__fns compiles to a long loop: 230 instr/graph in the first profile)
-__device__ __forceinline__ int select32(unsigned m, int k) {
-  int pos = 0, c;
-  c = __popc(m & 0xFFFFu); if (k >= c) { k -= c; pos = 16; m >>= 16; }
-  c = __popc(m & 0xFFu);   if (k >= c) { k -= c; pos += 8; m >>= 8; }
-  c = __popc(m & 0xFu);    if (k >= c) { k -= c; pos += 4; m >>= 4; }
-  c = __popc(m & 0x3u);    if (k >= c) { k -= c; pos += 2; m >>= 2; }
-  if (k >= (int)(m & 1u)) pos += 1;
-  return pos;
-}
-__device__ __forceinline__ int select64(unsigned long long m, int k) {
-  const unsigned lo = (unsigned)m;
-  const int cl = __popc(lo);
-  return k < cl ? select32(lo, k) : 32 + select32((unsigned)(m >> 32), k - cl);
-}
 
 struct SmallLayout {
   int o_vis, o_rem, o_ord, o_ring;   // byte offsets inside a warp slice
@@ -295,7 +252,7 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
 int sent_small_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
                         int64_t* out, int64_t stride, cudaStream_t st, bool* handled) {
   *handled = false;
-  if (c->max_nodes > 64 || (stride & 1) || c->adj64 == nullptr) return GTOK_OK;
+  if (c->max_nodes > 64 || (stride & 1) || c->adj64 == nullptr || c->adj_words > 1) return GTOK_OK;
   // largest token before the remap: node index / node label / edge label (needs the label bound)
   long long tmax = (long long)cfg->idx_offset + 64;
   bool narrow = tmax < 65536;

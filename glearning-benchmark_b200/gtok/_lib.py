@@ -46,7 +46,7 @@ class ZincVocabC(C.Structure):
 
 class CsrBatchC(C.Structure):
     _fields_ = [("num_graphs", i64), ("node_off", vp), ("rowptr", vp), ("col", vp), ("eattr", vp), ("x", vp),
-                ("query_u", vp), ("query_v", vp), ("max_nodes", i32), ("max_nnz", i32), ("max_label", i32), ("reserved_", i32), ("adj64", vp), ("order", vp)]
+                ("query_u", vp), ("query_v", vp), ("max_nodes", i32), ("max_nnz", i32), ("max_label", i32), ("adj_words", i32), ("adj64", vp), ("order", vp)]
 
 
 class SentCfgC(C.Structure):

@@ -391,7 +391,8 @@ class CsrBatch:
     max_nodes: int
     max_nnz: int
     max_label: int = 0          # labels lie in [0, max_label]; 0 = unknown
-    adj64: Optional[torch.Tensor] = None   # int64[N_total] adjacency bit rows (graphs of <= 64 nodes)
+    adj64: Optional[torch.Tensor] = None   # int64[N_total * adj_words] adjacency bit rows (graphs of <= 256 nodes)
+    adj_words: int = 1                     # 64-bit words per adjacency row (1: <= 64 nodes, 2: <= 128, 4: <= 256)
     order: Optional[torch.Tensor] = None   # int32[G] processing order (graphs sorted by work)
 
     @property
@@ -459,11 +460,13 @@ def build_csr(batch: GraphBatch, balance_window: int = 0) -> CsrBatch:
         hi = max(int(batch.x.max()), int(eattr.max()))
         max_label = hi if lo >= 0 else 0
     max_nodes = int(n.max()) if G else 1
-    adj64 = None
-    if max_nodes <= 64:
+    adj64, adj_words = None, 1
+    if max_nodes <= 256:
         # neighbours are unique, so the sum of distinct powers of two is the OR (bit 63 wraps to the sign bit)
-        adj64 = torch.zeros(Ntot, dtype=torch.int64, device=dev)
-        adj64.scatter_add_(0, rows, torch.ones_like(rows) << col_local.to(torch.int64))
+        adj_words = 1 if max_nodes <= 64 else (2 if max_nodes <= 128 else 4)
+        cl = col_local.to(torch.int64)
+        adj64 = torch.zeros(Ntot * adj_words, dtype=torch.int64, device=dev)
+        adj64.scatter_add_(0, rows * adj_words + (cl >> 6), torch.ones_like(rows) << (cl & 63))
     order = None
     if adj64 is not None and G and balance_window > 1:
         # one thread walks one graph: give the 32 lanes of a warp graphs of similar work, but only reorder
@@ -472,7 +475,7 @@ def build_csr(batch: GraphBatch, balance_window: int = 0) -> CsrBatch:
         w = torch.arange(G, device=dev) // int(balance_window)
         order = torch.argsort(w * (1 << 40) + n * 4096 + nnz_g, stable=True).to(torch.int32)
     return CsrBatch(batch.node_off, rowptr.to(torch.int32), col_local, eattr, batch.x, batch.query_u, batch.query_v,
-                    max_nodes, int(nnz_g.max()) if G else 0, max_label, adj64, order)
+                    max_nodes, int(nnz_g.max()) if G else 0, max_label, adj64, adj_words, order)
 
 
 @dataclass
@@ -502,7 +505,7 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
     lengths = torch.empty(G, dtype=torch.int32, device=dev)
     cc = _lib.CsrBatchC(G, _ptr(csr.node_off), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.eattr), _ptr(csr.x),
                         _ptr(csr.query_u), _ptr(csr.query_v), max(1, csr.max_nodes), max(0, csr.max_nnz),
-                        max(0, csr.max_label), 0, _ptr(csr.adj64), _ptr(csr.order))
+                        max(0, csr.max_label), int(csr.adj_words), _ptr(csr.adj64), _ptr(csr.order))
     sc = _lib.SentCfgC(cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset, cfg.max_length, int(cfg.labeled),
                        cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query))
     ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))

@@ -116,9 +116,9 @@ typedef struct GtokCsrBatch {
   int32_t max_nnz;           /* upper bound on CSR entries per graph (required, > 0) */
   int32_t max_label;         /* every x[] and eattr[] value lies in [0, max_label]; 0 = unknown (the
                                 thread-per-graph kernel stages labels as 8/16-bit and needs the bound) */
-  int32_t reserved_;
-  const uint64_t* adj64;     /* [N_total] optional: bit v of adj64[node_off[g]+u] set iff {u,v} is an edge of graph g
-                                (only meaningful when max_nodes <= 64; enables the thread-per-graph SENT kernel) */
+  int32_t adj_words;         /* 64-bit words per adjacency row in adj64: 0 or 1 (max_nodes <= 64), 2 (<= 128), 4 (<= 256) */
+  const uint64_t* adj64;     /* [N_total * adj_words] optional: bit v of row node_off[g]+u set iff {u,v} is an edge of
+                                graph g (enables the thread-per-graph SENT kernels; graphs up to 256 nodes) */
   const int32_t* order;      /* [G] optional processing order (a permutation of 0..G-1, e.g. graphs sorted by
                                 size so the 32 graphs of a warp take similar time); rows are still written
                                 at their own index g */

@@ -507,7 +507,7 @@ def test_sent_sharding_invariance(dev):
 
 
 # --------------------------------------------------------------------------- large graphs (BASELINE config 5)
-@pytest.mark.parametrize("N", [64, 65, 512, 4096])
+@pytest.mark.parametrize("N", [64, 65, 128, 129, 200, 256, 257, 512, 4096])
 def test_large_graph_sweep_ibtt_sent_collate(dev, N):
     """64..4096-node graphs, mean degree ~8, untruncated: IBTT rows, SENT rows (general warp-per-graph
     kernel beyond 64 nodes) and the padded batch, all against the oracle."""
@@ -543,3 +543,39 @@ def test_large_graph_sweep_ibtt_sent_collate(dev, N):
         rp, col, _ = S.canonical_csr(n, s.tolist(), d.tolist())
         want = S.sent_tokenize(n, rp, col, ocfg, S.PhiloxWords(N, g))
         assert tok[g, :ln[g]].tolist() == want.tolist(), (N, g)
+
+
+@pytest.mark.parametrize("N", [70, 128, 256])
+def test_sent_mid_labeled_truncated_replay(dev, N):
+    """65..256-node graphs on the multi-word thread-per-graph kernel: labeled mode with the ZINC remap, truncation
+    at max_length, dense graphs (brackets longer than the token ring), explicit choice stream + query append."""
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    rng = np.random.default_rng(N)
+    mols = []
+    for i in range(40):
+        n = int(rng.integers(65, N + 1)) if N > 65 else 70
+        m = int(rng.integers(n, 6 * n)) if i % 5 else int(n * (n - 1) // 3)      # every fifth graph is dense
+        s_, d_ = rng.integers(0, n, m), rng.integers(0, n, m)
+        mols.append({"n": n, "src": s_.tolist(), "dst": d_.tolist(), "x": rng.integers(0, 12, n).tolist(),
+                     "attr": rng.integers(1, 6, m).tolist()})
+    gb = GraphBatch.from_lists([m["n"] for m in mols], [list(zip(m["src"], m["dst"])) for m in mols],
+                               x_lists=[m["x"] for m in mols], attr_lists=[m["attr"] for m in mols],
+                               queries=[(int(rng.integers(0, m["n"])), int(rng.integers(0, m["n"]))) for m in mols]).to(dev)
+    csr = engine.build_csr(gb)
+    assert csr.adj_words == (2 if N <= 128 else 4)
+    nmax = max(m["n"] for m in mols)
+    for max_length, remap, append in ((20000, False, False), (301, True, False), (1000, True, True)):
+        cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 12, max_length=max_length,
+                                labeled=True, remap_zinc=remap, append_query=append)
+        tok, ln = engine.tokenize_sent(csr, cfg, seed=5)
+        tok, ln = tok.cpu(), ln.cpu().tolist()
+        ocfg = S.SentConfig(6, 6 + nmax, 6 + nmax + 12, max_length, True)
+        for g, m in enumerate(mols):
+            rp, col, ea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"])
+            want = S.sent_tokenize(m["n"], rp, col, ocfg, S.PhiloxWords(5, g), x=m["x"], eattr=ea)
+            if remap:
+                want = O.remap_zinc(want, 6, 6 + nmax, 6 + nmax + 12)
+            if append:
+                want = O.append_query(want, 6, m["n"], int(gb.query_u[g]), int(gb.query_v[g]))
+            assert tok[g, :ln[g]].tolist() == np.asarray(want).tolist(), (N, max_length, g)
