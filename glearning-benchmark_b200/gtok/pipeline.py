@@ -84,27 +84,57 @@ class _PipelineBase:
         for k, dst in self.dev_in.items():
             dst.copy_(src[k], non_blocking=True)
 
-    def upload_packed(self, host: PackedGraphBatch) -> None:
-        """compact pinned host arrays -> narrow device staging -> gtok_widen_i32 / gtok_counts_to_offsets into the
-        resident int32 layout (all async on the current stream)."""
-        st = _stream()
-        if getattr(self, "_wire", None) is None or self._wire_key != tuple(
-                (n, getattr(host, n).dtype, getattr(host, n).numel()) for n in host.ARRAYS if getattr(host, n) is not None):
-            self._wire = {n: torch.empty_like(getattr(host, n), device=self.device) for n in host.ARRAYS
-                          if getattr(host, n) is not None}
-            self._wire_key = tuple((n, getattr(host, n).dtype, getattr(host, n).numel()) for n in host.ARRAYS
-                                   if getattr(host, n) is not None)
+    # -- compact wire format, double buffered -----------------------------------------------------------------
+    def _wire_slot(self, host: PackedGraphBatch, slot: int):
+        key = tuple((n, getattr(host, n).dtype, getattr(host, n).numel()) for n in host.ARRAYS if getattr(host, n) is not None)
+        if getattr(self, "_wire", None) is None:
+            self._wire, self._wire_key, self._wire_evt, self._wire_src = [None, None], [None, None], [None, None], [None, None]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
             self._cnt_tmp = torch.empty(max(1, self.G), dtype=torch.int32, device=self.device)
+        if self._wire_key[slot] != key:
+            self._wire[slot] = {n: torch.empty_like(getattr(host, n), device=self.device) for n in host.ARRAYS
+                                if getattr(host, n) is not None}
+            self._wire_key[slot] = key
+        return self._wire[slot]
+
+    def _copy_packed(self, host: PackedGraphBatch, slot: int, stream) -> None:
+        """pinned host arrays -> the slot's narrow device staging buffers, async on `stream`."""
+        w = self._wire_slot(host, slot)
+        with torch.cuda.stream(stream):
+            for n, d in w.items():
+                d.copy_(getattr(host, n), non_blocking=True)
+            evt = torch.cuda.Event()
+            evt.record(stream)
+        self._wire_evt[slot], self._wire_src[slot] = evt, host
+
+    def upload_packed(self, host: PackedGraphBatch, prefetch: Optional[PackedGraphBatch] = None) -> None:
+        """compact pinned host arrays -> narrow device staging -> gtok_widen_i32 / gtok_counts_to_offsets into the
+        resident int32 layout.  `prefetch` (the NEXT call's input) starts travelling on a copy stream into the other
+        staging slot right away, so its PCIe time hides behind this call's kernels; a later call with that object
+        finds it already on the device."""
+        main = torch.cuda.current_stream()
+        self._wire_slot(host, 0)
+        slot = next((s_ for s_ in (0, 1) if self._wire_src[s_] is host), None)
+        if slot is None:                                  # not prefetched: copy now, on the main stream
+            slot = 0 if self._wire_src[0] is None or self._wire_src[1] is not None else 1
+            self._copy_packed(host, slot, main)
+        if prefetch is not None:
+            other = 1 - slot
+            # the other slot's last reader (the previous call's widen kernels) finished before that call returned
+            self._copy_packed(prefetch, other, self._copy_stream)
+        main.wait_event(self._wire_evt[slot])
         self._h2d_packed = host.nbytes()
-        for n, d in self._wire.items():
-            d.copy_(getattr(host, n), non_blocking=True)
-        w = self._wire
+        w = self._wire[slot]
+        st = _stream()
         for cnt, off in (("node_cnt", "node_off"), ("entry_cnt", "edge_off")):
             check(lib.gtok_counts_to_offsets(_ptr(w[cnt]), w[cnt].element_size(), self.G, _ptr(self.dev_in[off]),
                                              _ptr(self._cnt_tmp), _ptr(self.ws), self.ws_bytes, st))
         for n in ("src", "dst", "x", "edge_attr", "query_u", "query_v"):
             if n in self.dev_in and n in w:
+                if w[n].numel() > self.dev_in[n].numel():
+                    raise ValueError(f"{n}: {w[n].numel()} elements exceed the pipeline's capacity {self.dev_in[n].numel()}")
                 check(lib.gtok_widen_i32(_ptr(w[n]), w[n].element_size(), w[n].numel(), _ptr(self.dev_in[n]), st))
+        self._wire_src[slot] = None                       # consumed (a slot is reused only after this call returned)
 
     def use_device_batch(self, dev_batch: GraphBatch) -> None:
         """Point the pipeline at arrays already resident in HBM (no copy)."""
@@ -153,8 +183,13 @@ class ZincIbttPipeline(_PipelineBase):
     """BASELINE config 2: IBTT tokenization of ZINC-shaped molecules + collate."""
 
     def __init__(self, host_batch: GraphBatch, vocab: Dict[str, int], max_len: int, batch_size: int, device,
-                 fused: Optional[bool] = None, mode: str = "auto"):
-        """mode: "collate"  one kernel, molecules -> padded batches (gtok_zinc_collate; the ragged stream is
+                 fused: Optional[bool] = None, mode: str = "auto", max_nodes: Optional[int] = None,
+                 max_entries: Optional[int] = None, node_capacity: Optional[int] = None,
+                 entry_capacity: Optional[int] = None):
+        """`host_batch` sizes the buffers (graph count is fixed; node / entry totals and the per-molecule bounds can be
+        raised with max_nodes / max_entries / node_capacity / entry_capacity when a stream of different shards of
+        G graphs goes through the same pipeline).
+           mode: "collate"  one kernel, molecules -> padded batches (gtok_zinc_collate; the ragged stream is
                             never materialised), the default when the shapes allow it;
                  "ragged"   gtok_zinc_tokenize (ragged ids, kept for TokenDataset.seqs) + the K4 collate kernels;
                  "auto"     "collate" if batch_size is a multiple of 32 <= 256 and molecules are <= 64 atoms /
@@ -162,9 +197,10 @@ class ZincIbttPipeline(_PipelineBase):
         G = host_batch.num_graphs
         n = host_batch.num_nodes()
         e = host_batch.num_entries()
-        self.max_nodes = int(n.max()) if G else 1
-        self.max_entries = int(e.max()) if G else 1
-        n_total, e_total = int(host_batch.node_off[-1]), int(host_batch.edge_off[-1])
+        self.max_nodes = max(int(n.max()) if G else 1, max_nodes or 0)
+        self.max_entries = max(int(e.max()) if G else 1, max_entries or 0)
+        n_total = max(int(host_batch.node_off[-1]), node_capacity or 0)
+        e_total = max(int(host_batch.edge_off[-1]), entry_capacity or 0)
         row_bound = min(max_len, 2 * self.max_nodes + 4 * self.max_entries + 4)
         tok_cap = min(G * row_bound, 2 * n_total + 4 * e_total + 4 * G)
         super().__init__(G, n_total, e_total, tok_cap + 2, G * row_bound + 2, batch_size, device, ["x", "edge_attr"])
@@ -212,11 +248,12 @@ class ZincIbttPipeline(_PipelineBase):
             C.byref(bc), C.byref(self.zv), _ptr(self.offsets), _ptr(self.tokens), st)))
         self._collate(self.pad_id)
 
-    def run(self, host_batch) -> EpochResult:
+    def run(self, host_batch, prefetch=None) -> EpochResult:
         """Public end-to-end call: pinned host graphs in (GraphBatch, or the compact PackedGraphBatch wire
-        format), device batches + host row metadata out."""
+        format), device batches + host row metadata out.  `prefetch`: the PackedGraphBatch of the NEXT call
+        (its upload overlaps this call's kernels)."""
         if isinstance(host_batch, PackedGraphBatch):
-            self.upload_packed(host_batch)
+            self.upload_packed(host_batch, prefetch)
         else:
             self.upload(host_batch)
         self.launch()
@@ -286,9 +323,9 @@ class GraphTokenIbttPipeline(_PipelineBase):
             C.byref(bc), C.byref(self.rules), _ptr(self.offsets), _ptr(self.tokens), st)))
         self._collate(self.pad_id)
 
-    def run(self, host_batch) -> EpochResult:
+    def run(self, host_batch, prefetch=None) -> EpochResult:
         if isinstance(host_batch, PackedGraphBatch):
-            self.upload_packed(host_batch)
+            self.upload_packed(host_batch, prefetch)
         else:
             self.upload(host_batch)
         self.launch()

@@ -330,7 +330,7 @@ def test_zinc_properties_large(dev):
 def test_ingest_widen_and_packed_pipeline(dev):
     """compact wire format: widen kernels restore the int32 layout bit for bit, and the pipeline fed with a
     PackedGraphBatch produces the same batches as with the int32 GraphBatch."""
-    from gtok import synth
+    from gtok import engine, synth
     from gtok._lib import lib, check
     from gtok.batch import PackedGraphBatch
     from gtok.engine import _ptr, _stream
@@ -358,6 +358,21 @@ def test_ingest_widen_and_packed_pipeline(dev):
         assert int(b.host_xoff[-1]) == tot and torch.equal(b.host_lengths, la)
         assert torch.equal(b.padded.X[:tot], Xa[:tot]) and torch.equal(b.padded.attn[:tot], Aa[:tot])
         assert torch.equal(pipe.dev_in["node_off"].cpu(), gb.node_off) and torch.equal(pipe.dev_in["edge_off"].cpu(), gb.edge_off)
+        # double-buffered uploads: a stream of three different shards, each prefetched during its predecessor
+        shards = [synth.zinc_shaped(5000, seed=s_) for s_ in (11, 12, 13)]
+        pks = [PackedGraphBatch.from_batch(s_).pin_memory() for s_ in shards]
+        p2 = ZincIbttPipeline(shards[0], vocab, 1024, 128, dev, mode=mode, max_nodes=37, max_entries=80,
+                              node_capacity=max(int(s_.node_off[-1]) for s_ in shards),
+                              entry_capacity=max(int(s_.edge_off[-1]) for s_ in shards))
+        for i, (sh, pk_) in enumerate(zip(shards, pks)):
+            r = p2.run(pk_, prefetch=pks[i + 1] if i + 1 < len(pks) else None)
+            ref = engine.zinc_collate_epoch(sh.to(dev), vocab, 1024, 128)[0] if mode == "collate" else None
+            want_len = [len(O.zinc_ids(*[t.tolist() for t in (sh.graph(g)[3], sh.graph(g)[1], sh.graph(g)[2], sh.graph(g)[4])], vocab, 1024, 1024))
+                        for g in range(0, 5000, 617)]
+            assert [int(r.host_lengths[g]) for g in range(0, 5000, 617)] == want_len
+            if ref is not None:
+                tot = int(ref.xoff[-1])
+                assert int(r.host_xoff[-1]) == tot and torch.equal(r.padded.X[:tot], ref.X[:tot])
 
 
 # --------------------------------------------------------------------------- K4
