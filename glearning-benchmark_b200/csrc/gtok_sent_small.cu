@@ -26,7 +26,7 @@ namespace gtok {
 namespace {
 
 struct SmallLayout {
-  int o_vis, o_rem, o_ord, o_ring;   // byte offsets inside a warp slice
+  int o_vis, o_rem, o_ord, o_xs, o_ea, o_ring;   // byte offsets inside a warp slice
   int warp_bytes;
 };
 
@@ -36,12 +36,14 @@ constexpr int kRing = 64;      // ring slots per lane (tokens leave 16 at a time
 
 }  // namespace
 
-static SmallLayout small_layout(int nmax, bool labeled, int ring_elem) {
+static SmallLayout small_layout(int nmax, int zmax, bool labeled, bool stage_labels, int ring_elem) {
   SmallLayout L;
   int o = 0;
   L.o_vis = o; o += 32 * nmax;                 // u8  [v][lane]  node -> visit index
   L.o_rem = o; o += 32 * nmax;                 // u8  [v][lane]  unvisited neighbours left (visited nodes only)
   L.o_ord = o; o += labeled ? 32 * nmax : 0;   // u8  [k][lane]  visit index -> node
+  L.o_xs = o; o += (labeled && stage_labels) ? 32 * nmax : 0;   // u8 [v][lane]  node label
+  L.o_ea = o; o += (labeled && stage_labels) ? 32 * zmax : 0;   // u8 [e][lane]  edge label per CSR entry
   o = (o + 15) & ~15;
   L.o_ring = o; o += kRing * 32 * ring_elem;   // [slot][lane] pending tokens (16-bit when every token fits)
   L.warp_bytes = (o + 15) & ~15;
@@ -65,7 +67,10 @@ static SmallLayout small_layout(int nmax, bool labeled, int ring_elem) {
 //     served by the whole warp, was 15-20 % of instructions and the top stall);
 //   * one select64 site (the pick among unvisited neighbours and the restart pick share it); a bracket with
 //     one member (the common case) skips the visit-index ordering.
-template <bool LABELED, typename RingT>
+//   * labeled graphs: node and edge labels of the lane's graph are copied into shared memory as bytes before the
+//     walk (independent loads, issued back to back); the walk itself then never waits for HBM on a label (the
+//     dependent eattr / x loads were 30 % of all stall samples, profiles/r1p).
+template <bool LABELED, bool STAGE_LABELS, typename RingT>
 __global__ void __launch_bounds__(kSmallThreads)
 sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch, const SmallLayout lay,
                   int32_t* __restrict__ len_out, int64_t* __restrict__ out, int64_t stride) {
@@ -76,6 +81,8 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
   unsigned char* vis = base + lay.o_vis + lane;
   unsigned char* rem = base + lay.o_rem + lane;
   unsigned char* ord = base + lay.o_ord + lane;
+  unsigned char* xs = base + lay.o_xs + lane;
+  unsigned char* eas = base + lay.o_ea + lane;
   RingT* ring = reinterpret_cast<RingT*>(base + lay.o_ring) + lane;
   const unsigned long long* __restrict__ adj64 = reinterpret_cast<const unsigned long long*>(c.adj64);
 
@@ -120,10 +127,27 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
     auto flush_guard = [&]() {                                   // inside a long bracket: never let the ring wrap (rare)
       if (pos - flushed >= kRing - 8 && flushed + 16 <= Lcap) flush16();
     };
+    // labels into shared memory (bytes): x[0..N), eattr[rp0 .. rp0+nnz)
+    int rp0 = 0;
+    if (LABELED && STAGE_LABELS) {
+      rp0 = __ldg(c.rowptr + my_n0);
+      const int nnz = valid ? __ldg(c.rowptr + my_n0 + N) - rp0 : 0;
+      const int32_t* __restrict__ gx = c.x + my_n0;
+      const int32_t* __restrict__ ge = c.eattr + rp0;
+#pragma unroll 4
+      for (int i = 0; i < N; ++i) xs[i * 32] = (unsigned char)__ldg(gx + i);
+#pragma unroll 4
+      for (int e = 0; e < nnz; ++e) eas[e * 32] = (unsigned char)__ldg(ge + e);
+    }
     // label of CSR entry (cur -> v): rank of v inside cur's row; rp = rowptr of cur, fetched together with its adjacency
     auto edge_label = [&](int rp, int v, unsigned long long au) -> int {
       const unsigned long long below = au & ((1ull << v) - 1ull);
-      return edge_off + __ldg(c.eattr + rp + __popcll(below)) + cfg.edge_label_shift;
+      const int e = rp + __popcll(below);
+      const int a = (LABELED && STAGE_LABELS) ? (int)eas[(e - rp0) * 32] : __ldg(c.eattr + e);
+      return edge_off + a + cfg.edge_label_shift;
+    };
+    auto node_label = [&](int v) -> int {
+      return node_off + ((LABELED && STAGE_LABELS) ? (int)xs[v * 32] : __ldg(c.x + my_n0 + v));
     };
 
     // random words
@@ -171,7 +195,7 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
           vis[cur * 32] = (unsigned char)k;
           if (LABELED) ord[k * 32] = (unsigned char)cur;
           emit(idx_off + k);
-          if (LABELED) emit(node_off + __ldg(c.x + my_n0 + cur));
+          if (LABELED) emit(node_label(cur));
           unsigned long long Mall = a_cur & visited;              // visited neighbours = bracket members + the trail
           if (prev >= 0) Mall &= ~(1ull << prev);                 // predecessor (already accounted for when we left it)
           visited |= 1ull << cur;
@@ -262,11 +286,17 @@ int sent_small_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const Gto
     narrow = narrow && a < 65536 && b < 65536 && cfg->node_idx_offset >= 0 && cfg->edge_idx_offset + cfg->edge_label_shift >= 0;
   }
   narrow = narrow && cfg->idx_offset >= 0;
-  const SmallLayout lay = small_layout(c->max_nodes, cfg->labeled != 0, narrow ? 2 : 4);
+  // labels travel as bytes through shared memory when their bound allows it and the rows are molecule sized
+  const bool stage_labels = cfg->labeled && c->max_label > 0 && c->max_label < 256 && c->max_nnz <= 256;
+  const SmallLayout lay = small_layout(c->max_nodes, c->max_nnz, cfg->labeled != 0, stage_labels, narrow ? 2 : 4);
   const size_t smem = (size_t)kSmallWarps * lay.warp_bytes;
   void (*k)(GtokCsrBatch, GtokSentCfg, GtokChoice, SmallLayout, int32_t*, int64_t*, int64_t);
-  if (cfg->labeled) k = narrow ? sent_small_kernel<true, uint16_t> : sent_small_kernel<true, int32_t>;
-  else k = narrow ? sent_small_kernel<false, uint16_t> : sent_small_kernel<false, int32_t>;
+  if (cfg->labeled) {
+    if (stage_labels) k = narrow ? sent_small_kernel<true, true, uint16_t> : sent_small_kernel<true, true, int32_t>;
+    else k = narrow ? sent_small_kernel<true, false, uint16_t> : sent_small_kernel<true, false, int32_t>;
+  } else {
+    k = narrow ? sent_small_kernel<false, false, uint16_t> : sent_small_kernel<false, false, int32_t>;
+  }
   GTOK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t warps = (c->num_graphs + 31) / 32;
   const int grid = persistent_grid(k, kSmallThreads, smem, (warps + kSmallWarps - 1) / kSmallWarps);
