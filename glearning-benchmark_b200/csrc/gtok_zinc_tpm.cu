@@ -87,7 +87,6 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
   __shared__ int s_wtot[2][kTpmMaxT / 32];
   __shared__ int s_wmax[2][kTpmMaxT / 32];
   __shared__ long long s_base[2];
-  __shared__ volatile unsigned int s_ready[2];          // tile+1 once s_base[parity] is valid
   __shared__ unsigned int s_tile[2];
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -110,7 +109,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
   if (tid == 9) s_atom[9] = (StageT)v.atom_oov;
   if (tid >= 16 && tid < 20) s_bond[tid - 16] = (StageT)v.bond_tok[tid - 16];
   if (tid == 20) s_bond[4] = (StageT)v.bond_oov;
-  if (tid == 0) { s_ready[0] = 0u; s_ready[1] = 0u; s_tile[0] = atomicAdd(ticket, 1u); }
+  if (tid == 0) s_tile[0] = atomicAdd(ticket, 1u);
   const long long E_total = __ldg(b.edge_off + G), N_total = __ldg(b.node_off + G);
   const unsigned tk_bos = (unsigned)v.tok_bos, tk_atom = (unsigned)v.tok_atom, tk_bond = (unsigned)v.tok_bond;
   const int tail_tok = lane == 0 ? v.tok_q : (lane == 1 ? v.tok_regression : v.tok_p);
@@ -126,7 +125,9 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
     const int64_t g0 = t0 + 32 * w;                      // this warp's first molecule
     const int nv = (int)(g0 >= G ? 0 : ((G - g0 < 32) ? (G - g0) : 32));
 
-    // header of the tile `pf_dist` tickets ahead: its inputs are pulled into L2 while this tile computes
+    // header of the tile `pf_dist` tickets ahead: its inputs are pulled into L2 while this tile computes.  The lead has
+    // to cover the prefetch's own latency at the rate tickets are drawn (~11 tiles/us): 256-320 tickets measured best,
+    // 128 lands too late (only 28 % of the staging sectors hit L2, profiles/r1l), 512+ is slower again
     long long pe_lo = 0, pe_hi = 0, pn_lo = 0, pn_hi = 0;
     const int64_t pt0 = (tile + pf_dist) * T;
     const bool do_pf = pf_dist > 0 && tid == T - 1 && pt0 < G && vec_ok;
@@ -265,6 +266,11 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
     }
     const int my_off = wexcl + incl - my_len;            // tile-local token offset of this lane's row
     const long long pub = PADDED ? (long long)nvalid * lmax : (long long)ttotal;
+    // The other warps pick the tile's base up at named barrier 1: warp 0 ARRIVES there once the look-back is done
+    // (it never waits), they SYNC on it right before their first store.  A warp parked at a hardware barrier
+    // issues nothing - polling a shared flag instead cost 28 % of all issued instructions (profiles/r1l).
+    long long base = -1;
+    bool have_base = false;
     if (w == 0) {
       const long long tb = lookback_exclusive(status, tile, pub);
       if (lane == 0) {
@@ -273,13 +279,21 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
           if (PADDED) o.xoff_out[tile + 1] = tb + pub;
           else o.off_out[G] = tb + pub;
         }
-        __threadfence_block();
-        s_ready[par] = (unsigned)tile + 1u;
       }
+      __threadfence_block();
+      if (nwarps > 1) asm volatile("bar.arrive 1, %0;" ::"r"(T) : "memory");
+      base = tb;
+      have_base = true;
     }
+    auto wait_base = [&]() {
+      if (!have_base) {
+        asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
+        base = *reinterpret_cast<volatile long long*>(&s_base[par]);
+        have_base = true;
+      }
+    };
 
     // ---- 4. rows: the warp builds row j in a row buffer (lane i <-> atom i / bond i), then streams it out ----
-    long long base = -1;
     auto build = [&](int j, StageT* rb) {                // tokens of row j at rb[1 + r]
       const int rN = __shfl_sync(kFull, N, j), rcnt = __shfl_sync(kFull, cnt, j);
       const int reo = __shfl_sync(kFull, eo, j), rno = __shfl_sync(kFull, no, j);
@@ -355,21 +369,13 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
       fix_eos(j, rb0);
       if (two) fix_eos(j + 1, rb1);
       __syncwarp();
-      if (base < 0) {
-        while (s_ready[par] != (unsigned)tile + 1u) __nanosleep(128);
-        __threadfence_block();
-        base = s_base[par];
-      }
+      wait_base();
       flush(j, rb0);
       if (two) flush(j + 1, rb1);
       __syncwarp();                                      // row buffers drained before the next pair overwrites them
     }
+    wait_base();                                         // every warp passes barrier 1 exactly once per tile
     if (nv > 0) {
-      if (base < 0) {
-        while (s_ready[par] != (unsigned)tile + 1u) __nanosleep(128);
-        __threadfence_block();
-        base = s_base[par];
-      }
       if (lane < nv) {
         o.len_out[g0 + lane] = my_len;
         if (!PADDED) o.off_out[g0 + lane] = base + my_off;
@@ -380,7 +386,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
 }
 
 int tpm_prefetch_dist() {
-  static const int d = [] { const char* e = getenv("GTOK_ZINC_PREFETCH"); return e ? atoi(e) : 128; }();
+  static const int d = [] { const char* e = getenv("GTOK_ZINC_PREFETCH"); return e ? atoi(e) : 288; }();
   return d;
 }
 
