@@ -403,8 +403,11 @@ bool tpm_layout(int T, int max_nodes, int max_entries, int smem_optin, TpmLayout
   int o = 0;
   L.o_col = o; o += ((L.col_cap + 8) * 2 + 15) & ~15;           // +8: the aligned first / last group may spill over
   L.o_x = o; o += (L.x_cap + 8 + 15) & ~15;
-  L.o_bm = o; o += 32 * L.bm_words * 4;
-  L.o_row = o; o += 2 * L.row_cap * (int)sizeof(StageT);
+  // the pair bitmaps die with the walk, the row buffers are born after it (same warp, program order): same bytes
+  const int bm_bytes = 32 * L.bm_words * 4, row_bytes = 2 * L.row_cap * (int)sizeof(StageT);
+  L.o_bm = o;
+  L.o_row = o;
+  o += bm_bytes > row_bytes ? bm_bytes : row_bytes;
   L.warp_bytes = (o + 15) & ~15;
   L.smem = (T / 32) * L.warp_bytes;
   if (L.smem + 2048 > smem_optin) return false;
