@@ -5,8 +5,8 @@
 // PADDED variant - collate as well (data_loader.py:488-497): molecules -> padded X / attn
 // batches without the ragged stream ever touching HBM.
 //
-// Why thread per molecule: the warp-per-molecule kernels (gtok_zinc.cu, gtok_zinc_fused.cu)
-// are ISSUE bound at ~500 warp instructions per molecule (profiles/r1*): the only sequential
+// Why thread per molecule: the warp-per-molecule kernels (gtok_zinc.cu and the fused single-pass kernel this
+// file replaced, profiles/r1a..r1g) are ISSUE bound at ~500 warp instructions per molecule: the only sequential
 // part of the job, the first-seen dedupe of unordered pairs, was paid with match_any /
 // ballot / syncwarp per 32-column chunk.  Here a thread owns a molecule and walks its
 // columns against a private triangular pair bitmap, so one warp instruction advances 32
@@ -452,7 +452,7 @@ int tpm_launch(const GtokGraphBatch* batch, const GtokZincVocab* vocab, const Tp
 
 }  // namespace
 
-// Ragged single pass; called by gtok_zinc_tokenize (gtok_zinc_fused.cu) before the warp-per-molecule kernel.
+// Ragged single pass behind gtok_zinc_tokenize (below).
 int zinc_tpm_ragged(const GtokGraphBatch* batch, const GtokZincVocab* vocab, int32_t* len_out, int64_t* off_out,
                     int64_t* tok_out, int64_t tok_capacity, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled) {
   TpmOut o{};
@@ -509,5 +509,45 @@ extern "C" int gtok_zinc_collate(const GtokGraphBatch* batch, const GtokZincVoca
   if (rc != GTOK_OK) return rc;
   GTOK_REQUIRE(handled, GTOK_EUNSUPPORTED, "zinc_collate: a tile of %lld molecules with these bounds does not fit shared memory",
                (long long)batch_size);
+  return GTOK_OK;
+}
+
+extern "C" size_t gtok_zinc_tokenize_workspace_bytes(int64_t num_graphs) {
+  const int64_t tiles = (num_graphs + 31) / 32;           // smallest tile any ZINC kernel uses
+  return 16 + (size_t)(tiles > 0 ? tiles : 1) * 8;
+}
+
+extern "C" int gtok_zinc_tokenize(const GtokGraphBatch* batch, const GtokZincVocab* vocab, int32_t* len_out,
+                                  int64_t* off_out, int64_t* tok_out, int64_t tok_capacity, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(batch && vocab, GTOK_EINVAL, "zinc_tokenize: null batch/vocab");
+  GTOK_REQUIRE(batch->num_graphs >= 0, GTOK_EINVAL, "zinc_tokenize: negative graph count");
+  GTOK_REQUIRE(off_out != nullptr, GTOK_EINVAL, "zinc_tokenize: null off_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (batch->num_graphs == 0) {
+    GTOK_CUDA_TRY(cudaMemsetAsync(off_out, 0, sizeof(int64_t), st));
+    return GTOK_OK;
+  }
+  GTOK_REQUIRE(batch->node_off && batch->edge_off && batch->src && batch->dst && batch->x, GTOK_EINVAL,
+               "zinc_tokenize: null graph arrays (x is required)");
+  GTOK_REQUIRE(len_out && tok_out && ws, GTOK_EINVAL, "zinc_tokenize: null output/workspace");
+  GTOK_REQUIRE(tok_capacity >= 0, GTOK_EINVAL, "zinc_tokenize: negative capacity");
+  GTOK_REQUIRE(vocab->item_max_len >= 2 && vocab->ds_max_len >= 0, GTOK_EINVAL, "zinc_tokenize: max_len must be >= 2");
+  GTOK_REQUIRE(vocab->node_tok_len == 0 || vocab->node_tok != nullptr, GTOK_EINVAL, "zinc_tokenize: null node_tok table");
+  GTOK_REQUIRE(batch->max_nodes > 0 && batch->max_entries > 0, GTOK_EINVAL, "zinc_tokenize: max_nodes/max_entries bounds required");
+  GTOK_REQUIRE(batch->max_nodes <= 64 && batch->max_entries <= 256, GTOK_EUNSUPPORTED,
+               "zinc_tokenize: fused path covers molecules with <= 64 atoms and <= 256 edge_index columns "
+               "(got bounds %d, %d); use gtok_zinc_lengths + gtok_scan_offsets + gtok_zinc_serialize",
+               batch->max_nodes, batch->max_entries);
+  GTOK_REQUIRE((reinterpret_cast<uintptr_t>(tok_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
+               GTOK_EINVAL, "zinc_tokenize: tok_out and workspace must be 16-byte aligned");
+  const size_t need = gtok_zinc_tokenize_workspace_bytes(batch->num_graphs);
+  GTOK_REQUIRE(ws_bytes >= need, GTOK_EWORKSPACE, "zinc_tokenize: workspace %zu < %zu bytes", ws_bytes, need);
+  bool handled = false;
+  const int rc = zinc_tpm_ragged(batch, vocab, len_out, off_out, tok_out, tok_capacity, ws, ws_bytes, st, &handled);
+  if (rc != GTOK_OK) return rc;
+  GTOK_REQUIRE(handled, GTOK_EUNSUPPORTED, "zinc_tokenize: these bounds (%d atoms, %d columns) do not fit shared memory; use "
+               "gtok_zinc_lengths + gtok_scan_offsets + gtok_zinc_serialize", batch->max_nodes, batch->max_entries);
   return GTOK_OK;
 }

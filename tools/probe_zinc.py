@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """GPU probe: ZINC tokenizer kernels on 1M molecules (CUDA events, inputs resident).
-   python tools/probe_zinc.py [G] ; env GTOK_ZINC_IMPL=warp selects the warp-per-molecule kernel,
+   python tools/probe_zinc.py [G] ; env GTOK_ZINC_TILE / GTOK_ZINC_PREFETCH tune the tile size / L2 prefetch lead,
    GTOK_ZINC_CTAS_PER_SM sizes the thread-per-molecule staging."""
 import ctypes as C
 import os
@@ -54,7 +54,7 @@ def ragged():
 ms = timeit(ragged)
 tot = int(off[-1])
 byt = 12 * e_total + 4 * n_total + 16 * G + 8 * tot
-print(f"zinc_tokenize (ragged) impl={os.environ.get('GTOK_ZINC_IMPL', 'tpm')} tile={os.environ.get('GTOK_ZINC_TILE', '128')}: "
+print(f"zinc_tokenize (ragged) tile={os.environ.get('GTOK_ZINC_TILE', '128')}: "
       f"{ms:.4f} ms  {G / ms / 1e3:.0f} Mgraphs/s  {byt / ms / 1e6:.0f} GB/s  frac {byt / ms / 1e6 / PEAK:.3f}")
 
 nb = (G + B - 1) // B
