@@ -187,6 +187,55 @@ def test_ibtt_empty_batch(dev):
     assert rag.tokens.numel() == 0 and rag.offsets.cpu().tolist() == [0]
 
 
+def test_fused_entry_points_edge_cases(dev):
+    """empty inputs, ragged last batches, graphs without edges / single nodes, and the error codes of the fused
+    tokenize+collate entry points (no silent fallback: unsupported shapes raise)."""
+    import ctypes as C
+    from gtok import engine, _lib
+    from gtok._lib import lib, GtokError
+    from gtok.batch import GraphBatch
+    from gtok.engine import _ptr, _stream
+    gvoc = {t: i for i, t in enumerate(O.SPECIAL)}
+    gvoc.update({str(k): 9 + k for k in range(8)})
+    gvoc["has_cycle"] = 17
+    zvoc = O.zinc_extend_vocab(O.zinc_fixed_vocab(), [str(k) for k in range(8)] + ["X", "unknown"])
+    empty = GraphBatch.from_lists([], [], x_lists=[], attr_lists=[]).to(dev)
+    ep, lens = engine.ibtt_collate_epoch(empty, gvoc, "cycle_check", 64, 128, max_nodes=1)
+    assert ep.num_batches == 0 and lens.numel() == 0 and ep.X.numel() == 0
+    ep, lens = engine.zinc_collate_epoch(empty, zvoc, 64, 128, max_nodes=1, max_entries=1)
+    assert ep.num_batches == 0 and lens.numel() == 0 and int(ep.xoff[-1]) == 0
+    # 33 tiny graphs: no edges, single nodes, a 2-cycle listed twice; batch 32 -> ragged last batch of one row
+    nn = [1, 2, 3] * 11
+    el = [[], [(0, 1), (1, 0), (0, 1)], [(2, 0)]] * 11
+    gb = GraphBatch.from_lists(nn, el, x_lists=[[0] * n for n in nn], attr_lists=[[1] * len(e) for e in el]).to(dev)
+    ep, lens = engine.zinc_collate_epoch(gb, zvoc, 64, 32)
+    want = [O.zinc_ids([0] * n, [a for a, _ in e], [b for _, b in e], [1] * len(e), zvoc, 64, 64) for n, e in zip(nn, el)]
+    assert ep.num_batches == 2 and lens.cpu().tolist() == [len(w_) for w_ in want]
+    for k in range(2):
+        Xw, Aw, _ = O.collate(want[k * 32:(k + 1) * 32], [0] * len(want[k * 32:(k + 1) * 32]), zvoc["<pad>"])
+        X, A = ep.batch(k)
+        assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+    ep, lens = engine.ibtt_collate_epoch(gb, gvoc, "cycle_check", 64, 32)
+    wantg = [np.asarray(O.ibtt_ids(n, np.asarray([a for a, _ in e], dtype=np.int64), np.asarray([b for _, b in e], dtype=np.int64),
+                                   "cycle_check", gvoc, 64)) for n, e in zip(nn, el)]
+    for k in range(2):
+        Xw, Aw, _ = O.collate(wantg[k * 32:(k + 1) * 32], [0] * len(wantg[k * 32:(k + 1) * 32]), 0)
+        X, A = ep.batch(k)
+        assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+    # unsupported shapes raise GTOK_EUNSUPPORTED instead of falling back to anything
+    with pytest.raises(GtokError) as ei:
+        engine.zinc_collate_epoch(gb, zvoc, 64, 48)                       # batch size not a multiple of 32
+    assert ei.value.code == _lib.GTOK_EUNSUPPORTED
+    with pytest.raises(GtokError) as ei:
+        engine.zinc_collate_epoch(gb, zvoc, 64, 32, max_nodes=100)        # beyond molecule shapes
+    assert ei.value.code == _lib.GTOK_EUNSUPPORTED
+    with pytest.raises(GtokError) as ei:                                   # null pointers are EINVAL, not a crash
+        bc = engine._batch_c(gb, 3, 3)
+        zv, _t = engine.zinc_vocab_c(zvoc, 64, 64, 3, dev)
+        engine.check(lib.gtok_zinc_collate(C.byref(bc), C.byref(zv), 32, 2, None, None, _ptr(lens), None, None, 0, None, 0, _stream()))
+    assert ei.value.code == _lib.GTOK_EINVAL
+
+
 def test_ibtt_roundtrip_property_large(dev):
     """Size-independent property at scale: detokenised rows parse back (reference inverse
     parser grammar, graph_token_dataset_autograph.py:14-54) to the input edge lists, and
