@@ -414,18 +414,22 @@ class TokenDataset(Dataset):
             gb = src_ds.graph_batch.select(idx).to(self.device)
             self.ragged = engine.tokenize_zinc(gb, vocab, max_len, item_max_len=src_ds.max_len)
         else:
-            parsed = [ex.get("_graph") or graph_of_text(ex["text"]) for ex in kept]
-            if any(p is None for p in parsed):
-                bad = next(ex["text"] for ex, p in zip(kept, parsed) if p is None)
-                raise ValueError("text is not graph-token grammar and carries no graph handle; the CUDA "
-                                 f"tokenizers cannot encode it (no CPU fallback): {bad[:80]!r}")
-            tasks = {p[2] for p in parsed}
-            if len(tasks) > 1:
-                raise ValueError(f"mixed tasks in one TokenDataset: {sorted(tasks)}")
-            task = tasks.pop() if tasks else "cycle_check"
-            gb = GraphBatch.from_lists([p[0] for p in parsed], [p[1] for p in parsed],
-                                       queries=[p[3] for p in parsed] if task == "shortest_path" else None)
-            self.ragged = engine.tokenize_ibtt(gb.to(self.device), vocab, task, max_len)
+            if kept and all(ex.get("_graph") is None for ex in kept):
+                # plain strings (what load_examples returns): the texts are parsed on the GPU too
+                gb, task = engine.graphs_from_texts([ex["text"] for ex in kept], self.device)
+            else:
+                parsed = [ex.get("_graph") or graph_of_text(ex["text"]) for ex in kept]
+                if any(p is None for p in parsed):
+                    bad = next(ex["text"] for ex, p in zip(kept, parsed) if p is None)
+                    raise ValueError("text is not graph-token grammar and carries no graph handle; the CUDA "
+                                     f"tokenizers cannot encode it (no CPU fallback): {bad[:80]!r}")
+                tasks = {p[2] for p in parsed}
+                if len(tasks) > 1:
+                    raise ValueError(f"mixed tasks in one TokenDataset: {sorted(tasks)}")
+                task = tasks.pop() if tasks else "cycle_check"
+                gb = GraphBatch.from_lists([p[0] for p in parsed], [p[1] for p in parsed],
+                                           queries=[p[3] for p in parsed] if task == "shortest_path" else None).to(self.device)
+            self.ragged = engine.tokenize_ibtt(gb, vocab, task, max_len)
         host = torch.empty(self.ragged.tokens.numel(), dtype=torch.int64).pin_memory()
         host.copy_(self.ragged.tokens)
         lens = self.ragged.lengths.cpu().tolist()

@@ -66,6 +66,8 @@ PROTOTYPES = {
     "gtok_device_sm_count": (C.c_int, []),
     "gtok_widen_i32": (C.c_int, [vp, i32, i64, vp, vp]),
     "gtok_counts_to_offsets": (C.c_int, [vp, i32, i64, vp, vp, vp, C.c_size_t, vp]),
+    "gtok_text_scan": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp, vp]),
+    "gtok_text_edges": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]),
     "gtok_vocab_histogram": (C.c_int, [C.POINTER(GraphBatchC), i32, i32, vp, vp, vp]),
     "gtok_ibtt_lengths": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(IbttRulesC), vp, vp]),
     "gtok_scan_workspace_bytes": (C.c_size_t, [i64]),

@@ -124,6 +124,54 @@ def tokenize_ibtt(batch: GraphBatch, vocab: Dict[str, int], task: str, max_len: 
 SPECIAL = ["<pad>", "<bos>", "<e>", "<n>", "<q>", "<p>", "<eos>", "yes", "no"]      # data_loader.py:10
 
 
+def graphs_from_texts(texts: Sequence[str], device="cuda"):
+    """Ingest: graph-token texts -> (GraphBatch on `device`, task).  The inverse of the external serializer, run
+    per text on the host by the reference (graph_token_dataset_autograph.py:14-54 parse_graph_from_text +
+    data_loader.py:60-74 parse_query_nodes_from_text); here two kernels over the concatenated bytes
+    (gtok_text_scan / gtok_text_edges).  Raises ValueError on a text that is not of the grammar or on mixed
+    tasks - the CUDA tokenizers cannot encode such a text and there is no CPU fallback."""
+    dev = torch.device(device)
+    G = len(texts)
+    if G == 0:
+        z = torch.zeros(1, dtype=torch.int64, device=dev)
+        e = torch.zeros(0, dtype=torch.int32, device=dev)
+        return GraphBatch(z, z.clone(), e, e.clone()), "cycle_check"
+    try:
+        blob = "".join(texts).encode("ascii")
+    except UnicodeEncodeError as ex:
+        raise ValueError(f"text is not graph-token grammar (non-ASCII character): {ex}") from None
+    lens = torch.tensor([len(t) for t in texts], dtype=torch.int64)
+    off = torch.zeros(G + 1, dtype=torch.int64)
+    off[1:] = lens.cumsum(0)
+    assert int(off[-1]) == len(blob)
+    text_d = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    off_d = off.to(dev)
+    nn = torch.empty(G, dtype=torch.int32, device=dev)
+    ne = torch.empty(G, dtype=torch.int32, device=dev)
+    task = torch.empty(G, dtype=torch.int32, device=dev)
+    qu = torch.empty(G, dtype=torch.int32, device=dev)
+    qv = torch.empty(G, dtype=torch.int32, device=dev)
+    check(lib.gtok_text_scan(_ptr(text_d), _ptr(off_d), G, _ptr(nn), _ptr(ne), _ptr(task), _ptr(qu), _ptr(qv), _stream()))
+    node_off, edge_off = scan_offsets(nn), scan_offsets(ne)
+    E = int(edge_off[-1])
+    src = torch.empty(E, dtype=torch.int32, device=dev)
+    dst = torch.empty(E, dtype=torch.int32, device=dev)
+    status = torch.empty(G, dtype=torch.int32, device=dev)
+    check(lib.gtok_text_edges(_ptr(text_d), _ptr(off_d), G, _ptr(nn), _ptr(task), _ptr(edge_off), _ptr(src), _ptr(dst),
+                              _ptr(status), _stream()))
+    bad = (status == 0).nonzero()
+    if bad.numel():
+        i = int(bad[0])
+        raise ValueError("text is not graph-token grammar and carries no graph handle; the CUDA tokenizers cannot "
+                         f"encode it (no CPU fallback): {texts[i][:80]!r}")
+    t0 = int(task[0])
+    if bool((task != t0).any()):
+        raise ValueError("mixed tasks in one TokenDataset: ['cycle_check', 'shortest_path']")
+    name = "cycle_check" if t0 == _lib.TASK_CYCLE_CHECK else "shortest_path"
+    sp = name == "shortest_path"
+    return GraphBatch(node_off, edge_off, src, dst, None, None, qu if sp else None, qv if sp else None), name
+
+
 def vocab_from_graphs(batch: GraphBatch, task: str, label_tokens: Sequence[str], min_freq: int = 1,
                       max_tokens: Optional[int] = None):
     """build_vocab_from_texts (data_loader.py:451-463) without the texts: identical (vocab, itos) to running the

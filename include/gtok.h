@@ -163,6 +163,20 @@ GTOK_API int gtok_widen_i32(const void* in, int32_t elem_bytes, int64_t n, int32
 GTOK_API int gtok_counts_to_offsets(const void* counts, int32_t elem_bytes, int64_t num_items, int64_t* off_out,
                                     int32_t* tmp_i32, void* ws, size_t ws_bytes, void* stream);
 
+/* Ingest  graph-token TEXTS -> graph arrays on the GPU: the inverse of the external serializer that the reference
+ *      runs per text on the host (graph_token_dataset_autograph.py:14-54 parse_graph_from_text, data_loader.py:19-74
+ *      query / label parsers) and that the drop-in TokenDataset needs before any tokenizer can run on plain
+ *      strings.  text = the texts' ASCII bytes back to back, text_off int64[G+1].
+ *      gtok_text_scan: num_nodes / num_edges int32[G], task int32[G] (GTOK_TASK_*, or -1 when the text is not
+ *      of the grammar), query_u / query_v int32[G] (may be NULL).  The caller scans num_edges into edge_off
+ *      (gtok_scan_offsets), then gtok_text_edges writes src / dst int32[E] and status int32[G] (1 = every edge
+ *      token is a decimal, every third one is <e>, the node list is 0..N-1; 0 otherwise). */
+GTOK_API int gtok_text_scan(const uint8_t* text, const int64_t* text_off, int64_t num_texts, int32_t* num_nodes,
+                            int32_t* num_edges, int32_t* task, int32_t* query_u, int32_t* query_v, void* stream);
+GTOK_API int gtok_text_edges(const uint8_t* text, const int64_t* text_off, int64_t num_texts, const int32_t* num_nodes,
+                             const int32_t* task, const int64_t* edge_off, int32_t* src, int32_t* dst, int32_t* status,
+                             void* stream);
+
 /* K5   token statistics for build_vocab_from_texts (data_loader.py:451-463) computed from the graphs instead
  *      of from their serialized texts: for every node index k < num_bins, counts[k] = occurrences of the
  *      string str(k) over all graph-token texts (edge endpoints + node list + query nodes) and first[k] =

@@ -187,6 +187,48 @@ def test_ibtt_empty_batch(dev):
     assert rag.tokens.numel() == 0 and rag.offsets.cpu().tolist() == [0]
 
 
+@pytest.mark.parametrize("task", ["cycle_check", "shortest_path"])
+def test_text_ingest_matches_host_parser(dev, task):
+    """graph-token texts -> graph arrays on the GPU == the host inverse parser (graph_of_text, itself checked
+    against the reference's parse_graph_from_text in the host tests), incl. odd whitespace; every malformed text
+    is rejected with ValueError like the host path."""
+    from gtok import engine
+    from graph_data_loader.data_loader import graph_of_text
+    recs, texts, ex = gt_examples(task, 500, seed=13)
+    texts = list(texts)
+    texts[3] = "  " + texts[3].replace(" ", "  ") + " \n"            # runs of blanks, leading / trailing whitespace
+    texts[4] = texts[4].replace(" ", "\t", 5)
+    gb, got_task = engine.graphs_from_texts(texts, dev)
+    assert got_task == task and gb.num_graphs == len(texts)
+    cpu = gb.to("cpu")
+    for g, t in enumerate(texts):
+        n, edges, tk, q = graph_of_text(t)
+        nn, s_, d_, _, _ = cpu.graph(g)
+        assert nn == n and list(zip(s_.tolist(), d_.tolist())) == edges and tk == task
+        if task == "shortest_path":
+            assert (int(cpu.query_u[g]), int(cpu.query_v[g])) == q
+    good = texts[0]
+    toks = good.split()
+    bad_cases = [
+        " ".join(toks[1:]),                                           # no <bos>
+        good.replace("<n>", "<m>", 1),                                # no <n>
+        good.replace("<p>", "<x>", 1),                                # no <p>
+        " ".join(toks[:1] + ["x7"] + toks[2:]),                       # edge endpoint is not an integer
+        " ".join(toks[:3] + ["<f>"] + toks[4:]) if toks[3] == "<e>" else good.replace("<e>", "<f>", 1),
+        good.replace("<n> 0 1", "<n> 0 2", 1),                        # node list is not 0 1 2 ..
+        good.replace("has_cycle", "has_cycles").replace("shortest_distance", "shortest_path"),
+        "",
+        good + " \u00e9",
+    ]
+    for b_ in bad_cases:
+        assert graph_of_text(b_) is None if b_.isascii() else True
+        with pytest.raises(ValueError):
+            engine.graphs_from_texts([good, b_, good], dev)
+    other = gt_examples("shortest_path" if task == "cycle_check" else "cycle_check", 4, seed=1)[1]
+    with pytest.raises(ValueError):
+        engine.graphs_from_texts([good, other[0]], dev)               # mixed tasks
+
+
 def test_fused_entry_points_edge_cases(dev):
     """empty inputs, ragged last batches, graphs without edges / single nodes, and the error codes of the fused
     tokenize+collate entry points (no silent fallback: unsupported shapes raise)."""
