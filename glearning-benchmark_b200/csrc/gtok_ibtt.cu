@@ -128,6 +128,112 @@ ibtt_collate_kernel(GtokGraphBatch b, GtokIbttRules r, const int64_t* __restrict
   // neighbour), so a handful of 50k-token rows still occupies every warp.
   const int64_t nwarps = (int64_t)gridDim.x * kIcWarps;
   const int64_t items = G * spans;
+  if (spans == 1) {
+    // ---- the common case (rows fit the row buffer): a 2-deep software pipeline per warp -------------------
+    // row i's tokens are built and streamed out while row i+1's edge columns and row i+2's header are already
+    // in flight: with the loads issued right before their use, 63 % of all stall samples sat on them (r1q).
+    struct Hdr { int64_t g, e0; int N, E; bool valid; };
+    auto load_hdr = [&](int64_t row, Hdr& h) {
+      h.valid = row < G;
+      h.g = 0; h.e0 = 0; h.N = 0; h.E = 0;
+      if (h.valid) {
+        h.g = batch_idx ? __ldg(batch_idx + row) : row;
+        int64_t s = 0;
+        if (lane < 2) s = __ldg(b.node_off + h.g + lane);
+        else if (lane < 4) s = __ldg(b.edge_off + h.g + lane - 2);
+        const int64_t n0 = __shfl_sync(kFull, s, 0), n1 = __shfl_sync(kFull, s, 1);
+        const int64_t e0 = __shfl_sync(kFull, s, 2), e1 = __shfl_sync(kFull, s, 3);
+        h.N = (int)(n1 - n0); h.E = (int)(e1 - e0); h.e0 = e0;
+      }
+    };
+    auto load_edges = [&](const Hdr& h, int (&es)[2], int (&ed)[2]) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int e = c * kWarp + lane;
+        es[c] = 0; ed[c] = 0;
+        if (h.valid && e < h.E) { es[c] = __ldcs(b.src + h.e0 + e); ed[c] = __ldcs(b.dst + h.e0 + e); }
+      }
+    };
+    const int64_t row0 = (int64_t)blockIdx.x * kIcWarps + w;
+    Hdr h0, h1, h2;
+    int cs[2], cd[2], ns[2], nd[2];
+    load_hdr(row0, h0);
+    load_hdr(row0 + nwarps, h1);
+    load_edges(h0, cs, cd);
+    for (int64_t row = row0; row < G; row += nwarps) {
+      load_edges(h1, ns, nd);                              // next row's columns: in flight during this row's build + flush
+      load_hdr(row + 2 * nwarps, h2);
+      const int64_t k = row / B;
+      const int rr = (int)(row - k * B);
+      const int Lm = __ldg(lmax + k);
+      const int64_t o = __ldg(xoff + k) + (int64_t)rr * Lm;
+      const int N = h0.N, E = h0.E, E3 = 3 * E;
+      const long long full = 3ll * E + N + qlen;
+      const int L = (int)(full < r.max_len ? full : r.max_len);
+      const int32_t* __restrict__ src = b.src + h0.e0;
+      const int32_t* __restrict__ dst = b.dst + h0.e0;
+      int qu = 0, qv = 0;
+      if (TASK == GTOK_TASK_SHORTEST_PATH) {
+        qu = __ldg(b.query_u + h0.g);
+        qv = __ldg(b.query_v + h0.g);
+      }
+      if (full <= row_cap) {
+        if (lane == 0) rb[0] = (StageT)r.tok_bos;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int e = c * kWarp + lane;
+          if (e < E) {
+            rb[1 + 3 * e] = (StageT)node(cs[c]);
+            rb[2 + 3 * e] = (StageT)node(cd[c]);
+            rb[3 + 3 * e] = (StageT)r.tok_e;
+          }
+        }
+        for (int e = 2 * kWarp + lane; e < E; e += kWarp) {   // more than 64 edges: the rest on demand
+          rb[1 + 3 * e] = (StageT)node(__ldcs(src + e));
+          rb[2 + 3 * e] = (StageT)node(__ldcs(dst + e));
+          rb[3 + 3 * e] = (StageT)r.tok_e;
+        }
+        if (lane == 0) rb[E3 + 1] = (StageT)r.tok_n;
+        for (int i = lane; i < N; i += kWarp) rb[E3 + 2 + i] = (StageT)node(i);
+        if (lane == 0) {
+          int t = E3 + 2 + N;
+          rb[t++] = (StageT)r.tok_q;
+          rb[t++] = (StageT)r.tok_task;
+          if (TASK == GTOK_TASK_SHORTEST_PATH) { rb[t++] = (StageT)node(qu); rb[t++] = (StageT)node(qv); }
+          rb[t] = (StageT)r.tok_p;
+        }
+        __syncwarp();
+        const StageT* __restrict__ rbc = rb;
+        warp_pad_row(L, Lm, pad, X + o, attn + o, [&](int p) -> int { return (int)rbc[p]; });
+        __syncwarp();                                     // row buffer drained before the next row overwrites it
+      } else {
+        auto tok = [&](int p) -> int {                    // closed form per position (same as ibtt_serialize_kernel)
+          if (p == 0) return r.tok_bos;
+          if (p <= E3) {
+            const int e = (int)(__umulhi((unsigned)(p - 1), 0xAAAAAAABu) >> 1);
+            const int rem = (p - 1) - 3 * e;
+            if (rem == 2) return r.tok_e;
+            return node(rem == 0 ? __ldg(src + e) : __ldg(dst + e));
+          }
+          const int t = p - E3 - 1;
+          if (t == 0) return r.tok_n;
+          if (t <= N) return node(t - 1);
+          const int u = t - N - 1;
+          if (u == 0) return r.tok_q;
+          if (u == 1) return r.tok_task;
+          if (TASK == GTOK_TASK_SHORTEST_PATH) {
+            if (u == 2) return node(qu);
+            if (u == 3) return node(qv);
+          }
+          return r.tok_p;
+        };
+        warp_pad_row(L, Lm, pad, X + o, attn + o, tok);
+      }
+      h0 = h1; h1 = h2;
+      cs[0] = ns[0]; cs[1] = ns[1]; cd[0] = nd[0]; cd[1] = nd[1];
+    }
+    return;
+  }
   for (int64_t item = (int64_t)blockIdx.x * kIcWarps + w; item < items; item += nwarps) {
     const int64_t row = spans == 1 ? item : item / spans;
     const int span = spans == 1 ? 0 : (int)(item - row * spans);
