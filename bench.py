@@ -229,7 +229,19 @@ def run_extras(dev, G, peak):
         byt = csr.sent_input_bytes(labeled) + 8 * tot + 4 * G
         out[name] = {"ms_per_step": ms, "graphs_per_s": G / ms * 1e3, "tokens_per_s": tot / ms * 1e3,
                      "mean_len": tot / G, "algo_bytes": byt, "GBps": byt / ms / 1e6, "frac": byt / ms / 1e6 / peak}
-        del buf
+        # the whole AGTT epoch: fresh trails + collate_fn (pad id 5, train_agtt.py:276-302) of every batch of 128
+        row_start = torch.arange(G, device=dev, dtype=torch.int64) * stride
+        ep = engine.pad_mask_epoch(buf.view(-1), row_start, ln, 5, BATCH)
+        cells = int(ep.xoff[-1])
+        X, A = ep.X, ep.attn
+
+        # (timed as two stages: buffers sized for this seed's trails could be too small for another seed's)
+        ms_c = timeit(lambda: engine.pad_mask_epoch(buf.view(-1), row_start, ln, 5, BATCH, X=X, attn=A), 5, 2)
+        out[name]["collate_ms"] = ms_c
+        out[name]["collate_frac"] = (8 * tot + 9 * cells) / ms_c / 1e6 / peak
+        out[name]["epoch_ms"] = ms + ms_c
+        out[name]["epoch_graphs_per_s"] = G / (ms + ms_c) * 1e3
+        del buf, X, A, ep
 
     sent("sent_graph_token", gb, engine.SentConfig(idx_offset=6, max_length=600), 600, False, 2048)
     out["sent_graph_token"]["workload"] = f"{G} ER graph-token graphs, unlabeled SENT, max_length 600, Philox-seeded (BASELINE configs[2])"

@@ -11,6 +11,7 @@ print("  roofline", d["roofline"])
 print("  step_roofline", round(d["step_roofline"]["frac"], 3), d["clocks"])
 print("  cpu_baseline", d.get("cpu_baseline"))
 for k, v in (d.get("extras") or {}).items():
-    print(f"  extra {k}: {v.get('ms_per_step'):.3f} ms/step  {v.get('graphs_per_s', 0) / 1e6:.0f} Mgraphs/s  frac {v.get('frac')}")
+    print(f"  extra {k}: {v.get('ms_per_step'):.3f} ms/step  {v.get('graphs_per_s', 0) / 1e6:.0f} Mgraphs/s  frac {v.get('frac')}" +
+          (f"  | +collate {v['collate_ms']:.3f} ms (frac {v['collate_frac']:.2f}) -> epoch {v['epoch_graphs_per_s'] / 1e6:.0f} Mgraphs/s" if 'collate_ms' in v else ""))
     for kk, vv in (v.get("kernels") or {}).items():
         print(f"      {kk:18s} {vv['ms']:.4f} ms  {vv['GBps']:7.0f} GB/s  frac {vv['frac']:.3f}")
