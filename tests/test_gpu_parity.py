@@ -651,9 +651,9 @@ def test_large_graph_sweep_ibtt_sent_collate(dev, N):
         assert tok[g, :ln[g]].tolist() == want.tolist(), (N, g)
 
 
-@pytest.mark.parametrize("N", [70, 128, 256])
+@pytest.mark.parametrize("N", [70, 128, 256, 300, 700])
 def test_sent_mid_labeled_truncated_replay(dev, N):
-    """65..256-node graphs on the multi-word thread-per-graph kernel: labeled mode with the ZINC remap, truncation
+    """65..256-node graphs on the multi-word thread-per-graph kernel, larger ones on the CSR thread-per-graph kernel: labeled mode with the ZINC remap, truncation
     at max_length, dense graphs (brackets longer than the token ring), explicit choice stream + query append."""
     from gtok import engine
     from gtok.batch import GraphBatch
@@ -661,7 +661,7 @@ def test_sent_mid_labeled_truncated_replay(dev, N):
     mols = []
     for i in range(40):
         n = int(rng.integers(65, N + 1)) if N > 65 else 70
-        m = int(rng.integers(n, 6 * n)) if i % 5 else int(n * (n - 1) // 3)      # every fifth graph is dense
+        m = int(rng.integers(n, 6 * n)) if i % 5 else int(min(n * (n - 1) // 3, 20000))      # every fifth graph is dense
         s_, d_ = rng.integers(0, n, m), rng.integers(0, n, m)
         mols.append({"n": n, "src": s_.tolist(), "dst": d_.tolist(), "x": rng.integers(0, 12, n).tolist(),
                      "attr": rng.integers(1, 6, m).tolist()})
@@ -669,7 +669,10 @@ def test_sent_mid_labeled_truncated_replay(dev, N):
                                x_lists=[m["x"] for m in mols], attr_lists=[m["attr"] for m in mols],
                                queries=[(int(rng.integers(0, m["n"])), int(rng.integers(0, m["n"]))) for m in mols]).to(dev)
     csr = engine.build_csr(gb)
-    assert csr.adj_words == (2 if N <= 128 else 4)
+    if N <= 256:
+        assert csr.adj_words == (2 if N <= 128 else 4)
+    else:
+        assert csr.adj64 is None
     nmax = max(m["n"] for m in mols)
     for max_length, remap, append in ((20000, False, False), (301, True, False), (1000, True, True)):
         cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 12, max_length=max_length,
