@@ -202,24 +202,53 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
           const unsigned long long C0 = a_cur & ~visited;
           rem[cur * 32] = (unsigned char)__popcll(C0);
           if (C0) open |= 1ull << cur;
-          unsigned long long V = 0ull;                            // bracket members in visit-index space
-          while (Mall) {
-            const int u = __ffsll((long long)Mall) - 1;
-            Mall &= Mall - 1;
-            const int r = (int)rem[u * 32] - 1;                   // cur is no longer an unvisited neighbour of u
-            rem[u * 32] = (unsigned char)r;
-            if (r == 0) open &= ~(1ull << u);
-            V |= 1ull << vis[u * 32];
-          }
-          if (V) {
+          // Mall: bracket members (visited neighbours except the trail predecessor).  Each one loses cur as an
+          // unvisited neighbour; their visit indices, OR-ed into V, enumerate ascending without a sort.  The loops
+          // run on 32-bit halves (a 64-bit find-first-set / clear-lowest pair costs twice the instructions).
+          if (Mall) {
             emit(LADJ);
-            do {
-              const int jv = __ffsll((long long)V) - 1;
-              V &= V - 1;
-              if (LABELED) emit(edge_label(rp_cur, (int)ord[jv * 32], a_cur));
+            auto close_member = [&](int u) -> int {             // counter update of member u -> its visit index
+              const int r = (int)rem[u * 32] - 1;               // cur is no longer an unvisited neighbour of u
+              rem[u * 32] = (unsigned char)r;
+              if (r == 0) open &= ~(1ull << u);
+              return (int)vis[u * 32];
+            };
+            if ((Mall & (Mall - 1)) == 0ull) {                  // one member (the common case): nothing to order
+              const int u = __ffsll((long long)Mall) - 1;
+              const int jv = close_member(u);
+              if (LABELED) emit(edge_label(rp_cur, u, a_cur));
               emit(idx_off + jv);
-              flush_guard();
-            } while (V);
+            } else {
+              unsigned vlo = 0u, vhi = 0u;
+              unsigned mlo = (unsigned)Mall, mhi = (unsigned)(Mall >> 32);
+              while (mlo) {
+                const int u = __ffs((int)mlo) - 1;
+                mlo &= mlo - 1;
+                const int jv = close_member(u);
+                if (jv < 32) vlo |= 1u << jv; else vhi |= 1u << (jv - 32);
+              }
+              while (mhi) {
+                const int u = 32 + __ffs((int)mhi) - 1;
+                mhi &= mhi - 1;
+                const int jv = close_member(u);
+                if (jv < 32) vlo |= 1u << jv; else vhi |= 1u << (jv - 32);
+              }
+              const bool longb = __popc(vlo) + __popc(vhi) > 10;  // only a long bracket can outrun the ring
+              while (vlo) {
+                const int jv = __ffs((int)vlo) - 1;
+                vlo &= vlo - 1;
+                if (LABELED) emit(edge_label(rp_cur, (int)ord[jv * 32], a_cur));
+                emit(idx_off + jv);
+                if (longb) flush_guard();
+              }
+              while (vhi) {
+                const int jv = 32 + __ffs((int)vhi) - 1;
+                vhi &= vhi - 1;
+                if (LABELED) emit(edge_label(rp_cur, (int)ord[jv * 32], a_cur));
+                emit(idx_off + jv);
+                if (longb) flush_guard();
+              }
+            }
             emit(RADJ);
           }
         } else {
@@ -236,7 +265,8 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
             emit(RESET);
           }
           const int nsel = __popcll(sel);
-          const int nxt = select64(sel, pick(nsel));
+          const int kth = pick(nsel);                             // one word per event, also when there is no choice
+          const int nxt = nsel == 1 ? __ffsll((long long)sel) - 1 : select64(sel, kth);
           a_nxt = __ldg(arow + nxt);
           if (LABELED) rp_nxt = __ldg(c.rowptr + my_n0 + nxt);
           if (C) {                                                // trail step: nxt stops being an unvisited neighbour of cur
