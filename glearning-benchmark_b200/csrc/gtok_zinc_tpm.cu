@@ -79,7 +79,7 @@ template <typename StageT, bool HAS_ATTR, bool PADDED>
 __global__ void __launch_bounds__(kTpmMaxT)
 zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v, const TpmLayout lay, const TpmOut o,
                 unsigned int* __restrict__ ticket, unsigned long long* __restrict__ status, const int vec_ok,
-                const int pf_dist) {
+                const int pf_dist, const uint16_t* __restrict__ p_col16, const uint8_t* __restrict__ p_x8) {
   extern __shared__ __align__(16) unsigned char t_smem[];
   __shared__ StageT s_nt[64];
   __shared__ StageT s_atom[10];
@@ -151,7 +151,9 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
     // header-only rows instead of corrupting shared memory
     const bool fits = Et <= lay.col_cap && Nt <= lay.x_cap && Et >= 0 && Nt >= 0;
     if (!fits) { Et = 0; Nt = 0; }
-    const long long E0a = vec_ok ? (E0 & ~3ll) : E0, N0a = vec_ok ? (N0 & ~3ll) : N0;   // staged index 0
+    const bool packed = p_col16 != nullptr;             // columns arrive as 16-bit words (u6 | v6 << 6 | attr4 << 12), atoms as bytes
+    const long long E0a = packed ? (E0 & ~7ll) : (vec_ok ? (E0 & ~3ll) : E0);           // staged index 0
+    const long long N0a = packed ? (N0 & ~15ll) : (vec_ok ? (N0 & ~3ll) : N0);
     const int eo = (int)(e_lo - E0a), no = (int)(n_lo - N0a);
     const int Ed = fits ? (int)(e_hi - e_lo) : 0;
     const int N = fits ? (int)(n_hi - n_lo) : 0;
@@ -160,10 +162,29 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
     {
       auto pack = [&](int a, int c, int t) -> unsigned {
         const unsigned aa = min((unsigned)a, nclamp), cc = min((unsigned)c, nclamp);
-        const unsigned bb = HAS_ATTR ? min((unsigned)(t - 1), 4u) : 4u;
+        const unsigned bb = HAS_ATTR ? min((unsigned)t, 15u) : 0u;   // raw edge_attr, 4 bits (0 / 5.. = 'unknown')
         return aa | (cc << 6) | (bb << 12);
       };
-      if (vec_ok) {
+      if (packed) {
+        // the wire / compact resident format IS the staged format: 16-byte copies, nothing to pack
+        const long long j0 = E0a >> 3, j1 = (E0 + Et + 7) >> 3, j1v = min(j1, E_total >> 3);
+        const uint4* __restrict__ c4g = reinterpret_cast<const uint4*>(p_col16);
+        uint4* c4 = reinterpret_cast<uint4*>(s_col);
+#pragma unroll 4
+        for (long long j = j0 + lane; j < j1v; j += 32) c4[j - j0] = __ldcs(c4g + j);
+        if (j1v < j1) {
+          const long long e = (j1v << 3) + lane;
+          if (lane < 8 && e < E_total) s_col[e - E0a] = p_col16[e];
+        }
+        const long long i0 = N0a >> 4, i1 = (N0 + Nt + 15) >> 4, i1v = min(i1, N_total >> 4);
+        const uint4* __restrict__ x4g = reinterpret_cast<const uint4*>(p_x8);
+        uint4* x4s = reinterpret_cast<uint4*>(s_x);
+        for (long long j = i0 + lane; j < i1v; j += 32) x4s[j - i0] = __ldcs(x4g + j);
+        if (i1v < i1) {
+          const long long e = (i1v << 4) + lane;
+          if (lane < 16 && e < N_total) s_x[e - N0a] = p_x8[e];
+        }
+      } else if (vec_ok) {
         const long long j0 = E0a >> 2, j1 = (E0 + Et + 3) >> 2, j1v = min(j1, E_total >> 2);
         const int4* __restrict__ s4 = reinterpret_cast<const int4*>(g_src);
         const int4* __restrict__ d4 = reinterpret_cast<const int4*>(g_dst);
@@ -213,10 +234,21 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + a), "r"(bytes) : "memory");
         }
       };
-      pf(g_src, pe_lo, pe_hi, E_total);
-      pf(g_dst, pe_lo, pe_hi, E_total);
-      if (HAS_ATTR) pf(g_attr, pe_lo, pe_hi, E_total);
-      pf(g_x, pn_lo, pn_hi, N_total);
+      if (packed) {
+        auto pfb = [&](const void* p, long long lo, long long hi, long long total, int esz) {   // byte ranges, 16-byte granules
+          long long a = (lo * esz) & ~15ll, z = (hi * esz + 15) & ~15ll;
+          if (z > total * esz) z = (total * esz) & ~15ll;
+          if (z > a)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(static_cast<const char*>(p) + a), "r"((unsigned)(z - a)) : "memory");
+        };
+        pfb(p_col16, pe_lo, pe_hi, E_total, 2);
+        pfb(p_x8, pn_lo, pn_hi, N_total, 1);
+      } else {
+        pf(g_src, pe_lo, pe_hi, E_total);
+        pf(g_dst, pe_lo, pe_hi, E_total);
+        if (HAS_ATTR) pf(g_attr, pe_lo, pe_hi, E_total);
+        pf(g_x, pn_lo, pn_hi, N_total);
+      }
     }
     __syncwarp();
 
@@ -228,7 +260,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
 #pragma unroll 1
       for (int i = 0; i < Ed; ++i) {
         const unsigned wv = colp[i];
-        const unsigned a = wv & 63u, c = (wv >> 6) & 63u;
+        const unsigned a = min(wv & 63u, nclamp), c = min((wv >> 6) & 63u, nclamp);   // (packed input is not clamped at staging)
         const unsigned mn = min(a, c), mx = max(a, c);
         const unsigned idx = ((mx * (mx + 1u)) >> 1) + mn;
         const unsigned wd = (idx >> 5) * 32u, bit = 1u << (idx & 31u);
@@ -298,11 +330,11 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
       const int rN = __shfl_sync(kFull, N, j), rcnt = __shfl_sync(kFull, cnt, j);
       const int reo = __shfl_sync(kFull, eo, j), rno = __shfl_sync(kFull, no, j);
       if (lane == 0) rb[1] = (StageT)tk_bos;
-      for (int i = lane; i < rN; i += 32) put2(rb, 2 + 2 * i, tk_atom, (unsigned)s_atom[s_x[rno + i]]);
+      for (int i = lane; i < rN; i += 32) put2(rb, 2 + 2 * i, tk_atom, (unsigned)s_atom[min((unsigned)s_x[rno + i], 9u)]);
       const int bb = 2 + 2 * rN;
       for (int k = lane; k < rcnt; k += 32) {
         const unsigned wv = s_col[reo + k];
-        put2(rb, bb + 4 * k, tk_bond, (unsigned)s_bond[wv >> 12]);
+        put2(rb, bb + 4 * k, tk_bond, (unsigned)s_bond[min((wv >> 12) - 1u, 4u)]);
         put2(rb, bb + 4 * k + 2, (unsigned)s_nt[wv & 63u], (unsigned)s_nt[(wv >> 6) & 63u]);
       }
       if (lane < 3) rb[bb + 4 * rcnt + lane] = (StageT)tail_tok;
@@ -401,8 +433,8 @@ bool tpm_layout(int T, int max_nodes, int max_entries, int smem_optin, TpmLayout
   L.x_cap = 32 * L.nmax;
   L.row_cap = (2 * L.nmax + 4 * max_entries + 8 + 7) & ~7;      // untruncated row + slack, keeps buffers 16-byte aligned
   int o = 0;
-  L.o_col = o; o += ((L.col_cap + 8) * 2 + 15) & ~15;           // +8: the aligned first / last group may spill over
-  L.o_x = o; o += (L.x_cap + 8 + 15) & ~15;
+  L.o_col = o; o += ((L.col_cap + 16) * 2 + 15) & ~15;          // slack: the aligned first / last 16-byte group may spill over
+  L.o_x = o; o += (L.x_cap + 32 + 15) & ~15;
   // the pair bitmaps die with the walk, the row buffers are born after it (same warp, program order): same bytes
   const int bm_bytes = 32 * L.bm_words * 4, row_bytes = 2 * L.row_cap * (int)sizeof(StageT);
   L.o_bm = o;
@@ -417,7 +449,7 @@ bool tpm_layout(int T, int max_nodes, int max_entries, int smem_optin, TpmLayout
 
 template <typename StageT, bool PADDED>
 int tpm_launch(const GtokGraphBatch* batch, const GtokZincVocab* vocab, const TpmOut& o, int T_fixed, void* ws,
-               size_t ws_bytes, cudaStream_t st, bool* handled) {
+               size_t ws_bytes, cudaStream_t st, bool* handled, const uint16_t* col16 = nullptr, const uint8_t* x8 = nullptr) {
   *handled = false;
   int dev = 0, optin = 0;
   GTOK_CUDA_TRY(cudaGetDevice(&dev));
@@ -436,15 +468,15 @@ int tpm_launch(const GtokGraphBatch* batch, const GtokZincVocab* vocab, const Tp
   const int64_t tiles = (batch->num_graphs + lay.T - 1) / lay.T;
   const size_t need = 16 + (size_t)tiles * 8;
   GTOK_REQUIRE(ws_bytes >= need, GTOK_EWORKSPACE, "zinc tokenizer: workspace %zu < %zu bytes", ws_bytes, need);
-  auto k = batch->edge_attr ? zinc_tpm_kernel<StageT, true, PADDED> : zinc_tpm_kernel<StageT, false, PADDED>;
+  auto k = (batch->edge_attr || col16) ? zinc_tpm_kernel<StageT, true, PADDED> : zinc_tpm_kernel<StageT, false, PADDED>;
   GTOK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
   GTOK_CUDA_TRY(cudaMemsetAsync(ws, 0, need, st));
   const int grid = persistent_grid(k, lay.T, (size_t)lay.smem, tiles);
-  const int vec_ok = ((reinterpret_cast<uintptr_t>(batch->src) | reinterpret_cast<uintptr_t>(batch->dst) |
-                       reinterpret_cast<uintptr_t>(batch->edge_attr) | reinterpret_cast<uintptr_t>(batch->x)) & 15) == 0;
+  const int vec_ok = col16 ? 1 : ((reinterpret_cast<uintptr_t>(batch->src) | reinterpret_cast<uintptr_t>(batch->dst) |
+                                   reinterpret_cast<uintptr_t>(batch->edge_attr) | reinterpret_cast<uintptr_t>(batch->x)) & 15) == 0;
   k<<<grid, lay.T, lay.smem, st>>>(*batch, *vocab, lay, o, reinterpret_cast<unsigned int*>(ws),
                                    reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + 16), vec_ok,
-                                   tpm_prefetch_dist());
+                                   tpm_prefetch_dist(), col16, x8);
   GTOK_CUDA_TRY(cudaGetLastError());
   *handled = true;
   return GTOK_OK;
@@ -549,5 +581,49 @@ extern "C" int gtok_zinc_tokenize(const GtokGraphBatch* batch, const GtokZincVoc
   if (rc != GTOK_OK) return rc;
   GTOK_REQUIRE(handled, GTOK_EUNSUPPORTED, "zinc_tokenize: these bounds (%d atoms, %d columns) do not fit shared memory; use "
                "gtok_zinc_lengths + gtok_scan_offsets + gtok_zinc_serialize", batch->max_nodes, batch->max_entries);
+  return GTOK_OK;
+}
+
+extern "C" int gtok_zinc_collate_packed(const GtokPackedMolBatch* pk, const GtokZincVocab* vocab, int64_t batch_size,
+                                        int64_t pad_id, int32_t* len_out, int32_t* lmax_out, int64_t* xoff_out, int64_t* X,
+                                        uint8_t* attn, int64_t x_capacity, void* ws, size_t ws_bytes, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(pk && vocab, GTOK_EINVAL, "zinc_collate_packed: null batch/vocab");
+  GTOK_REQUIRE(pk->num_graphs >= 0, GTOK_EINVAL, "zinc_collate_packed: negative graph count");
+  GTOK_REQUIRE(xoff_out != nullptr, GTOK_EINVAL, "zinc_collate_packed: null xoff_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pk->num_graphs == 0) {
+    GTOK_CUDA_TRY(cudaMemsetAsync(xoff_out, 0, sizeof(int64_t), st));
+    return GTOK_OK;
+  }
+  GTOK_REQUIRE(pk->node_off && pk->edge_off && pk->col16 && pk->x8, GTOK_EINVAL, "zinc_collate_packed: null graph arrays");
+  GTOK_REQUIRE(len_out && lmax_out && X && attn && ws, GTOK_EINVAL, "zinc_collate_packed: null output/workspace");
+  GTOK_REQUIRE(x_capacity >= 0, GTOK_EINVAL, "zinc_collate_packed: negative capacity");
+  GTOK_REQUIRE(vocab->item_max_len >= 2 && vocab->ds_max_len >= 0, GTOK_EINVAL, "zinc_collate_packed: max_len must be >= 2");
+  GTOK_REQUIRE(vocab->node_tok_len == 0 || vocab->node_tok != nullptr, GTOK_EINVAL, "zinc_collate_packed: null node_tok table");
+  GTOK_REQUIRE(pk->max_nodes > 0 && pk->max_entries > 0, GTOK_EINVAL, "zinc_collate_packed: max_nodes/max_entries bounds required");
+  GTOK_REQUIRE(batch_size >= 32 && batch_size <= kTpmMaxT && (batch_size & 31) == 0, GTOK_EUNSUPPORTED,
+               "zinc_collate_packed: batch size must be a multiple of 32 in [32, %d] (got %lld)", kTpmMaxT, (long long)batch_size);
+  GTOK_REQUIRE(pk->max_nodes <= 64 && pk->max_entries <= 256, GTOK_EUNSUPPORTED,
+               "zinc_collate_packed: covers molecules with <= 64 atoms and <= 256 edge_index columns (got bounds %d, %d)",
+               pk->max_nodes, pk->max_entries);
+  GTOK_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(pk->col16) |
+                 reinterpret_cast<uintptr_t>(pk->x8)) & 15) == 0, GTOK_EINVAL,
+               "zinc_collate_packed: X, workspace, col16 and x8 must be 16-byte aligned");
+  GtokGraphBatch b{};
+  b.num_graphs = pk->num_graphs; b.node_off = pk->node_off; b.edge_off = pk->edge_off;
+  b.max_nodes = pk->max_nodes; b.max_entries = pk->max_entries;
+  TpmOut o{};
+  o.len_out = len_out; o.lmax_out = lmax_out; o.xoff_out = xoff_out; o.X = X; o.attn = attn;
+  o.x_capacity = x_capacity; o.pad = pad_id;
+  bool handled = false;
+  int rc;
+  if (vocab->max_token_id > 0 && vocab->max_token_id < 65536)
+    rc = tpm_launch<uint16_t, true>(&b, vocab, o, (int)batch_size, ws, ws_bytes, st, &handled, pk->col16, pk->x8);
+  else
+    rc = tpm_launch<int32_t, true>(&b, vocab, o, (int)batch_size, ws, ws_bytes, st, &handled, pk->col16, pk->x8);
+  if (rc != GTOK_OK) return rc;
+  GTOK_REQUIRE(handled, GTOK_EUNSUPPORTED, "zinc_collate_packed: a tile of %lld molecules with these bounds does not fit shared memory",
+               (long long)batch_size);
   return GTOK_OK;
 }

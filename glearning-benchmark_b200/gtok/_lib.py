@@ -31,6 +31,11 @@ class GraphBatchC(C.Structure):
                 ("max_nodes", i32), ("max_entries", i32)]
 
 
+class PackedMolBatchC(C.Structure):
+    _fields_ = [("num_graphs", i64), ("node_off", vp), ("edge_off", vp), ("col16", vp), ("x8", vp),
+                ("max_nodes", i32), ("max_entries", i32)]
+
+
 class IbttRulesC(C.Structure):
     _fields_ = [("task", i32), ("max_len", i32), ("tok_bos", i32), ("tok_e", i32), ("tok_n", i32),
                 ("tok_q", i32), ("tok_p", i32), ("tok_task", i32), ("oov", i32), ("node_tok_len", i32),
@@ -81,6 +86,8 @@ PROTOTYPES = {
     "gtok_zinc_collate_workspace_bytes": (C.c_size_t, [i64, i64]),
     "gtok_zinc_collate": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(ZincVocabC), i64, i64, vp, vp, vp, vp, vp, i64,
                                     vp, C.c_size_t, vp]),
+    "gtok_zinc_collate_packed": (C.c_int, [C.POINTER(PackedMolBatchC), C.POINTER(ZincVocabC), i64, i64, vp, vp, vp, vp, vp, i64,
+                                           vp, C.c_size_t, vp]),
     "gtok_sent_tokenize": (C.c_int, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), C.POINTER(ChoiceC), vp, vp, i64, vp]),
     "gtok_pad_mask": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp]),
     "gtok_batch_extents": (C.c_int, [vp, vp, i64, i64, vp, vp, vp]),

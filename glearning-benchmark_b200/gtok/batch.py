@@ -211,15 +211,34 @@ class PackedGraphBatch:
     query_v: Optional[torch.Tensor] = None
     num_nodes_total: int = 0
     num_entries_total: int = 0
+    col16: Optional[torch.Tensor] = None      # src | dst << 6 | edge_attr << 12 per column (int16 storage); replaces src/dst/edge_attr
+    max_id: int = 0                           # largest local node id (the kernels size their pair bitmaps from it)
 
-    ARRAYS = ("node_cnt", "entry_cnt", "src", "dst", "x", "edge_attr", "query_u", "query_v")
+    ARRAYS = ("node_cnt", "entry_cnt", "src", "dst", "x", "edge_attr", "query_u", "query_v", "col16")
 
     @property
     def num_graphs(self) -> int:
         return int(self.node_cnt.numel())
 
     @staticmethod
-    def from_batch(b: GraphBatch) -> "PackedGraphBatch":
+    def from_batch(b: GraphBatch, fuse_columns: bool = False) -> "PackedGraphBatch":
+        """fuse_columns: molecule-sized graphs (local ids < 64, edge_attr in 0..15, atom types < 256) travel as ONE
+        16-bit word per edge_index column (GtokPackedMolBatch, include/gtok.h) - the layout the thread-per-molecule
+        ZINC kernel stages anyway; falls back to separate arrays when a value does not fit."""
+        if fuse_columns and b.num_graphs and b.src.numel():
+            mid = max(int(b.src.max()), int(b.dst.max()))
+            lo = min(int(b.src.min()), int(b.dst.min()))
+            ea = b.edge_attr
+            ok = lo >= 0 and mid < 64 and (ea is None or (int(ea.min()) >= 0 and int(ea.max()) < 16))
+            ok = ok and b.x is not None and int(b.x.min()) >= 0 and int(b.x.max()) < 256
+            if ok:
+                w = b.src.to(torch.int32) | (b.dst.to(torch.int32) << 6)
+                if ea is not None:
+                    w = w | (ea.to(torch.int32) << 12)
+                col16 = (w & 0xFFFF).to(torch.int16)
+                return PackedGraphBatch(_narrowest(b.num_nodes()), _narrowest(b.num_entries()), None, None,
+                                        b.x.to(torch.uint8), None, _narrowest(b.query_u), _narrowest(b.query_v),
+                                        int(b.node_off[-1]), int(b.edge_off[-1]), col16, mid)
         return PackedGraphBatch(_narrowest(b.num_nodes()), _narrowest(b.num_entries()), _narrowest(b.src),
                                 _narrowest(b.dst), _narrowest(b.x), _narrowest(b.edge_attr), _narrowest(b.query_u),
                                 _narrowest(b.query_v), int(b.node_off[-1]) if b.num_graphs else 0,
@@ -227,7 +246,8 @@ class PackedGraphBatch:
 
     def pin_memory(self) -> "PackedGraphBatch":
         kw = {n: (None if getattr(self, n) is None else getattr(self, n).pin_memory()) for n in self.ARRAYS}
-        return PackedGraphBatch(num_nodes_total=self.num_nodes_total, num_entries_total=self.num_entries_total, **kw)
+        return PackedGraphBatch(num_nodes_total=self.num_nodes_total, num_entries_total=self.num_entries_total,
+                                max_id=self.max_id, **kw)
 
     def nbytes(self) -> int:
         return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in self.ARRAYS

@@ -129,11 +129,18 @@ class _PipelineBase:
         for cnt, off in (("node_cnt", "node_off"), ("entry_cnt", "edge_off")):
             check(lib.gtok_counts_to_offsets(_ptr(w[cnt]), w[cnt].element_size(), self.G, _ptr(self.dev_in[off]),
                                              _ptr(self._cnt_tmp), _ptr(self.ws), self.ws_bytes, st))
-        for n in ("src", "dst", "x", "edge_attr", "query_u", "query_v"):
-            if n in self.dev_in and n in w:
-                if w[n].numel() > self.dev_in[n].numel():
-                    raise ValueError(f"{n}: {w[n].numel()} elements exceed the pipeline's capacity {self.dev_in[n].numel()}")
-                check(lib.gtok_widen_i32(_ptr(w[n]), w[n].element_size(), w[n].numel(), _ptr(self.dev_in[n]), st))
+        self._packed_dev = None
+        if "col16" in w and getattr(self, "mode", None) == "collate" and w["x"].dtype == torch.uint8:
+            # fused 16-bit columns: the collate kernel reads the wire buffers directly (gtok_zinc_collate_packed)
+            self._packed_dev = (w["col16"], w["x"], host.max_id)
+        else:
+            if "col16" in w:
+                raise ValueError("fused 16-bit columns are only consumed by the ZINC pipeline in collate mode")
+            for n in ("src", "dst", "x", "edge_attr", "query_u", "query_v"):
+                if n in self.dev_in and n in w:
+                    if w[n].numel() > self.dev_in[n].numel():
+                        raise ValueError(f"{n}: {w[n].numel()} elements exceed the pipeline's capacity {self.dev_in[n].numel()}")
+                    check(lib.gtok_widen_i32(_ptr(w[n]), w[n].element_size(), w[n].numel(), _ptr(self.dev_in[n]), st))
         self._wire_src[slot] = None                       # consumed (a slot is reused only after this call returned)
 
     def use_device_batch(self, dev_batch: GraphBatch) -> None:
@@ -231,6 +238,15 @@ class ZincIbttPipeline(_PipelineBase):
         """The hot path on whatever dev_in points at: 4 kernels (fused tokenizer) or 6, no sync."""
         bc = self._batch_c()
         st = _stream()
+        if self.mode == "collate" and getattr(self, "_packed_dev", None) is not None:
+            col16, x8, max_id = self._packed_dev
+            d = self.dev_in
+            pk = _lib.PackedMolBatchC(self.G, _ptr(d["node_off"]), _ptr(d["edge_off"]), _ptr(col16), _ptr(x8),
+                                      max(1, self.max_nodes, max_id + 1), max(1, self.max_entries))
+            self._timed("zinc_collate_packed", lambda: check(lib.gtok_zinc_collate_packed(
+                C.byref(pk), C.byref(self.zv), self.B, self.pad_id, _ptr(self.lengths), _ptr(self.lmax), _ptr(self.xoff),
+                _ptr(self.X), _ptr(self.attn), min(self.X.numel(), self.attn.numel()), _ptr(self.ws), self.ws_bytes, st)))
+            return
         if self.mode == "collate":
             self._timed("zinc_collate", lambda: check(lib.gtok_zinc_collate(
                 C.byref(bc), C.byref(self.zv), self.B, self.pad_id, _ptr(self.lengths), _ptr(self.lmax), _ptr(self.xoff),
@@ -255,8 +271,10 @@ class ZincIbttPipeline(_PipelineBase):
         if isinstance(host_batch, PackedGraphBatch):
             self.upload_packed(host_batch, prefetch)
         else:
+            self._packed_dev = None
             self.upload(host_batch)
         self.launch()
+        self._packed_dev = None                  # launch() on resident int32 arrays again unless the next run() is packed
         self.download()
         torch.cuda.current_stream().synchronize()
         return self._result(True)

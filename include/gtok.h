@@ -249,6 +249,24 @@ GTOK_API int gtok_zinc_collate(const GtokGraphBatch* batch, const GtokZincVocab*
                                int64_t pad_id, int32_t* len_out, int32_t* lmax_out, int64_t* xoff_out, int64_t* X,
                                uint8_t* attn, int64_t x_capacity, void* ws, size_t ws_bytes, void* stream);
 
+/* Compact resident / wire layout of molecule-sized graphs: one 16-bit word per edge_index column
+ *      (src | dst << 6 | edge_attr << 12: local ids < 64, edge_attr in 0..15; caller's column order) and one byte
+ *      per atom type.  0.12 KB per ZINC molecule instead of 0.68 KB in the int32 layout (1.3 KB as the reference's
+ *      int64 tensors), lossless for those ranges; it is also exactly what the thread-per-molecule kernel stages, so
+ *      gtok_zinc_collate_packed reads it with plain 16-byte copies.  Same outputs as gtok_zinc_collate. */
+typedef struct GtokPackedMolBatch {
+  int64_t num_graphs;
+  const int64_t* node_off;   /* [G+1] (gtok_counts_to_offsets from per-graph counts) */
+  const int64_t* edge_off;   /* [G+1] */
+  const uint16_t* col16;     /* [E] */
+  const uint8_t* x8;         /* [N] */
+  int32_t max_nodes;         /* bound on atoms per molecule AND on every local id + 1 (<= 64) */
+  int32_t max_entries;       /* bound on columns per molecule (<= 256) */
+} GtokPackedMolBatch;
+GTOK_API int gtok_zinc_collate_packed(const GtokPackedMolBatch* batch, const GtokZincVocab* vocab, int64_t batch_size,
+                                      int64_t pad_id, int32_t* len_out, int32_t* lmax_out, int64_t* xoff_out, int64_t* X,
+                                      uint8_t* attn, int64_t x_capacity, void* ws, size_t ws_bytes, void* stream);
+
 /* K3   Graph2TrailTokenizer.__call__ (external AutoGraph; spec in
  *      oracle/sent_oracle.py) + remap_zinc_tokens + query append
  *      (train_agtt.py:171-273).  Row g is written at tok_out[g*stride ..], its

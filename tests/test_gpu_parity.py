@@ -383,6 +383,39 @@ def test_zinc_fused_collate_vs_oracle(dev, golden_zinc, B):
                 assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw), (max_len, k)
 
 
+def test_zinc_collate_packed_adversarial(dev, golden_zinc):
+    """gtok_zinc_collate_packed (16-bit columns, byte atoms) == gtok_zinc_collate on shuffled / duplicated / self-loop
+    columns, out-of-range bond types 0 and 5..15, atom types up to 255, truncation; values that do not fit fall back."""
+    from gtok import engine
+    from gtok.batch import PackedGraphBatch
+    from gtok.pipeline import ZincIbttPipeline
+    rng = np.random.default_rng(21)
+    vocab = O.zinc_extend_vocab(O.zinc_fixed_vocab(), [str(k) for k in rng.permutation(50)] + ["X", "unknown"])
+    mols = []
+    for i in range(900):
+        n = int(rng.integers(1, 64))
+        m = int(rng.integers(0, 120)) if i % 7 else 0
+        mols.append({"n": n, "src": rng.integers(0, n, m).tolist(), "dst": rng.integers(0, n, m).tolist(),
+                     "x": rng.integers(0, 256, n).tolist(), "attr": rng.integers(0, 16, m).tolist()})
+    gb = _zinc_batch(mols, "cpu")
+    for max_len in (1024, 90):
+        pipe = ZincIbttPipeline(gb, vocab, max_len, 64, dev, mode="collate")
+        ref = pipe.run(gb.pin_memory())
+        tot = int(ref.host_xoff[-1])
+        Xa, Aa, la = ref.padded.X[:tot].clone(), ref.padded.attn[:tot].clone(), ref.host_lengths.clone()
+        pf = PackedGraphBatch.from_batch(gb, fuse_columns=True)
+        assert pf.col16 is not None
+        got = pipe.run(pf.pin_memory())
+        assert int(got.host_xoff[-1]) == tot and torch.equal(got.host_lengths, la)
+        assert torch.equal(got.padded.X[:tot], Xa) and torch.equal(got.padded.attn[:tot], Aa)
+        want = [O.zinc_ids(m["x"], m["src"], m["dst"], m["attr"], vocab, max_len, max_len) for m in mols[:64]]
+        Xw, Aw, _ = O.collate(want, [0] * 64, vocab["<pad>"])
+        X0, A0 = got.padded.batch(0)
+        assert np.array_equal(X0.cpu().numpy(), Xw) and np.array_equal(A0.cpu().numpy(), Aw)
+    big = _zinc_batch([{"n": 3, "src": [0, 1], "dst": [1, 2], "x": [0, 300, 1], "attr": [1, 17]}], "cpu")
+    assert PackedGraphBatch.from_batch(big, fuse_columns=True).col16 is None       # 300 / 17 do not fit: separate arrays
+
+
 def test_zinc_fused_collate_equals_two_step_large(dev):
     """200k ZINC-shaped molecules: the fused kernel's X/attn/extents are byte-identical to
     gtok_zinc_tokenize followed by gtok_pad_mask_batched."""
@@ -449,6 +482,13 @@ def test_ingest_widen_and_packed_pipeline(dev):
         assert int(b.host_xoff[-1]) == tot and torch.equal(b.host_lengths, la)
         assert torch.equal(b.padded.X[:tot], Xa[:tot]) and torch.equal(b.padded.attn[:tot], Aa[:tot])
         assert torch.equal(pipe.dev_in["node_off"].cpu(), gb.node_off) and torch.equal(pipe.dev_in["edge_off"].cpu(), gb.edge_off)
+        if mode == "collate":
+            # fused 16-bit columns + byte atoms: consumed by gtok_zinc_collate_packed without widening
+            pf = PackedGraphBatch.from_batch(gb, fuse_columns=True)
+            assert pf.col16 is not None and pf.src is None and pf.nbytes() < pk.nbytes()
+            c_ = pipe.run(pf.pin_memory())
+            assert int(c_.host_xoff[-1]) == tot and torch.equal(c_.host_lengths, la)
+            assert torch.equal(c_.padded.X[:tot], Xa[:tot]) and torch.equal(c_.padded.attn[:tot], Aa[:tot])
         # double-buffered uploads: a stream of three different shards, each prefetched during its predecessor
         shards = [synth.zinc_shaped(5000, seed=s_) for s_ in (11, 12, 13)]
         pks = [PackedGraphBatch.from_batch(s_).pin_memory() for s_ in shards]
