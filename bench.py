@@ -252,6 +252,34 @@ def run_extras(dev, G, peak):
     sent("sent_zinc", zb, cfgz, 384, True, 0)
     out["sent_zinc"]["workload"] = (f"{G} ZINC-shaped graphs, labeled SENT + fused remap_zinc_tokens, row capacity 384 "
                                     "(no row reaches it) (BASELINE configs[3] shape, per-GPU shard)")
+    # the headline workload on the compact resident layout (16-bit columns + byte atoms, GtokPackedMolBatch)
+    import ctypes as C
+    from gtok import _lib
+    from gtok._lib import lib, check
+    from gtok.batch import PackedGraphBatch
+    from gtok.engine import _ptr, _stream
+    vz = zinc_vocab()
+    pkb = PackedGraphBatch.from_batch(zb.to("cpu"), fuse_columns=True)
+    if pkb.col16 is not None:
+        col16, x8 = pkb.col16.to(dev), pkb.x.to(dev)
+        mn, me = int(zb.num_nodes().max()), int(zb.num_entries().max())
+        zv, _tbl = engine.zinc_vocab_c(vz, MAX_LEN, MAX_LEN, max(mn, pkb.max_id + 1), dev)
+        pk = _lib.PackedMolBatchC(G, _ptr(zb.node_off), _ptr(zb.edge_off), _ptr(col16), _ptr(x8), max(mn, pkb.max_id + 1), me)
+        nb = (G + BATCH - 1) // BATCH
+        xcap = G * min(MAX_LEN, 2 * mn + 4 * me + 4) + 2
+        Xp, Ap = torch.empty(xcap, dtype=torch.int64, device=dev), torch.empty(xcap, dtype=torch.bool, device=dev)
+        lens, lm = torch.empty(G, dtype=torch.int32, device=dev), torch.empty(nb, dtype=torch.int32, device=dev)
+        xo = torch.empty(nb + 1, dtype=torch.int64, device=dev)
+        nbytes = lib.gtok_zinc_collate_workspace_bytes(G, BATCH)
+        wsp = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ms = timeit(lambda: check(lib.gtok_zinc_collate_packed(C.byref(pk), C.byref(zv), BATCH, vz["<pad>"], _ptr(lens), _ptr(lm),
+                                                               _ptr(xo), _ptr(Xp), _ptr(Ap), xcap, _ptr(wsp), nbytes, _stream())), 10, 3)
+        cells = int(xo[-1])
+        byt = 2 * zb.src.numel() + zb.x.numel() + 16 * G + 9 * cells + 4 * G
+        out["ibtt_zinc_packed_resident"] = {
+            "workload": f"{G} ZINC-shaped graphs resident in the compact layout (one 16-bit word per edge_index column, one byte "
+                        "per atom): molecules -> padded batches, same outputs as the headline step",
+            "ms_per_step": ms, "graphs_per_s": G / ms * 1e3, "algo_bytes": byt, "GBps": byt / ms / 1e6, "frac": byt / ms / 1e6 / peak}
     return out
 
 

@@ -143,7 +143,11 @@ __device__ __forceinline__ long long lookback_exclusive(unsigned long long* stat
     const long long idx = j - t;
     unsigned long long w;
     if (idx >= 0) {
-      do { w = ld_relaxed_u64(status + idx); } while ((w >> 62) == 0);
+      w = ld_relaxed_u64(status + idx);
+      while ((w >> 62) == 0) {                          // predecessor not published yet: back off instead of hammering L2
+        __nanosleep(64);
+        w = ld_relaxed_u64(status + idx);
+      }
     } else {
       w = kFlagIncl;  // virtual tile -1: inclusive prefix 0
     }
