@@ -110,8 +110,14 @@ class Graph2TrailTokenizer:
         st["epoch"] += 1
         seed = (self.seed * 0x9E3779B97F4A7C15 + st["epoch"]) & (2 ** 64 - 1)
         tok, ln = engine.tokenize_sent(st["csr"], self._config(), seed=seed)
-        st["tok"], st["len"] = tok.cpu(), ln.cpu().tolist()
-        st["served"] = bytearray(len(st["len"]))
+        # only the valid tokens cross PCIe: rows are compacted on the device (stride = max_length, mean row ~10 % of it)
+        keep = torch.arange(tok.shape[1], device=tok.device)[None, :] < ln[:, None]
+        flat = tok[keep].cpu()
+        lens = ln.cpu().to(torch.int64)
+        off = torch.zeros(lens.numel() + 1, dtype=torch.int64)
+        off[1:] = lens.cumsum(0)
+        st["flat"], st["off"] = flat, off.tolist()
+        st["served"] = bytearray(lens.numel())
 
     def __call__(self, data) -> torch.Tensor:
         handle = getattr(data, "_gtok", None)
@@ -121,7 +127,7 @@ class Graph2TrailTokenizer:
             if st["served"] is None or st["served"][idx]:
                 self._sample(st)                       # first use, or this row was already served: new epoch
             st["served"][idx] = 1
-            return st["tok"][idx, :st["len"][idx]].clone()
+            return st["flat"][st["off"][idx]:st["off"][idx + 1]].clone()
         # stand-alone object (no dataset handle): one-graph launch
         from gtok.batch import GraphBatch
         gb = GraphBatch.from_data_list([data]).to(self._device())
