@@ -136,3 +136,59 @@ def test_agtt_tokenizer_shim_graph_token(tmp_path):
         rp, col, _ = S.canonical_csr(r["n"], [e[0] for e in r["edges"]], [e[1] for e in r["edges"]])
         want = S.sent_tokenize(r["n"], rp, col, cfg, S.PhiloxWords(0, i))
         assert tok(data).tolist() == want.tolist()
+
+
+def test_epoch_loaders_match_reference_collate():
+    """gtok.loader: one epoch of GPU-resident batches == the reference's per-batch collate over the same row order
+    (IBTT from graphs, IBTT from tokenized rows, AGTT with fresh trails per epoch), incl. shuffle, drop_last and a
+    ragged last batch."""
+    import numpy as np
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    from gtok.loader import AgttEpochLoader, IbttEpochLoader
+    from helpers import gt_examples
+    from oracle import ibtt_oracle as O
+    from oracle import sent_oracle as S
+    dev = torch.device("cuda:0")
+    recs, texts, ex = gt_examples("cycle_check", 300, seed=4)
+    vocab, _ = O.vocab_from_texts(texts, max_tokens=600)
+    gb = GraphBatch.from_lists([r["n"] for r in recs], [r["edges"] for r in recs]).to(dev)
+    labels = torch.tensor([e["label"] for e in ex])
+    want = [np.asarray(O.encode_text(t, vocab, 600), dtype=np.int64) for t in texts]
+
+    def check(loader, rows_of, pad, seed):
+        for epoch in range(2):
+            gen = torch.Generator(device="cpu")
+            gen.manual_seed(seed)
+            perms = [torch.randperm(300, generator=gen) for _ in range(epoch + 1)]
+            order = perms[-1].tolist() if loader.shuffle else list(range(300))
+            if loader.drop_last:
+                order = order[:len(loader) * loader.B]
+            got = list(loader)
+            assert len(got) == len(loader)
+            for k, (X, A, Y) in enumerate(got):
+                idx = order[k * loader.B:(k + 1) * loader.B]
+                Xw, Aw, _ = O.collate([rows_of(epoch, i) for i in idx], [0] * len(idx), pad)
+                assert X.is_cuda and np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+                assert Y.cpu().tolist() == [int(labels[i]) for i in idx]
+
+    for shuffle, drop_last, B in ((False, False, 128), (True, False, 64), (True, True, 128)):
+        check(IbttEpochLoader.from_graphs(gb, vocab, "cycle_check", 600, labels, B, shuffle, seed=7, drop_last=drop_last),
+              lambda ep, i: want[i], vocab["<pad>"], 7)
+        rag = engine.tokenize_ibtt(gb, vocab, "cycle_check", 600)
+        check(IbttEpochLoader.from_ragged(rag, vocab["<pad>"], labels, B, shuffle, seed=7, drop_last=drop_last),
+              lambda ep, i: want[i], vocab["<pad>"], 7)
+    # AGTT: trails differ per epoch, rows must equal the oracle's walk under the epoch's Philox seed
+    csr = engine.build_csr(gb)
+    cfg = engine.SentConfig(idx_offset=6, max_length=600)
+    ocfg = S.SentConfig(idx_offset=6, max_length=600)
+    csrs = [S.canonical_csr(r["n"], [e[0] for e in r["edges"]], [e[1] for e in r["edges"]]) for r in recs]
+    cache = {}
+
+    def sent_row(ep, i):
+        if (ep, i) not in cache:
+            seed = (11 * 0x9E3779B97F4A7C15 + ep) & (2 ** 64 - 1)
+            rp, col, _ = csrs[i]
+            cache[(ep, i)] = S.sent_tokenize(recs[i]["n"], rp, col, ocfg, S.PhiloxWords(seed, i))
+        return cache[(ep, i)]
+    check(AgttEpochLoader(csr, cfg, labels, 32, shuffle=True, seed=11), sent_row, 5, 11)
