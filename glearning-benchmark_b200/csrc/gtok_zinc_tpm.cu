@@ -61,12 +61,6 @@ struct TpmOut {
   int64_t pad;
 };
 
-__device__ __forceinline__ unsigned long long tpm_mask_bytes(int nvalid) {
-  if (nvalid <= 0) return 0ull;
-  if (nvalid >= 8) return 0x0101010101010101ull;
-  return 0x0101010101010101ull >> (8 * (8 - nvalid));
-}
-
 // two tokens at an EVEN index of a row buffer in one store
 __device__ __forceinline__ void put2(uint16_t* rb, int idx, unsigned t0, unsigned t1) {
   *reinterpret_cast<unsigned*>(rb + idx) = t0 | (t1 << 16);
@@ -364,31 +358,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
       } else {
         if (base + pub > o.x_capacity) return;
         const long long cell = base + (long long)(32 * w + j) * lmax;
-        int64_t* __restrict__ xrow = o.X + cell;
-        uint8_t* __restrict__ arow = o.attn + cell;
-        const int64_t pad = o.pad;
-        const int head = (int)(cell & 1);
-        if (head && lane == 0 && lmax > 0) st_stream_i64(xrow, 0 < len ? (int64_t)rb[1] : pad);
-        const int npair = (lmax - head) >> 1;
-        for (int q = lane; q < npair; q += kWarp) {
-          const int r = head + 2 * q;
-          const int64_t a0 = r < len ? (int64_t)rb[1 + r] : pad;
-          const int64_t b0 = r + 1 < len ? (int64_t)rb[2 + r] : pad;
-          st_stream_i64x2(xrow + r, a0, b0);
-        }
-        const int tx = head + 2 * npair;
-        if (tx < lmax && lane == 31) st_stream_i64(xrow + tx, tx < len ? (int64_t)rb[1 + tx] : pad);
-        int mh = (int)((16 - (reinterpret_cast<uintptr_t>(arow) & 15)) & 15);
-        if (mh > lmax) mh = lmax;
-        if (lane < mh) arow[lane] = (uint8_t)(lane < len);
-        const int nvec = (lmax - mh) >> 4;
-        for (int q = lane; q < nvec; q += kWarp) {
-          const int p = mh + 16 * q;
-          const int nvb = len - p;
-          __stcs(reinterpret_cast<ulonglong2*>(arow + p), make_ulonglong2(tpm_mask_bytes(nvb), tpm_mask_bytes(nvb - 8)));
-        }
-        const int tl = mh + 16 * nvec;
-        if (tl + lane < lmax && lane < 16) arow[tl + lane] = (uint8_t)(tl + lane < len);
+        warp_pad_row(len, lmax, o.pad, o.X + cell, o.attn + cell, [&](int p) -> int { return (int)rb[1 + p]; });
       }
     };
     StageT* rb0 = s_row;
