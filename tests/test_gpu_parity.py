@@ -264,6 +264,14 @@ def test_fused_entry_points_edge_cases(dev):
         Xw, Aw, _ = O.collate(wantg[k * 32:(k + 1) * 32], [0] * len(wantg[k * 32:(k + 1) * 32]), 0)
         X, A = ep.batch(k)
         assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+    # bounds that are too small for the data must not corrupt memory: the affected warps emit header-only rows
+    mols = [{"n": 20, "src": list(range(19)) * 2, "dst": list(range(1, 20)) * 2, "x": [0] * 20, "attr": [1] * 38}] * 70
+    gbb = _zinc_batch(mols, dev)
+    ep, lens = engine.zinc_collate_epoch(gbb, zvoc, 1024, 32, max_nodes=20, max_entries=2)
+    torch.cuda.synchronize()
+    assert lens.cpu().tolist() == [4] * 70 and ep.batch(0)[0][0].cpu().tolist() == [zvoc["<bos>"], zvoc["<q>"], zvoc["regression"], zvoc["<p>"]]
+    rag = engine.tokenize_zinc(gbb, zvoc, 1024, max_nodes=20, max_entries=2)
+    assert rag.lengths.cpu().tolist() == [4] * 70
     # unsupported shapes raise GTOK_EUNSUPPORTED instead of falling back to anything
     with pytest.raises(GtokError) as ei:
         engine.zinc_collate_epoch(gb, zvoc, 64, 48)                       # batch size not a multiple of 32
