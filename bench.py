@@ -505,7 +505,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gtok", choices=["gtok", "reference"])
     ap.add_argument("--graphs", type=int, default=1_000_000, help="graphs per GPU")
-    ap.add_argument("--cpu-graphs-per-core", type=int, default=4000)
+    ap.add_argument("--cpu-graphs-per-core", type=int, default=40000,
+                    help="CPU arm sample: graphs per host core per step (default: ~25 core-seconds of reference work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (graph-token IBTT, SENT)")
     ap.add_argument("--zinc-fused", type=int, default=-1, help="-1 auto, 0 three-kernel path, 1 fused single pass")
