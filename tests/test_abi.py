@@ -50,3 +50,32 @@ def test_no_cpu_fallback():
             if f.endswith(".py"):
                 text = open(os.path.join(root, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f"{f} imports the oracle"
+
+
+def test_header_is_plain_c():
+    """include/gtok.h is the drop-in boundary: it must compile as C (no C++-only constructs, no torch types)."""
+    import subprocess
+    src = "#include \"gtok.h\"\nint main(void) { return GTOK_VERSION == 100 ? 0 : 1; }\n"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                       input=src, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference runs without a GPU, prints exactly one JSON line on stdout with the keys of the
+    bench contract, and never touches the CUDA library."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-graphs-per-core", "64"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "graphs/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
