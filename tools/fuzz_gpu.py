@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Randomised CUDA-vs-oracle campaign beyond the unit tests (bit-exactness on odd shapes):
+   python tools/fuzz_gpu.py [rounds] [seed]
+ZINC: molecules up to 64 atoms / 256 columns, shuffled / duplicated / self-loop columns, out-of-range atom and bond
+types, random max_len (all truncation branches), batch sizes 32..256, graph counts around tile multiples; ragged,
+padded and packed-layout kernels.  Graph-token: random tasks / max_len / OOV vocabularies, fused collate with shuffled
+row order.  SENT: graphs up to 256 nodes (all three thread-per-graph word counts), labeled / remap / query / truncation."""
+import os
+import sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "glearning-benchmark_b200")]
+import numpy as np
+import torch
+from gtok import engine
+from gtok.batch import GraphBatch, PackedGraphBatch
+from gtok.pipeline import ZincIbttPipeline
+from oracle import ibtt_oracle as O
+from oracle import sent_oracle as S
+
+dev = torch.device("cuda:0")
+rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+bad = 0
+
+
+def zinc_round():
+    global bad
+    nmax = int(rng.choice([9, 33, 37, 64]))
+    G = int(rng.choice([1, 31, 127, 128, 129, 257, 1000, 3001]))
+    dense = rng.random() < 0.3
+    mols = []
+    for i in range(G):
+        n = int(rng.integers(1, nmax + 1))
+        m = 0 if rng.random() < 0.05 else int(rng.integers(1, 257 if dense else 90))
+        s = rng.integers(0, n, m)
+        d = rng.integers(0, n, m) if rng.random() < 0.7 else (s + 1) % n
+        mols.append({"n": n, "src": s.tolist(), "dst": d.tolist(), "x": rng.integers(-2, 40, n).tolist(),
+                     "attr": rng.integers(-1, 16, m).tolist()})
+    names = [str(k) for k in rng.permutation(70)[: int(rng.integers(1, 70))]] + (["X"] if rng.random() < 0.7 else []) + \
+            (["unknown"] if rng.random() < 0.7 else [])
+    vocab = O.zinc_extend_vocab(O.zinc_fixed_vocab(), names)
+    if rng.random() < 0.3:
+        vocab = {t: (i if i < 22 else i + 70000) for t, i in vocab.items()}
+    max_len = int(rng.choice([1024, 2, 3, 7, 40, 97, 200]))
+    B = int(rng.choice([32, 64, 128, 256]))
+    gb = GraphBatch.from_lists([m["n"] for m in mols], [list(zip(m["src"], m["dst"])) for m in mols],
+                               x_lists=[m["x"] for m in mols], attr_lists=[m["attr"] for m in mols])
+    want = [O.zinc_ids(m["x"], m["src"], m["dst"], m["attr"], vocab, max_len, max_len) for m in mols]
+    rag = engine.tokenize_zinc(gb.to(dev), vocab, max_len)
+    rows = rag.rows_cpu()
+    ok = all(r.tolist() == w.tolist() for r, w in zip(rows, want))
+    ep, lens = engine.zinc_collate_epoch(gb.to(dev), vocab, max_len, B)
+    ok = ok and lens.cpu().tolist() == [len(w) for w in want]
+    for k in range(ep.num_batches):
+        Xw, Aw, _ = O.collate(want[k * B:(k + 1) * B], [0] * len(want[k * B:(k + 1) * B]), vocab["<pad>"])
+        X, A = ep.batch(k)
+        ok = ok and np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+    # packed layout needs values in range: clip a copy and compare against the int32 path on the same clipped data
+    gc = GraphBatch(gb.node_off, gb.edge_off, gb.src, gb.dst, gb.x.clamp(0, 255), gb.edge_attr.clamp(0, 15))
+    pf = PackedGraphBatch.from_batch(gc, fuse_columns=True)
+    if pf.col16 is not None:
+        pipe = ZincIbttPipeline(gc, vocab, max_len, B, dev, mode="collate")
+        a = pipe.run(gc.pin_memory())
+        tot = int(a.host_xoff[-1])
+        Xa, Aa, la = a.padded.X[:tot].clone(), a.padded.attn[:tot].clone(), a.host_lengths.clone()
+        b = pipe.run(pf.pin_memory())
+        ok = ok and int(b.host_xoff[-1]) == tot and torch.equal(b.host_lengths, la) and torch.equal(b.padded.X[:tot], Xa) \
+            and torch.equal(b.padded.attn[:tot], Aa)
+    if not ok:
+        bad += 1
+    print(f"zinc   G={G:5d} nmax={nmax:2d} dense={int(dense)} max_len={max_len:4d} B={B:3d}: {'ok' if ok else 'MISMATCH'}")
+
+
+def gt_round():
+    global bad
+    task = str(rng.choice(["cycle_check", "shortest_path"]))
+    G = int(rng.choice([1, 7, 255, 256, 1000]))
+    nn, el, qs = [], [], []
+    for i in range(G):
+        n = int(rng.integers(1, 60))
+        m = int(rng.integers(0, 4 * n))
+        nn.append(n)
+        el.append(list(zip(rng.integers(0, n, m).tolist(), rng.integers(0, n, m).tolist())))
+        qs.append((int(rng.integers(0, n)), int(rng.integers(0, n))))
+    vocab = {t: i for i, t in enumerate(O.SPECIAL)}
+    for k in rng.permutation(60)[: int(rng.integers(1, 60))]:
+        vocab[str(int(k))] = len(vocab) + (70000 if rng.random() < 0.1 else 0)
+    vocab["has_cycle"] = max(vocab.values()) + 1
+    vocab["shortest_distance"] = max(vocab.values()) + 1
+    max_len = int(rng.choice([600, 5, 33, 250]))
+    B = int(rng.choice([1, 37, 128]))
+    gb = GraphBatch.from_lists(nn, el, queries=qs if task == "shortest_path" else None).to(dev)
+    want = [np.asarray(O.ibtt_ids(n, np.asarray([a for a, _ in e], dtype=np.int64), np.asarray([b for _, b in e], dtype=np.int64),
+                                  task, vocab, max_len, q if task == "shortest_path" else None)) for n, e, q in zip(nn, el, qs)]
+    rows = engine.tokenize_ibtt(gb, vocab, task, max_len).rows_cpu()
+    ok = all(r.tolist() == w.tolist() for r, w in zip(rows, want))
+    perm = torch.from_numpy(rng.permutation(G)).to(dev)
+    ep, _ = engine.ibtt_collate_epoch(gb, vocab, task, max_len, B, batch_idx=perm)
+    order = perm.cpu().tolist()
+    for k in range(ep.num_batches):
+        idx = order[k * B:(k + 1) * B]
+        Xw, Aw, _ = O.collate([want[i] for i in idx], [0] * len(idx), vocab["<pad>"])
+        X, A = ep.batch(k)
+        ok = ok and np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+    if not ok:
+        bad += 1
+    print(f"gtoken G={G:5d} task={task:13s} max_len={max_len:4d} B={B:3d}: {'ok' if ok else 'MISMATCH'}")
+
+
+def sent_round():
+    global bad
+    nmax = int(rng.choice([5, 32, 64, 100, 128, 200, 256, 300]))
+    G = int(rng.choice([1, 33, 120]))
+    labeled = rng.random() < 0.5
+    mols = []
+    for i in range(G):
+        n = int(rng.integers(1, nmax + 1))
+        m = int(rng.integers(0, 5 * n)) if rng.random() < 0.9 else int(min(n * n // 3, 6000))
+        mols.append({"n": n, "src": rng.integers(0, n, m).tolist(), "dst": rng.integers(0, n, m).tolist(),
+                     "x": rng.integers(0, 12, n).tolist(), "attr": rng.integers(1, 6, m).tolist()})
+    gb = GraphBatch.from_lists([m["n"] for m in mols], [list(zip(m["src"], m["dst"])) for m in mols],
+                               x_lists=[m["x"] for m in mols], attr_lists=[m["attr"] for m in mols],
+                               queries=[(int(rng.integers(0, m["n"])), int(rng.integers(0, m["n"]))) for m in mols]).to(dev)
+    csr = engine.build_csr(gb, balance_window=int(rng.choice([0, 16])))
+    mx = max(m["n"] for m in mols)
+    max_length = int(rng.choice([1, 2, 17, 200, 30000]))
+    remap, append = bool(labeled and rng.random() < 0.5), bool(rng.random() < 0.4)
+    seed = int(rng.integers(0, 2 ** 40))
+    cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + mx, edge_idx_offset=6 + mx + 12, max_length=max_length, labeled=labeled,
+                            remap_zinc=remap, append_query=append)
+    tok, ln = engine.tokenize_sent(csr, cfg, seed=seed, graph_id_base=5)
+    tok, ln = tok.cpu(), ln.cpu().tolist()
+    ocfg = S.SentConfig(6, 6 + mx, 6 + mx + 12, max_length, labeled)
+    ok = True
+    for g, m in enumerate(mols):
+        rp, col, ea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"])
+        w = S.sent_tokenize(m["n"], rp, col, ocfg, S.PhiloxWords(seed, 5 + g), x=m["x"], eattr=ea)
+        if remap:
+            w = O.remap_zinc(w, 6, 6 + mx, 6 + mx + 12)
+        if append:
+            w = O.append_query(w, 6, m["n"], int(gb.query_u[g]), int(gb.query_v[g]))
+        ok = ok and tok[g, :ln[g]].tolist() == np.asarray(w).tolist()
+    if not ok:
+        bad += 1
+    print(f"sent   G={G:5d} nmax={nmax:3d} labeled={int(labeled)} remap={int(remap)} query={int(append)} max_length={max_length:5d}: "
+          f"{'ok' if ok else 'MISMATCH'}")
+
+
+for r in range(rounds):
+    zinc_round()
+    gt_round()
+    sent_round()
+print("mismatching rounds:", bad)
+sys.exit(1 if bad else 0)
