@@ -361,7 +361,7 @@ extern "C" int gtok_ibtt_serialize(const GtokGraphBatch* batch, const GtokIbttRu
   if (rc) return rc;
   if (batch->num_graphs == 0) return GTOK_OK;
   GTOK_REQUIRE(off != nullptr && tok_out != nullptr, GTOK_EINVAL, "ibtt_serialize: null off/tok_out");
-  GTOK_REQUIRE(batch->src && batch->dst, GTOK_EINVAL, "ibtt_serialize: null src/dst");
+  // (src / dst may be null when the batch has no edge at all: the kernels never dereference them then)
   GTOK_REQUIRE((reinterpret_cast<uintptr_t>(tok_out) & 15) == 0, GTOK_EINVAL, "ibtt_serialize: tok_out must be 16-byte aligned");
   const int64_t work = (batch->num_graphs + (kIbttThreads / 32) - 1) / (kIbttThreads / 32);
   cudaStream_t st = (cudaStream_t)stream;
@@ -388,7 +388,6 @@ extern "C" int gtok_ibtt_collate(const GtokGraphBatch* batch, const GtokIbttRule
   if (num_rows == 0) return GTOK_OK;
   GTOK_REQUIRE(batch->num_graphs > 0, GTOK_EINVAL, "ibtt_collate: rows requested from an empty batch");
   GTOK_REQUIRE(lmax && xoff && X && attn, GTOK_EINVAL, "ibtt_collate: null pointer");
-  GTOK_REQUIRE(batch->src && batch->dst, GTOK_EINVAL, "ibtt_collate: null src/dst");
   GTOK_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0, GTOK_EINVAL, "ibtt_collate: X must be 16-byte aligned");
   const int64_t nb = (num_rows + batch_size - 1) / batch_size;
   // shared memory: node table (up to 4096 entries) + one row buffer per warp; rows longer than the buffer use the closed form

@@ -280,7 +280,10 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
         }
       }
       // ---- flush point (warp-synchronous) ----------------------------------------------------------
-      if (__any_sync(kFull, pos - flushed >= 32) && pos - flushed >= 16 && flushed + 16 <= Lcap) flush16();
+      if (__any_sync(kFull, pos - flushed >= 32)) {
+        if (pos - flushed >= 16 && flushed + 16 <= Lcap) flush16();
+        if (pos - flushed >= 32 && flushed + 16 <= Lcap) flush16();   // a labeled event can add more than 16 tokens:
+      }                                                                   // pending must be below 32 when the next one starts
       if (__all_sync(kFull, done)) break;
     }
     if (valid) {

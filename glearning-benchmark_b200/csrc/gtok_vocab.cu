@@ -74,7 +74,7 @@ extern "C" int gtok_vocab_histogram(const GtokGraphBatch* batch, int32_t task, i
   GTOK_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)num_bins * 8, st));
   GTOK_CUDA_TRY(cudaMemsetAsync(first, 0xff, (size_t)num_bins * 8, st));
   if (batch->num_graphs == 0) return GTOK_OK;
-  GTOK_REQUIRE(batch->node_off && batch->edge_off && batch->src && batch->dst, GTOK_EINVAL, "vocab_histogram: null graph arrays");
+  GTOK_REQUIRE(batch->node_off && batch->edge_off, GTOK_EINVAL, "vocab_histogram: null graph arrays");   // src/dst may be null without edges
   GTOK_REQUIRE(task != GTOK_TASK_SHORTEST_PATH || (batch->query_u && batch->query_v), GTOK_EINVAL,
                "vocab_histogram: shortest_path needs query_u/query_v");
   const int smem_bins = num_bins < kVocBinsMax ? num_bins : kVocBinsMax;

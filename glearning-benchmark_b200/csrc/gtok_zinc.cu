@@ -298,7 +298,7 @@ static int zinc_check(const GtokGraphBatch* b, const GtokZincVocab* v, const cha
   GTOK_REQUIRE(b != nullptr && v != nullptr, GTOK_EINVAL, "%s: null batch/vocab", who);
   GTOK_REQUIRE(b->num_graphs >= 0, GTOK_EINVAL, "%s: negative graph count", who);
   if (b->num_graphs == 0) return GTOK_OK;
-  GTOK_REQUIRE(b->node_off && b->edge_off && b->src && b->dst, GTOK_EINVAL, "%s: null graph arrays", who);
+  GTOK_REQUIRE(b->node_off && b->edge_off, GTOK_EINVAL, "%s: null graph arrays", who);   // src/dst may be null without edges
   GTOK_REQUIRE(v->item_max_len >= 2 && v->ds_max_len >= 0, GTOK_EINVAL, "%s: max_len must be >= 2", who);
   GTOK_REQUIRE(v->node_tok_len == 0 || v->node_tok != nullptr, GTOK_EINVAL, "%s: null node_tok table", who);
   GTOK_REQUIRE(b->max_entries > 0 && b->max_nodes > 0, GTOK_EINVAL,

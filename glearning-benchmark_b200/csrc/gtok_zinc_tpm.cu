@@ -145,7 +145,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
     // header-only rows instead of corrupting shared memory
     const bool fits = Et <= lay.col_cap && Nt <= lay.x_cap && Et >= 0 && Nt >= 0;
     if (!fits) { Et = 0; Nt = 0; }
-    const bool packed = p_col16 != nullptr;             // columns arrive as 16-bit words (u6 | v6 << 6 | attr4 << 12), atoms as bytes
+    const bool packed = p_x8 != nullptr;                // columns arrive as 16-bit words (u6 | v6 << 6 | attr4 << 12), atoms as bytes
     const long long E0a = packed ? (E0 & ~7ll) : (vec_ok ? (E0 & ~3ll) : E0);           // staged index 0
     const long long N0a = packed ? (N0 & ~15ll) : (vec_ok ? (N0 & ~3ll) : N0);
     const int eo = (int)(e_lo - E0a), no = (int)(n_lo - N0a);
@@ -438,11 +438,11 @@ int tpm_launch(const GtokGraphBatch* batch, const GtokZincVocab* vocab, const Tp
   const int64_t tiles = (batch->num_graphs + lay.T - 1) / lay.T;
   const size_t need = 16 + (size_t)tiles * 8;
   GTOK_REQUIRE(ws_bytes >= need, GTOK_EWORKSPACE, "zinc tokenizer: workspace %zu < %zu bytes", ws_bytes, need);
-  auto k = (batch->edge_attr || col16) ? zinc_tpm_kernel<StageT, true, PADDED> : zinc_tpm_kernel<StageT, false, PADDED>;
+  auto k = (batch->edge_attr || x8) ? zinc_tpm_kernel<StageT, true, PADDED> : zinc_tpm_kernel<StageT, false, PADDED>;
   GTOK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
   GTOK_CUDA_TRY(cudaMemsetAsync(ws, 0, need, st));
   const int grid = persistent_grid(k, lay.T, (size_t)lay.smem, tiles);
-  const int vec_ok = col16 ? 1 : ((reinterpret_cast<uintptr_t>(batch->src) | reinterpret_cast<uintptr_t>(batch->dst) |
+  const int vec_ok = x8 ? 1 : ((reinterpret_cast<uintptr_t>(batch->src) | reinterpret_cast<uintptr_t>(batch->dst) |
                                    reinterpret_cast<uintptr_t>(batch->edge_attr) | reinterpret_cast<uintptr_t>(batch->x)) & 15) == 0;
   k<<<grid, lay.T, lay.smem, st>>>(*batch, *vocab, lay, o, reinterpret_cast<unsigned int*>(ws),
                                    reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + 16), vec_ok,
@@ -484,8 +484,8 @@ extern "C" int gtok_zinc_collate(const GtokGraphBatch* batch, const GtokZincVoca
     GTOK_CUDA_TRY(cudaMemsetAsync(xoff_out, 0, sizeof(int64_t), st));
     return GTOK_OK;
   }
-  GTOK_REQUIRE(batch->node_off && batch->edge_off && batch->src && batch->dst && batch->x, GTOK_EINVAL,
-               "zinc_collate: null graph arrays (x is required)");
+  GTOK_REQUIRE(batch->node_off && batch->edge_off && batch->x, GTOK_EINVAL,
+               "zinc_collate: null graph arrays (x is required; src / dst may be null without edges)");
   GTOK_REQUIRE(len_out && lmax_out && X && attn && ws, GTOK_EINVAL, "zinc_collate: null output/workspace");
   GTOK_REQUIRE(x_capacity >= 0, GTOK_EINVAL, "zinc_collate: negative capacity");
   GTOK_REQUIRE(vocab->item_max_len >= 2 && vocab->ds_max_len >= 0, GTOK_EINVAL, "zinc_collate: max_len must be >= 2");
@@ -531,8 +531,8 @@ extern "C" int gtok_zinc_tokenize(const GtokGraphBatch* batch, const GtokZincVoc
     GTOK_CUDA_TRY(cudaMemsetAsync(off_out, 0, sizeof(int64_t), st));
     return GTOK_OK;
   }
-  GTOK_REQUIRE(batch->node_off && batch->edge_off && batch->src && batch->dst && batch->x, GTOK_EINVAL,
-               "zinc_tokenize: null graph arrays (x is required)");
+  GTOK_REQUIRE(batch->node_off && batch->edge_off && batch->x, GTOK_EINVAL,
+               "zinc_tokenize: null graph arrays (x is required; src / dst may be null without edges)");
   GTOK_REQUIRE(len_out && tok_out && ws, GTOK_EINVAL, "zinc_tokenize: null output/workspace");
   GTOK_REQUIRE(tok_capacity >= 0, GTOK_EINVAL, "zinc_tokenize: negative capacity");
   GTOK_REQUIRE(vocab->item_max_len >= 2 && vocab->ds_max_len >= 0, GTOK_EINVAL, "zinc_tokenize: max_len must be >= 2");
@@ -566,7 +566,7 @@ extern "C" int gtok_zinc_collate_packed(const GtokPackedMolBatch* pk, const Gtok
     GTOK_CUDA_TRY(cudaMemsetAsync(xoff_out, 0, sizeof(int64_t), st));
     return GTOK_OK;
   }
-  GTOK_REQUIRE(pk->node_off && pk->edge_off && pk->col16 && pk->x8, GTOK_EINVAL, "zinc_collate_packed: null graph arrays");
+  GTOK_REQUIRE(pk->node_off && pk->edge_off && pk->x8, GTOK_EINVAL, "zinc_collate_packed: null graph arrays");   // col16 may be null without edges
   GTOK_REQUIRE(len_out && lmax_out && X && attn && ws, GTOK_EINVAL, "zinc_collate_packed: null output/workspace");
   GTOK_REQUIRE(x_capacity >= 0, GTOK_EINVAL, "zinc_collate_packed: negative capacity");
   GTOK_REQUIRE(vocab->item_max_len >= 2 && vocab->ds_max_len >= 0, GTOK_EINVAL, "zinc_collate_packed: max_len must be >= 2");

@@ -736,3 +736,79 @@ def test_sent_mid_labeled_truncated_replay(dev, N):
             if append:
                 want = O.append_query(want, 6, m["n"], int(gb.query_u[g]), int(gb.query_v[g]))
             assert tok[g, :ln[g]].tolist() == np.asarray(want).tolist(), (N, max_length, g)
+
+
+def test_sent_small_labeled_dense_long_events(dev):
+    """<= 64-node labeled graphs whose single events add up to 26 tokens (vertex + label + 10 bracketed (edge label,
+    vertex) pairs + edge label): the per-lane token ring must drain fast enough (found by tools/fuzz_gpu.py seed 2)."""
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    rng = np.random.default_rng(11)
+    mols = []
+    for i in range(160):
+        n = int(rng.integers(12, 65))
+        m = int(rng.integers(4 * n, 12 * n))
+        s_, d_ = rng.integers(0, n, m), rng.integers(0, n, m)
+        mols.append({"n": n, "src": s_.tolist(), "dst": d_.tolist(), "x": rng.integers(0, 12, n).tolist(),
+                     "attr": rng.integers(1, 6, m).tolist()})
+    gb = GraphBatch.from_lists([m["n"] for m in mols], [list(zip(m["src"], m["dst"])) for m in mols],
+                               x_lists=[m["x"] for m in mols], attr_lists=[m["attr"] for m in mols]).to(dev)
+    csr = engine.build_csr(gb)
+    assert csr.adj64 is not None and csr.adj_words == 1
+    for max_length in (30000, 777):
+        cfg = engine.SentConfig(idx_offset=6, node_idx_offset=70, edge_idx_offset=82, max_length=max_length, labeled=True)
+        tok, ln = engine.tokenize_sent(csr, cfg, seed=21)
+        tok, ln = tok.cpu(), ln.cpu().tolist()
+        ocfg = S.SentConfig(6, 70, 82, max_length, True)
+        for g, m in enumerate(mols):
+            rp, col, ea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"])
+            want = S.sent_tokenize(m["n"], rp, col, ocfg, S.PhiloxWords(21, g), x=m["x"], eattr=ea)
+            assert tok[g, :ln[g]].tolist() == np.asarray(want).tolist(), (max_length, g)
+
+
+def test_batches_without_any_edge(dev):
+    """Every graph of the batch has zero edges: the edge arrays are empty tensors (data_ptr 0) and every entry point
+    must still produce the reference rows (found by tools/fuzz_gpu.py seed 3)."""
+    from gtok import engine
+    from gtok.batch import GraphBatch, PackedGraphBatch
+    ns = [1, 3, 7, 2, 5] * 9
+    qs = [(0, n - 1) for n in ns]
+    gb = GraphBatch.from_lists(ns, [[] for _ in ns], queries=qs).to(dev)
+    for task in ("cycle_check", "shortest_path"):
+        vocab = engine.vocab_from_graphs(gb, task, ["no"] * len(ns))[0]
+        texts = [O.graph_token_text(n, [], task, "no", q) for n, q in zip(ns, qs)]
+        assert vocab == O.vocab_from_texts(texts)[0]
+        want = [O.ibtt_ids(n, np.zeros(0, np.int32), np.zeros(0, np.int32), task, vocab, 600, q) for n, q in zip(ns, qs)]
+        rows = engine.tokenize_ibtt(gb, vocab, task, 600).rows_cpu()
+        assert [r.tolist() for r in rows] == [w.tolist() for w in want]
+        ep, lens = engine.ibtt_collate_epoch(gb, vocab, task, 600, 16)
+        assert lens.cpu().tolist() == [len(w) for w in want]
+        for k in range(ep.num_batches):
+            Xw, Aw, _ = O.collate(want[k * 16:(k + 1) * 16], [0] * len(want[k * 16:(k + 1) * 16]), vocab["<pad>"])
+            X, A = ep.batch(k)
+            assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+    # ZINC: atoms only
+    xs = [list(range(n)) for n in ns]
+    zb = GraphBatch.from_lists(ns, [[] for _ in ns], x_lists=xs, attr_lists=[[] for _ in ns])
+    zv = O.zinc_extend_vocab(O.zinc_fixed_vocab(), [str(i) for i in range(28)])
+    want = [O.zinc_ids(x, [], [], [], zv, 64, 64) for x in xs]
+    assert [r.tolist() for r in engine.tokenize_zinc(zb.to(dev), zv, 64).rows_cpu()] == [w.tolist() for w in want]
+    ep, lens = engine.zinc_collate_epoch(zb.to(dev), zv, 64, 32)
+    assert lens.cpu().tolist() == [len(w) for w in want]
+    from gtok.pipeline import ZincIbttPipeline
+    pipe = ZincIbttPipeline(zb, zv, 64, 32, dev, mode="collate")
+    res = pipe.run(PackedGraphBatch.from_batch(zb, fuse_columns=True).pin_memory())
+    assert res.host_lengths.tolist() == [len(w) for w in want]
+    ep2 = res.padded
+    for k in range(ep.num_batches):
+        Xw, Aw, _ = O.collate(want[k * 32:(k + 1) * 32], [0] * len(want[k * 32:(k + 1) * 32]), zv["<pad>"])
+        for e in (ep, ep2):
+            X, A = e.batch(k)
+            assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+    # SENT on edgeless graphs
+    csr = engine.build_csr(gb)
+    tok, ln = engine.tokenize_sent(csr, engine.SentConfig(idx_offset=6, max_length=100), seed=1)
+    for g, n in enumerate(ns):
+        rp, col, _ = S.canonical_csr(n, [], [])
+        w = S.sent_tokenize(n, rp, col, S.SentConfig(idx_offset=6, max_length=100), S.PhiloxWords(1, g))
+        assert tok[g, :int(ln[g])].cpu().tolist() == w.tolist()
