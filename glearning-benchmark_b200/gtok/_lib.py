@@ -59,6 +59,11 @@ class SentCfgC(C.Structure):
                 ("labeled", i32), ("edge_label_shift", i32), ("remap_zinc", i32), ("append_query", i32)]
 
 
+class ErSpecC(C.Structure):
+    _fields_ = [("num_buckets", i32), ("n_lo", i32 * 4), ("n_hi", i32 * 4), ("thr_lo", C.c_uint32), ("thr_hi", C.c_uint32),
+                ("reserved_", i32), ("seed", u64), ("graph_id_base", i64)]
+
+
 class ChoiceC(C.Structure):
     _fields_ = [("seed", u64), ("graph_id_base", i64), ("stream", vp), ("stream_off", vp)]
 
@@ -92,6 +97,10 @@ PROTOTYPES = {
     "gtok_pad_mask": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp]),
     "gtok_batch_extents": (C.c_int, [vp, vp, i64, i64, vp, vp, vp]),
     "gtok_pad_mask_batched": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, vp]),
+    "gtok_find_token": (C.c_int, [vp, vp, vp, i64, i64, vp, i64, vp, vp]),
+    "gtok_graph_labels": (C.c_int, [C.POINTER(CsrBatchC), vp, vp, vp, vp]),
+    "gtok_er_sizes": (C.c_int, [C.POINTER(ErSpecC), i64, vp, vp, vp, vp, vp]),
+    "gtok_er_edges": (C.c_int, [C.POINTER(ErSpecC), i64, vp, vp, vp, vp]),
 }
 
 

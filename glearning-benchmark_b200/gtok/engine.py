@@ -6,6 +6,8 @@ torch.distributed.  Each function names the reference code it stands in for.
 """
 from __future__ import annotations
 
+import math
+
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
@@ -526,6 +528,12 @@ def build_csr(batch: GraphBatch, balance_window: int = 0) -> CsrBatch:
                     max_nodes, int(nnz_g.max()) if G else 0, max_label, adj64, adj_words, order)
 
 
+def _csr_c(csr: CsrBatch) -> _lib.CsrBatchC:
+    return _lib.CsrBatchC(csr.num_graphs, _ptr(csr.node_off), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.eattr), _ptr(csr.x),
+                          _ptr(csr.query_u), _ptr(csr.query_v), max(1, csr.max_nodes), max(0, csr.max_nnz),
+                          max(0, csr.max_label), int(csr.adj_words), _ptr(csr.adj64), _ptr(csr.order))
+
+
 @dataclass
 class SentConfig:
     idx_offset: int = 6
@@ -551,11 +559,82 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
     if out is None:
         out = torch.empty((G, stride), dtype=torch.int64, device=dev)
     lengths = torch.empty(G, dtype=torch.int32, device=dev)
-    cc = _lib.CsrBatchC(G, _ptr(csr.node_off), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.eattr), _ptr(csr.x),
-                        _ptr(csr.query_u), _ptr(csr.query_v), max(1, csr.max_nodes), max(0, csr.max_nnz),
-                        max(0, csr.max_label), int(csr.adj_words), _ptr(csr.adj64), _ptr(csr.order))
+    cc = _csr_c(csr)
     sc = _lib.SentCfgC(cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset, cfg.max_length, int(cfg.labeled),
                        cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query))
     ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))
     check(lib.gtok_sent_tokenize(C.byref(cc), C.byref(sc), C.byref(ch), _ptr(lengths), _ptr(out), int(stride), _stream()))
     return out, lengths
+
+
+# ---------------------------------------------------------------------------
+# K6: around the path: query positions, task labels, on-device ER graphs
+# ---------------------------------------------------------------------------
+def query_positions(ep: PaddedEpoch, token: int = 0, token_per_batch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """First position of the <q> id in every row of a padded epoch (-1 when absent): what extract_query_nodes scans
+    for on the host, row by row (trainer/train_ibtt.py:89-103; trainer/train_agtt.py:101-112 with the per-batch id
+    idx_offset + num_nodes of the batch's first graph, :131).  -> int32[num_rows] in the epoch's row order."""
+    _require_cuda(ep.X, token_per_batch)
+    pos = torch.empty(ep.num_rows, dtype=torch.int32, device=ep.X.device)
+    if token_per_batch is not None:
+        if token_per_batch.dtype != torch.int64 or token_per_batch.numel() != ep.num_batches:
+            raise ValueError("token_per_batch: one int64 id per batch expected")
+    check(lib.gtok_find_token(_ptr(ep.X), _ptr(ep.xoff), _ptr(ep.lmax), ep.num_rows, ep.batch_size, _ptr(token_per_batch),
+                              int(token), _ptr(pos), _stream()))
+    return pos
+
+
+def graph_labels(csr: CsrBatch, edge_off: Optional[torch.Tensor] = None, cycle: bool = True, distance: bool = False):
+    """Task labels from the canonical CSR: has_cycle int32[G] (the reference's DFS oracle, test/train_performance_test.py:27-67,
+    on an edge list of edge_off[g+1]-edge_off[g] entries; None = simple graph) and the BFS hop count query_u -> query_v
+    int32[G] (-1 = INF).  -> (has_cycle | None, dist | None)."""
+    _require_cuda(csr.node_off, csr.rowptr, edge_off)
+    dev = csr.node_off.device
+    G = csr.num_graphs
+    if distance and (csr.query_u is None or csr.query_v is None):
+        raise ValueError("distance labels need query_u / query_v")
+    cyc = torch.empty(G, dtype=torch.int32, device=dev) if cycle else None
+    dist = torch.empty(G, dtype=torch.int32, device=dev) if distance else None
+    cc = _csr_c(csr)
+    check(lib.gtok_graph_labels(C.byref(cc), _ptr(edge_off), _ptr(cyc), _ptr(dist), _stream()))
+    return cyc, dist
+
+
+ER_BUCKETS = ((10, 20), (20, 40), (40, 50))        # docs/synthetic_data.md:130-138
+
+
+def er_spec(seed: int, graph_id_base: int = 0, buckets=ER_BUCKETS, p_min: float = 0.1, p_max: float = 0.2) -> _lib.ErSpecC:
+    if not 1 <= len(buckets) <= 4:
+        raise ValueError("1..4 size buckets expected")
+    thr = lambda p: max(0, min(0xFFFFFFFF, int(math.floor(float(p) * 4294967296.0))))
+    s = _lib.ErSpecC()
+    s.num_buckets = len(buckets)
+    for i, (lo, hi) in enumerate(buckets):
+        s.n_lo[i], s.n_hi[i] = int(lo), int(hi)
+    s.thr_lo, s.thr_hi = thr(p_min), thr(p_max)
+    s.seed, s.graph_id_base = int(seed) & (2 ** 64 - 1), int(graph_id_base)
+    return s
+
+
+def generate_er(num_graphs: int, seed: int = 0, graph_id_base: int = 0, buckets=ER_BUCKETS, p_min: float = 0.1,
+                p_max: float = 0.2, device="cuda") -> GraphBatch:
+    """Graph-token-shaped Erdos-Renyi graphs generated ON the device (docs/synthetic_data.md:93-94,130-138
+    distribution; stream = oracle/tasks_oracle.py er_graph): every undirected edge once, u < v ascending, plus a
+    query pair per graph.  Keyed by the global graph id, so shards of a larger job generate their own slice."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("gtok has no CPU path: a CUDA device is required")
+    G = int(num_graphs)
+    spec = er_spec(seed, graph_id_base, buckets, p_min, p_max)
+    nn = torch.empty(G, dtype=torch.int32, device=dev)
+    ne = torch.empty(G, dtype=torch.int32, device=dev)
+    qu = torch.empty(G, dtype=torch.int32, device=dev)
+    qv = torch.empty(G, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gtok_er_sizes(C.byref(spec), G, _ptr(nn), _ptr(ne), _ptr(qu), _ptr(qv), _stream()))
+        node_off, edge_off = scan_offsets(nn), scan_offsets(ne)
+        E = int(edge_off[-1]) if G else 0
+        src = torch.empty(E, dtype=torch.int32, device=dev)
+        dst = torch.empty(E, dtype=torch.int32, device=dev)
+        check(lib.gtok_er_edges(C.byref(spec), G, _ptr(edge_off), _ptr(src), _ptr(dst), _stream()))
+    return GraphBatch(node_off, edge_off, src, dst, query_u=qu, query_v=qv)

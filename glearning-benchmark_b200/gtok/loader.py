@@ -49,14 +49,16 @@ class _EpochLoaderBase:
         perm = torch.randperm(self.G, generator=self._gen)[:rows]       # torch's DataLoader draws its permutation the same way
         return perm.to(self.device)
 
-    def _yield(self, ep: engine.PaddedEpoch, order: Optional[torch.Tensor]) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+    def _yield(self, ep: engine.PaddedEpoch, order: Optional[torch.Tensor],
+               q_pos: Optional[torch.Tensor] = None) -> Iterator[Tuple[torch.Tensor, ...]]:
         xoff = ep.xoff.cpu().tolist()
         lmax = ep.lmax.cpu().tolist()
         Y = self.labels if order is None else self.labels[order]
         for k in range(ep.num_batches):
             rows = min(self.B, ep.num_rows - k * self.B)
             sl = slice(xoff[k], xoff[k + 1])
-            yield ep.X[sl].view(rows, lmax[k]), ep.attn[sl].view(rows, lmax[k]), Y[k * self.B:k * self.B + rows]
+            out = (ep.X[sl].view(rows, lmax[k]), ep.attn[sl].view(rows, lmax[k]), Y[k * self.B:k * self.B + rows])
+            yield out if q_pos is None else out + (q_pos[k * self.B:k * self.B + rows],)
 
 
 class IbttEpochLoader(_EpochLoaderBase):
@@ -67,18 +69,23 @@ class IbttEpochLoader(_EpochLoaderBase):
     * `from_ragged`  rows already tokenized (any tokenizer: ZINC, graph-token): gtok_pad_mask_batched with the
                      permutation as batch_idx (K4)."""
 
-    def __init__(self, make_epoch, num_rows, labels, batch_size, shuffle=False, seed=0, drop_last=False, device="cuda"):
+    def __init__(self, make_epoch, num_rows, labels, batch_size, shuffle=False, seed=0, drop_last=False, device="cuda",
+                 query_token: Optional[int] = None):
         super().__init__(num_rows, labels, batch_size, shuffle, seed, drop_last, device)
         self._make_epoch = make_epoch
+        self.query_token = query_token
 
     @classmethod
     def from_graphs(cls, batch: GraphBatch, vocab: Dict[str, int], task: str, max_len: int, labels=None, batch_size: int = 128,
-                    shuffle: bool = False, seed: int = 0, drop_last: bool = False):
+                    shuffle: bool = False, seed: int = 0, drop_last: bool = False, with_q_pos: bool = False):
+        """with_q_pos: batches come as (X, attn, Y, q_pos) - q_pos int32[rows] = first position of <q> in each row
+        (-1 when truncation cut it off), what extract_query_nodes looks up per row (train_ibtt.py:89-103)."""
         max_nodes = int(batch.num_nodes().max()) if batch.num_graphs else 0
 
         def make(order):
             return engine.ibtt_collate_epoch(batch, vocab, task, max_len, batch_size, batch_idx=order, max_nodes=max_nodes)[0]
-        return cls(make, batch.num_graphs, labels, batch_size, shuffle, seed, drop_last, batch.device)
+        return cls(make, batch.num_graphs, labels, batch_size, shuffle, seed, drop_last, batch.device,
+                   query_token=int(vocab["<q>"]) if with_q_pos else None)
 
     @classmethod
     def from_ragged(cls, ragged: engine.Ragged, pad_id: int, labels=None, batch_size: int = 128, shuffle: bool = False,
@@ -92,7 +99,8 @@ class IbttEpochLoader(_EpochLoaderBase):
         self.epoch += 1
         if order is not None and order.numel() == 0:
             return iter(())
-        return self._yield(self._make_epoch(order), order)
+        ep = self._make_epoch(order)
+        return self._yield(ep, order, None if self.query_token is None else engine.query_positions(ep, self.query_token))
 
 
 class AgttEpochLoader(_EpochLoaderBase):
@@ -103,8 +111,12 @@ class AgttEpochLoader(_EpochLoaderBase):
     PAD = 5
 
     def __init__(self, csr: engine.CsrBatch, config: engine.SentConfig, labels=None, batch_size: int = 32, shuffle: bool = False,
-                 seed: int = 0, drop_last: bool = False, graph_id_base: int = 0):
+                 seed: int = 0, drop_last: bool = False, graph_id_base: int = 0, with_q_pos: bool = False):
+        """with_q_pos: batches come as (X, attn, Y, q_pos); the id searched in batch k is the reference's
+        idx_offset + num_nodes of the batch's FIRST graph (train_agtt.py:131), first hit per row (:101-112)."""
         super().__init__(csr.num_graphs, labels, batch_size, shuffle, seed, drop_last, csr.node_off.device)
+        self.with_q_pos = bool(with_q_pos)
+        self._num_nodes = csr.node_off[1:] - csr.node_off[:-1]
         self.csr, self.config, self.seed, self.graph_id_base = csr, config, int(seed), int(graph_id_base)
         need = config.max_length + (3 if config.append_query else 0)
         self.stride = need + (need & 1)
@@ -120,4 +132,9 @@ class AgttEpochLoader(_EpochLoaderBase):
         _, ln = engine.tokenize_sent(self.csr, self.config, seed=seed, graph_id_base=self.graph_id_base, out=self._buf,
                                      stride=self.stride)
         ep = engine.pad_mask_epoch(self._buf.view(-1), self._row_start, ln, self.PAD, self.B, batch_idx=order)
-        return self._yield(ep, order)
+        q_pos = None
+        if self.with_q_pos:
+            first = torch.arange(0, ep.num_rows, self.B, device=self.device)
+            first = first if order is None else order[first]
+            q_pos = engine.query_positions(ep, token_per_batch=self.config.idx_offset + self._num_nodes[first])
+        return self._yield(ep, order, q_pos)

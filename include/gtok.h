@@ -296,6 +296,46 @@ GTOK_API int gtok_pad_mask_batched(const int64_t* tok, const int64_t* row_start,
                           const int64_t* batch_idx, int64_t G, int64_t B, const int32_t* lmax,
                           const int64_t* xoff, int64_t pad_id, int64_t* X, uint8_t* attn, void* stream);
 
+/* K6   the steps around the path: consumer-side query positions, task labels, and an
+ *      on-device Erdos-Renyi generator for fully device-side benchmarks.
+ *
+ *      gtok_find_token: extract_query_nodes (trainer/train_ibtt.py:89-103, trainer/train_agtt.py:101-112) scans
+ *      every row of a batch on the host for the FIRST position of the <q> id.  Here one launch does it for all
+ *      rows of a padded epoch (layout of gtok_pad_mask_batched: batch k at X + xoff[k], [rows_k, lmax[k]]):
+ *      pos_out[r] = first p with X[r, p] == t, else -1; t = token_per_batch[r / B] when given (AGTT: the id is
+ *      idx_offset + num_nodes of the batch's first graph, train_agtt.py:131), else `token`. */
+GTOK_API int gtok_find_token(const int64_t* X, const int64_t* xoff, const int32_t* lmax, int64_t num_rows,
+                             int64_t batch_size, const int64_t* token_per_batch, int64_t token, int32_t* pos_out,
+                             void* stream);
+
+/*      gtok_graph_labels: the two graph-token task labels straight from the canonical CSR.
+ *      has_cycle_out[g] (0/1) = the reference's DFS label oracle (test/train_performance_test.py:27-67) on the
+ *      edge list: true iff M_g > N_g - C_g with C_g connected components and M_g listed edges = edge_off[g+1] -
+ *      edge_off[g] (every extra list entry - a chord, a repeated edge, a self loop - closes a cycle for that
+ *      DFS); edge_off NULL: M_g = CSR entries / 2 (simple graph).  dist_out[g] = BFS hops query_u -> query_v,
+ *      -1 when unreachable / out of range (the generator's `lenK` / `INF` label, data_loader.py:19-41).
+ *      Either output may be NULL; dist needs csr->query_u/query_v. */
+GTOK_API int gtok_graph_labels(const GtokCsrBatch* csr, const int64_t* edge_off, int32_t* has_cycle_out,
+                               int32_t* dist_out, void* stream);
+
+/*      On-device ER graphs with the docs' size / sparsity distribution (docs/synthetic_data.md:93-94,130-138);
+ *      the stream definition is oracle/tasks_oracle.py er_graph (Philox-4x32-10 keyed by seed, counter = global
+ *      graph id, so output is invariant to sharding).  gtok_er_sizes writes per-graph node / edge counts and a
+ *      query pair; the caller scans the counts (gtok_counts_to_offsets) and gtok_er_edges fills src / dst
+ *      (each edge once, u < v ascending - the order graph-token texts list them in). */
+typedef struct GtokErSpec {
+  int32_t num_buckets;       /* 1..4 size buckets, one drawn uniformly per graph */
+  int32_t n_lo[4], n_hi[4];  /* N uniform in [n_lo, n_hi), 1 <= n_lo < n_hi <= 32768 */
+  uint32_t thr_lo, thr_hi;   /* edge probability p ~ U(thr_lo, thr_hi) / 2^32 */
+  int32_t reserved_;
+  uint64_t seed;
+  int64_t graph_id_base;
+} GtokErSpec;
+GTOK_API int gtok_er_sizes(const GtokErSpec* spec, int64_t num_graphs, int32_t* num_nodes_out, int32_t* num_edges_out,
+                           int32_t* query_u_out, int32_t* query_v_out, void* stream);
+GTOK_API int gtok_er_edges(const GtokErSpec* spec, int64_t num_graphs, const int64_t* edge_off, int32_t* src_out,
+                           int32_t* dst_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,138 @@
+"""CPU oracle for the steps AROUND the tokenization path.  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs - never by the product path.
+
+* has_cycle_dfs           restates the reference's own label oracle, test/train_performance_test.py:27-67
+                          (parent-tracking DFS on the UNDIRECTED multigraph built from an edge list that names
+                          every edge once).  That module imports torch_geometric at import time (:22) and the
+                          pre-refactor dataset module (:23), so it cannot be imported here; the
+                          function is 30 lines of list logic and is restated statement for statement.
+* shortest_distance       BFS hop count; the label the graph-token task generator (external alip67/graph-token,
+                          not vendored) writes as `lenK` / `INF` and graph_data_loader/data_loader.py:19-41 parses
+                          back (class = K - 1, INF dropped).
+* first_token_pos         IBTT/AGTT `extract_query_nodes`: position of the FIRST occurrence of the <q> id in a
+                          padded row (trainer/train_ibtt.py:89-103, trainer/train_agtt.py:101-112), -1 when absent.
+* er_graph                the engine's own on-device Erdos-Renyi generator, defined HERE (it is synthetic data; the
+                          reference's generator is networkx inside the external graph-token repo, driven by Python's
+                          `random`, and is not reproducible from any seed we could share).  Distribution follows
+                          docs/synthetic_data.md:93-94,130-138: size bucket uniform over {[10,20),[20,40),[40,50)},
+                          N uniform in the bucket, p ~ U(0.1, 0.2), pairs u < v in ascending order.
+
+Parity status: has_cycle_dfs and first_token_pos are PINNED to outputs of the reference itself
+(tests/golden/tasks_labels.json, produced by tests/golden/make_tasks_golden.py, which lifts has_cycle_dfs out of the
+reference file with `ast` and runs it unmodified on 400 seeded multigraph edge lists, and evaluates the trainer's
+first-<q> expression with torch).  shortest_distance has no in-repo reference implementation (checked against
+networkx in tests/test_oracle_tasks.py); er_graph is engine-defined - the oracle is the specification.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .sent_oracle import philox4x32_10
+
+_MASK = 0xFFFFFFFF
+ER_STREAM = 1          # Philox counter word 3: keeps the generator's stream apart from the SENT walk's (stream 0)
+ER_PAIR_WORD0 = 8      # pair k of a graph reads word ER_PAIR_WORD0 + k of the graph's stream
+
+
+def has_cycle_dfs(num_nodes: int, edge_list: Sequence[Tuple[int, int]]) -> bool:
+    """test/train_performance_test.py:27-67, recursion unrolled into an explicit stack (same visiting order)."""
+    if len(edge_list) == 0:
+        return False
+    adj: List[List[int]] = [[] for _ in range(num_nodes)]
+    for s, t in edge_list:
+        adj[s].append(t)
+        adj[t].append(s)
+    visited = [False] * num_nodes
+    for root in range(num_nodes):
+        if visited[root]:
+            continue
+        visited[root] = True
+        stack = [(root, -1, 0)]
+        while stack:
+            node, parent, i = stack.pop()
+            if i < len(adj[node]):
+                stack.append((node, parent, i + 1))
+                nb = adj[node][i]
+                if not visited[nb]:
+                    visited[nb] = True
+                    stack.append((nb, node, 0))
+                elif nb != parent:
+                    return True
+    return False
+
+
+def shortest_distance(num_nodes: int, edge_list: Sequence[Tuple[int, int]], u: int, v: int) -> int:
+    """Hops from u to v over the undirected graph; -1 when unreachable or when u / v is not a node."""
+    if not (0 <= u < num_nodes and 0 <= v < num_nodes):
+        return -1
+    adj: List[List[int]] = [[] for _ in range(num_nodes)]
+    for s, t in edge_list:
+        adj[s].append(t)
+        adj[t].append(s)
+    dist = {u: 0}
+    frontier = [u]
+    while frontier:
+        nxt = []
+        for a in frontier:
+            for b in adj[a]:
+                if b not in dist:
+                    dist[b] = dist[a] + 1
+                    nxt.append(b)
+        frontier = nxt
+    return dist.get(v, -1)
+
+
+def distance_label_token(d: int) -> str:
+    return "INF" if d < 0 else f"len{d}"
+
+
+def first_token_pos(row: Sequence[int], token: int) -> int:
+    for i, t in enumerate(row):
+        if int(t) == token:
+            return i
+    return -1
+
+
+# --------------------------------------------------------------------------- ER generator (engine-defined)
+class _Words:
+    def __init__(self, seed: int, gid: int):
+        self.key = (seed & _MASK, (seed >> 32) & _MASK)
+        self.gid = gid
+        self._cache = {}
+
+    def __call__(self, d: int) -> int:
+        b = d >> 2
+        if b not in self._cache:
+            self._cache[b] = philox4x32_10((self.gid & _MASK, (self.gid >> 32) & _MASK, b, ER_STREAM), self.key)
+        return self._cache[b][d & 3]
+
+
+def prob_threshold(p: float) -> int:
+    """P(edge) = thr / 2^32, thr = floor(p * 2^32) clipped to u32 (the host computes this once for p_min / p_max)."""
+    return max(0, min(_MASK, int(np.floor(float(p) * 4294967296.0))))
+
+
+def er_graph(seed: int, gid: int, buckets: Sequence[Tuple[int, int]] = ((10, 20), (20, 40), (40, 50)),
+             p_min: float = 0.1, p_max: float = 0.2):
+    """-> (n, edges [(u, v)] with u < v ascending, (query_u, query_v)).
+    word 0: bucket = mulhi(w, len(buckets));  word 1: n = lo + mulhi(w, hi - lo);
+    word 2: thr = t_lo + mulhi(w, t_hi - t_lo);  word 3: query_u = mulhi(w, n);
+    word 4: query_v = (query_u + 1 + mulhi(w, n - 1)) % n  (n == 1: query_v = query_u);
+    pair k (row-major over u < v) is an edge iff word(8 + k) < thr."""
+    w = _Words(seed, gid)
+    lo, hi = buckets[(w(0) * len(buckets)) >> 32]
+    n = lo + ((w(1) * (hi - lo)) >> 32)
+    t_lo, t_hi = prob_threshold(p_min), prob_threshold(p_max)
+    thr = t_lo + ((w(2) * (t_hi - t_lo)) >> 32)
+    qu = (w(3) * n) >> 32
+    qv = (qu + 1 + ((w(4) * (n - 1)) >> 32)) % n if n > 1 else qu
+    edges = []
+    k = 0
+    for u in range(n):
+        for v in range(u + 1, n):
+            if w(ER_PAIR_WORD0 + k) < thr:
+                edges.append((u, v))
+            k += 1
+    return n, edges, (qu, qv)

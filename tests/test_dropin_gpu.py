@@ -192,3 +192,41 @@ def test_epoch_loaders_match_reference_collate():
             cache[(ep, i)] = S.sent_tokenize(recs[i]["n"], rp, col, ocfg, S.PhiloxWords(seed, i))
         return cache[(ep, i)]
     check(AgttEpochLoader(csr, cfg, labels, 32, shuffle=True, seed=11), sent_row, 5, 11)
+
+
+def test_epoch_loaders_query_positions():
+    """with_q_pos: every batch carries the position extract_query_nodes would find by scanning the row on the host
+    (train_ibtt.py:91-96 with vocab['<q>']; train_agtt.py:101-112,131 with idx_offset + num_nodes of the batch's
+    first graph - which can collide with a node-position token of a larger graph, quirk C9, reproduced)."""
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    from gtok.loader import AgttEpochLoader, IbttEpochLoader
+    from helpers import gt_examples
+    from oracle import ibtt_oracle as O
+    dev = torch.device("cuda:0")
+    recs, texts, ex = gt_examples("shortest_path", 200, seed=6)
+    vocab, _ = O.vocab_from_texts(texts, max_tokens=600)
+    gb = GraphBatch.from_lists([r["n"] for r in recs], [r["edges"] for r in recs], queries=[r["query"] for r in recs]).to(dev)
+    for max_len in (600, 120):
+        n_rows = 0
+        for X, A, Y, qp in IbttEpochLoader.from_graphs(gb, vocab, "shortest_path", max_len, None, 32, shuffle=True, seed=1, with_q_pos=True):
+            assert qp.dtype == torch.int32 and qp.numel() == X.shape[0]
+            for b in range(X.shape[0]):
+                nz = (X[b] == vocab["<q>"]).nonzero(as_tuple=True)[0]
+                assert int(qp[b]) == (int(nz[0]) if len(nz) else -1)
+            n_rows += X.shape[0]
+        assert n_rows == 200
+    csr = engine.build_csr(gb)
+    cfg = engine.SentConfig(idx_offset=6, max_length=600, append_query=True)
+    loader = AgttEpochLoader(csr, cfg, None, 16, shuffle=True, seed=3, with_q_pos=True)
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(3)
+    order = torch.randperm(200, generator=gen).tolist()
+    found = 0
+    for k, (X, A, Y, qp) in enumerate(loader):
+        q_id = 6 + recs[order[k * 16]]["n"]                      # data_list[0].num_nodes
+        for b in range(X.shape[0]):
+            nz = (X[b] == q_id).nonzero(as_tuple=True)[0]
+            assert int(qp[b]) == (int(nz[0]) if len(nz) else -1)
+            found += len(nz) > 0
+    assert found > 0

@@ -812,3 +812,123 @@ def test_batches_without_any_edge(dev):
         rp, col, _ = S.canonical_csr(n, [], [])
         w = S.sent_tokenize(n, rp, col, S.SentConfig(idx_offset=6, max_length=100), S.PhiloxWords(1, g))
         assert tok[g, :int(ln[g])].cpu().tolist() == w.tolist()
+
+
+# --------------------------------------------------------------------------- K6
+def test_graph_labels_match_reference_golden(dev):
+    """has_cycle from the kernels == the reference's own DFS label oracle (golden fixture), on both kernels
+    (thread-per-graph bit rows; warp-per-graph bitmaps) with repeated edges and self loops in the lists."""
+    import json
+    import os
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    from oracle import tasks_oracle as T
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tasks_labels.json")))["cycle_cases"]
+    rng = np.random.default_rng(0)
+    qs = [(int(rng.integers(0, c["n"])), int(rng.integers(0, c["n"]))) for c in gold]
+    gb = GraphBatch.from_lists([c["n"] for c in gold], [[tuple(e) for e in c["edges"]] for c in gold], queries=qs).to(dev)
+    csr = engine.build_csr(gb)
+    want_c = [int(c["has_cycle"]) for c in gold]
+    want_d = [T.shortest_distance(c["n"], [tuple(e) for e in c["edges"]], u, v) for c, (u, v) in zip(gold, qs)]
+    assert csr.adj64 is not None and csr.adj_words == 1
+    cyc, dist = engine.graph_labels(csr, edge_off=gb.edge_off, distance=True)
+    assert cyc.cpu().tolist() == want_c and dist.cpu().tolist() == want_d
+    import dataclasses
+    general = dataclasses.replace(csr, adj64=None)                        # force the warp-per-graph kernel
+    cyc2, dist2 = engine.graph_labels(general, edge_off=gb.edge_off, distance=True)
+    assert cyc2.cpu().tolist() == want_c and dist2.cpu().tolist() == want_d
+    only_c, none_d = engine.graph_labels(csr, edge_off=gb.edge_off)
+    assert none_d is None and only_c.cpu().tolist() == want_c
+
+
+@pytest.mark.parametrize("N", [64, 65, 300, 2500])
+def test_graph_labels_larger_graphs_vs_oracle(dev, N):
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    from oracle import tasks_oracle as T
+    rng = np.random.default_rng(N)
+    recs = []
+    for i in range(24):
+        n = int(rng.integers(max(2, N // 2), N + 1))
+        if i % 3 == 0:      # forest with a few components
+            edges = [(int(rng.integers(max(0, v - 40), v)), v) for v in range(1, n) if rng.random() < 0.97]
+        elif i % 3 == 1:    # long path (deep BFS) + chords
+            edges = [(v - 1, v) for v in range(1, n)] + [(int(a), int(b)) for a, b in zip(rng.integers(0, n, 3), rng.integers(0, n, 3)) if a != b]
+        else:               # sparse ER-like, mean degree ~2: many components, unreachable pairs
+            m = n
+            edges = list({(int(min(a, b)), int(max(a, b))) for a, b in zip(rng.integers(0, n, m), rng.integers(0, n, m)) if a != b})
+        recs.append((n, edges, (int(rng.integers(0, n)), int(rng.integers(0, n)))))
+    gb = GraphBatch.from_lists([r[0] for r in recs], [r[1] for r in recs], queries=[r[2] for r in recs]).to(dev)
+    csr = engine.build_csr(gb)
+    cyc, dist = engine.graph_labels(csr, edge_off=gb.edge_off, distance=True)
+    assert cyc.cpu().tolist() == [int(T.has_cycle_dfs(n, e)) for n, e, _ in recs]
+    assert dist.cpu().tolist() == [T.shortest_distance(n, e, u, v) for n, e, (u, v) in recs]
+    simple, _ = engine.graph_labels(csr)                                   # edge_off None: M = CSR entries / 2
+    assert simple.cpu().tolist() == [int(T.has_cycle_dfs(n, sorted(set(e)))) for n, e, _ in recs]
+
+
+def test_query_positions_vs_reference_expression(dev, golden_gt):
+    """gtok_find_token on real padded epochs == (x[b] == q).nonzero()[0] row by row (train_ibtt.py:91-96), for the
+    IBTT <q> id, for a per-batch id (AGTT, train_agtt.py:131) and for an id that is absent / cut off by truncation."""
+    from gtok import engine
+    recs, texts, ex = gt_examples("shortest_path", 300, seed=9)
+    vocab, _ = O.vocab_from_texts(texts)
+    gb = _gb_from_recs(recs, True).to(dev)
+    for max_len, B in ((600, 32), (90, 7)):
+        ep, _ = engine.ibtt_collate_epoch(gb, vocab, "shortest_path", max_len, B)
+        per_batch = torch.tensor([vocab["<q>"] if k % 3 else vocab.get("5", 0) for k in range(ep.num_batches)], dtype=torch.int64, device=dev)
+        for tok, tpb in ((vocab["<q>"], None), (10 ** 9, None), (0, per_batch)):
+            pos = engine.query_positions(ep, tok, tpb).cpu().tolist()
+            r = 0
+            for k in range(ep.num_batches):
+                X, _ = ep.batch(k)
+                t = int(per_batch[k]) if tpb is not None else tok
+                for b in range(X.shape[0]):
+                    nz = (X[b] == t).nonzero(as_tuple=True)[0]
+                    assert pos[r] == (int(nz[0]) if len(nz) else -1), (max_len, k, b)
+                    r += 1
+            assert r == ep.num_rows
+
+
+def test_generate_er_matches_oracle_and_shards(dev):
+    """On-device ER graphs == oracle/tasks_oracle.py er_graph bit for bit; a shard generated with graph_id_base is
+    the same slice of the full job; labels from the generated graphs agree with the DFS / BFS oracles; the generated
+    batch tokenizes through K1."""
+    from gtok import engine
+    from oracle import tasks_oracle as T
+    G = 700
+    gb = engine.generate_er(G, seed=5, device=dev)
+    n = gb.num_nodes().cpu().tolist()
+    eo = gb.edge_off.cpu().tolist()
+    src, dst = gb.src.cpu().tolist(), gb.dst.cpu().tolist()
+    qu, qv = gb.query_u.cpu().tolist(), gb.query_v.cpu().tolist()
+    recs = []
+    for g in range(G):
+        wn, we, (wu, wv) = T.er_graph(5, g)
+        assert n[g] == wn and (qu[g], qv[g]) == (wu, wv), g
+        assert list(zip(src[eo[g]:eo[g + 1]], dst[eo[g]:eo[g + 1]])) == we, g
+        recs.append((wn, we, (wu, wv)))
+    part = engine.generate_er(200, seed=5, graph_id_base=300, device=dev)
+    assert part.num_nodes().cpu().tolist() == n[300:500]
+    assert part.src.cpu().tolist() == src[eo[300]:eo[500]] and part.query_v.cpu().tolist() == qv[300:500]
+    csr = engine.build_csr(gb)
+    cyc, dist = engine.graph_labels(csr, edge_off=gb.edge_off, distance=True)
+    assert cyc.cpu().tolist() == [int(T.has_cycle_dfs(a, e)) for a, e, _ in recs]
+    assert dist.cpu().tolist() == [T.shortest_distance(a, e, u, v) for a, e, (u, v) in recs]
+    labels = [T.distance_label_token(d) for d in dist.cpu().tolist()]
+    vocab, _ = engine.vocab_from_graphs(gb, "shortest_path", labels)
+    texts = [O.graph_token_text(a, e, "shortest_path", lt, q) for (a, e, q), lt in zip(recs, labels)]
+    assert vocab == O.vocab_from_texts(texts)[0]
+    rows = engine.tokenize_ibtt(gb, vocab, "shortest_path", 600).rows_cpu()
+    for t, got in zip(texts[:100], rows[:100]):
+        assert got.tolist() == O.encode_text(t, vocab, 600)
+    # other bucket shapes: one node (no pair), larger graphs (several Philox trips per lane), p = 0
+    for buckets, p0, p1, gcount in ((((1, 3),), 0.5, 0.5, 64), (((150, 260), (2, 9)), 0.01, 0.08, 40), (((5, 30),), 0.0, 0.0, 33)):
+        b2 = engine.generate_er(gcount, seed=11, buckets=buckets, p_min=p0, p_max=p1, device=dev)
+        n2, eo2 = b2.num_nodes().cpu().tolist(), b2.edge_off.cpu().tolist()
+        s2, d2 = b2.src.cpu().tolist(), b2.dst.cpu().tolist()
+        for g in range(gcount):
+            wn, we, wq = T.er_graph(11, g, buckets=buckets, p_min=p0, p_max=p1)
+            assert n2[g] == wn and list(zip(s2[eo2[g]:eo2[g + 1]], d2[eo2[g]:eo2[g + 1]])) == we, (buckets, g)
+            assert (int(b2.query_u[g]), int(b2.query_v[g])) == wq
+    assert engine.generate_er(0, device=dev).num_graphs == 0

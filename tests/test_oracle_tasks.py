@@ -1,0 +1,115 @@
+"""tasks oracle self-checks: the restated DFS label oracle against brute force and against the
+"listed edges > N - components" form the kernels use, BFS distances against networkx, the first-<q> scan against
+the reference's own expression, and the engine-defined ER stream (shape, determinism, distribution)."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ibtt_oracle as O
+from oracle import tasks_oracle as T
+
+
+def _components(n, edges):
+    parent = list(range(n))
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+    for u, v in edges:
+        parent[find(u)] = find(v)
+    return len({find(a) for a in range(n)})
+
+
+def test_has_cycle_dfs_known_cases():
+    assert T.has_cycle_dfs(3, []) is False
+    assert T.has_cycle_dfs(3, [(0, 1), (1, 2)]) is False
+    assert T.has_cycle_dfs(3, [(0, 1), (1, 2), (0, 2)]) is True
+    assert T.has_cycle_dfs(4, [(0, 1), (2, 3)]) is False
+    assert T.has_cycle_dfs(2, [(0, 1), (0, 1)]) is True          # a repeated edge closes a cycle for that DFS
+    assert T.has_cycle_dfs(2, [(0, 1), (1, 0)]) is True
+    assert T.has_cycle_dfs(3, [(1, 1)]) is True                  # and so does a self loop
+    assert T.has_cycle_dfs(5, [(0, 1), (1, 2), (3, 4), (4, 3)]) is True
+
+
+def test_has_cycle_equals_edge_count_form():
+    """The kernels compute the label as M > N - C; exhaustive over multigraph edge lists on <= 4 nodes, random beyond."""
+    for n in (1, 2, 3, 4):
+        pairs = [(u, v) for u in range(n) for v in range(n)]
+        for m in range(0, 4):
+            for edges in itertools.product(pairs, repeat=m):
+                assert T.has_cycle_dfs(n, list(edges)) == (len(edges) > n - _components(n, edges)), (n, edges)
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        n = int(rng.integers(1, 30))
+        m = int(rng.integers(0, 2 * n))
+        edges = [(int(a), int(b)) for a, b in zip(rng.integers(0, n, m), rng.integers(0, n, m))]
+        assert T.has_cycle_dfs(n, edges) == (len(edges) > n - _components(n, edges))
+
+
+def test_shortest_distance_vs_networkx():
+    nx = pytest.importorskip("networkx")
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        n = int(rng.integers(1, 40))
+        g = nx.gnp_random_graph(n, float(rng.uniform(0.02, 0.3)), seed=int(rng.integers(0, 1 << 30)))
+        u, v = int(rng.integers(0, n)), int(rng.integers(0, n))
+        try:
+            want = nx.shortest_path_length(g, u, v)
+        except nx.NetworkXNoPath:
+            want = -1
+        assert T.shortest_distance(n, list(g.edges()), u, v) == want
+    assert T.shortest_distance(3, [(0, 1)], 0, 5) == -1
+    assert T.distance_label_token(-1) == "INF" and T.distance_label_token(3) == "len3"
+    # the label the reference parses back: lenK -> class K - 1, INF -> dropped (data_loader.py:19-41)
+    assert O.distance_label("<q> shortest_distance 0 1 <p> len3 <eos>") == 2
+    assert O.distance_label("<q> shortest_distance 0 1 <p> INF <eos>") is None
+
+
+def test_first_token_pos_is_the_reference_expression():
+    """(x[b] == q).nonzero()[0] of trainer/train_ibtt.py:91-96."""
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        row = rng.integers(0, 6, int(rng.integers(1, 40)))
+        q = int(rng.integers(0, 7))
+        nz = (torch.from_numpy(row) == q).nonzero(as_tuple=True)[0]
+        assert T.first_token_pos(row, q) == (int(nz[0]) if len(nz) else -1)
+
+
+def test_er_graph_stream():
+    seen_b = set()
+    dens = []
+    for gid in range(400):
+        n, edges, (qu, qv) = T.er_graph(7, gid)
+        assert 10 <= n < 50 and 0 <= qu < n and 0 <= qv < n and qu != qv
+        assert edges == sorted(set(edges)) and all(u < v < n for u, v in edges)
+        seen_b.add(0 if n < 20 else (1 if n < 40 else 2))
+        dens.append(len(edges) / (n * (n - 1) / 2))
+        if gid < 5:
+            assert T.er_graph(7, gid) == (n, edges, (qu, qv))
+            assert T.er_graph(8, gid) != (n, edges, (qu, qv))
+    assert seen_b == {0, 1, 2}
+    assert 0.13 < float(np.mean(dens)) < 0.17            # p ~ U(0.1, 0.2)
+    n, edges, q = T.er_graph(0, 0, buckets=((1, 2),))
+    assert n == 1 and edges == [] and q == (0, 0)
+    assert T.er_graph(0, 3, buckets=((5, 6),), p_min=1.0, p_max=1.0)[1] == [(u, v) for u in range(5) for v in range(u + 1, 5)] \
+        or T.prob_threshold(1.0) == 0xFFFFFFFF           # p = 1 saturates at (2^32 - 1) / 2^32
+    assert T.er_graph(0, 3, buckets=((5, 6),), p_min=0.0, p_max=0.0)[1] == []
+
+
+def test_oracle_matches_reference_golden():
+    """tests/golden/tasks_labels.json holds outputs of the reference's own has_cycle_dfs (lifted out of
+    test/train_performance_test.py by tests/golden/make_tasks_golden.py) and of the trainer's first-<q> expression."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tasks_labels.json")))
+    assert len(gold["cycle_cases"]) == 400
+    for c in gold["cycle_cases"]:
+        edges = [tuple(e) for e in c["edges"]]
+        assert T.has_cycle_dfs(c["n"], edges) == c["has_cycle"]
+        assert (len(edges) > c["n"] - _components(c["n"], edges)) == c["has_cycle"]
+    for r in gold["query_rows"]:
+        assert T.first_token_pos(r["row"], r["q"]) == r["pos"]
