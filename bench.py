@@ -252,6 +252,25 @@ def run_extras(dev, G, peak):
     sent("sent_zinc", zb, cfgz, 384, True, 0)
     out["sent_zinc"]["workload"] = (f"{G} ZINC-shaped graphs, labeled SENT + fused remap_zinc_tokens, row capacity 384 "
                                     "(no row reaches it) (BASELINE configs[3] shape, per-GPU shard)")
+    # around the path: graphs generated on the device, task labels, query positions
+    ms_gen = timeit(lambda: engine.generate_er(G, seed=1, device=dev), 5, 2)
+    eb = engine.generate_er(G, seed=1, device=dev)
+    ecsr = engine.build_csr(eb)
+    ms_lab = timeit(lambda: engine.graph_labels(ecsr, edge_off=eb.edge_off, distance=True), 5, 2)
+    cyc, dist = engine.graph_labels(ecsr, edge_off=eb.edge_off, distance=True)
+    vq = dict(vocab)
+    vq["shortest_distance"] = len(vq)
+    epq, _ = engine.ibtt_collate_epoch(eb, vq, "shortest_path", 600, BATCH)
+    ms_q = timeit(lambda: engine.query_positions(epq, vq["<q>"]), 5, 2)
+    qp = engine.query_positions(epq, vq["<q>"])
+    out["around_the_path"] = {
+        "workload": f"{G} ER graphs generated on the device (docs size / sparsity distribution), cycle + shortest-distance "
+                    "labels from the CSR, first-<q> position of every padded row",
+        "generate_er_ms": ms_gen, "generate_er_graphs_per_s": G / ms_gen * 1e3, "edges": int(eb.src.numel()),
+        "graph_labels_ms": ms_lab, "cyclic_frac": float(cyc.float().mean()), "reachable_frac": float((dist >= 0).float().mean()),
+        "query_positions_ms": ms_q, "query_positions_GBps": 8 * float((qp.to(torch.int64) + 1).sum()) / ms_q / 1e6,
+        "rows_with_q": int((qp >= 0).sum())}
+    del eb, ecsr, epq
     # the headline workload on the compact resident layout (16-bit columns + byte atoms, GtokPackedMolBatch)
     import ctypes as C
     from gtok import _lib

@@ -1,8 +1,8 @@
 // gtok_tasks.cu - K6: the steps either side of the tokenization path.
 //
 //   find_token_kernel   extract_query_nodes' per-row host scan for the first <q> (trainer/train_ibtt.py:89-103,
-//                       trainer/train_agtt.py:101-112) for every row of a padded epoch: a warp per row, 256 bytes
-//                       per trip, stops at the first hit.  8 bytes per cell up to the hit.
+//                       trainer/train_agtt.py:101-112) for every row of a padded epoch: a warp per row, 1 KB in
+//                       flight per trip, stops after the trip with the first hit.  8 bytes per cell up to the hit.
 //   labels_*_kernel     cycle_check / shortest_path labels from the canonical CSR (the reference's DFS label
 //                       oracle, test/train_performance_test.py:27-67, as "listed edges > N - components"; BFS hop
 //                       count for `lenK` / INF).  <= 64 nodes: a thread per graph on the 64-bit adjacency rows,
@@ -32,10 +32,18 @@ find_token_kernel(const int64_t* __restrict__ X, const int64_t* __restrict__ xof
     const int64_t* __restrict__ row = X + __ldg(xoff + k) + (r - k * B) * (int64_t)L;
     const int64_t t = tok_per_batch ? __ldg(tok_per_batch + k) : token;
     int pos = -1;
-    for (int p0 = 0; p0 < L; p0 += kWarp) {
-      const int p = p0 + lane;
-      const unsigned hit = __ballot_sync(kFull, p < L && __ldg(row + p) == t);
-      if (hit) { pos = p0 + __ffs(hit) - 1; break; }
+    for (int p0 = 0; p0 < L && pos < 0; p0 += 4 * kWarp) {       // four 256-byte loads in flight per trip
+      int64_t val[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = p0 + j * kWarp + lane;
+        val[j] = p < L ? __ldg(row + p) : ~t;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned hit = __ballot_sync(kFull, val[j] == t);
+        if (hit && pos < 0) pos = p0 + j * kWarp + __ffs(hit) - 1;
+      }
     }
     if (lane == 0) pos_out[r] = pos;
   }

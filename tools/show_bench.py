@@ -11,6 +11,9 @@ print("  roofline", d["roofline"])
 print("  step_roofline", round(d["step_roofline"]["frac"], 3), d["clocks"])
 print("  cpu_baseline", d.get("cpu_baseline"))
 for k, v in (d.get("extras") or {}).items():
+    if "ms_per_step" not in v:
+        print(f"  extra {k}: " + "  ".join(f"{a}={b:.4g}" if isinstance(b, float) else f"{a}={b}" for a, b in v.items() if a != "workload"))
+        continue
     print(f"  extra {k}: {v.get('ms_per_step'):.3f} ms/step  {v.get('graphs_per_s', 0) / 1e6:.0f} Mgraphs/s  frac {v.get('frac')}" +
           (f"  | +collate {v['collate_ms']:.3f} ms (frac {v['collate_frac']:.2f}) -> epoch {v['epoch_graphs_per_s'] / 1e6:.0f} Mgraphs/s" if 'collate_ms' in v else ""))
     for kk, vv in (v.get("kernels") or {}).items():
