@@ -19,11 +19,9 @@
 // Random words: Philox-4x32-10 keyed by the seed, counter = (global graph id,
 // decision >> 2), or an explicit per-graph choice stream (deterministic replay).
 // Algorithmic bytes / graph: 4(N+1) + 4 nnz (CSR) [+4N + 4 nnz labels] + 8 L.
-#include "gtok_common.cuh"
+#include "gtok_sent_common.cuh"
 
 namespace gtok {
-
-constexpr int SOS = 0, RESET = 1, LADJ = 2, RADJ = 3, EOS = 4;
 
 __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
                                               unsigned k1, unsigned (&o)[4]) {
@@ -207,106 +205,90 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
     if (N > 0) {
       int nvis = 0, prev = -1;
       int cur = pick(N);
+      int lo = RP(cur), hi = RP(cur + 1);
       while (len < Lcap) {
-        const int lo = RP(cur), hi = RP(cur + 1);
         const int vc = vis[cur];
-        if (vc < 0) {
-          // ---- first visit: node token [+ label], then bracketed neighbourhood set
-          const int nv = nvis;
-          const int nwords = (nv + 31) >> 5;
-          for (int i = lane; i < nwords; i += kWarp) bits[i] = 0u;
-          if (lane == 0) {
-            vis[cur] = (short)nv;
-            visb[cur >> 5] |= 1u << (cur & 31);
-            put(len, cfg.idx_offset + nv);
-            if (LABELED) put(len + 1, cfg.node_idx_offset + __ldg(c.x + n0 + cur));
+        if (hi - lo <= kWarp) {
+          // ---- fast path: the whole row sits in the lanes (lane <-> neighbour).  The row extents of every
+          // neighbour are requested right away and the rows of the candidates are prefetched, so the next step
+          // finds its (lo, hi) in a register and its row in L1 / L2: one dependent HBM round trip per step
+          // instead of three (rowptr, col, col again).
+          const int e = lo + lane;
+          const bool valid = e < hi;
+          const int u = valid ? COL(e) : 0;
+          int rlo = 0, rhi = 0, eav = 0;
+          if (valid) {
+            rlo = RP(u); rhi = RP(u + 1);
+            if (LABELED) eav = EA(e);
           }
-          len += per;
-          ++nvis;
-          __syncwarp();
-          int closed = 0;
-          for (int e0 = lo; e0 < hi; e0 += kWarp) {
-            const int e = e0 + lane;
+          const int vu = valid ? (int)vis[u] : 0;
+          if (vc < 0) {
+            // first visit: node token [+ label], then the bracketed set of visited neighbours (not the one we came
+            // from) in ascending visit index - ranked inside the warp, no bitmap
+            const int nv = nvis;
+            if (lane == 0) {
+              vis[cur] = (short)nv;
+              visb[cur >> 5] |= 1u << (cur & 31);
+              put(len, cfg.idx_offset + nv);
+              if (LABELED) put(len + 1, cfg.node_idx_offset + __ldg(c.x + n0 + cur));
+            }
+            len += per;
+            ++nvis;
             bool z = false;
-            if (e < hi) {
-              const int u = COL(e);
-              const int vu = vis[u];
-              const int r = (int)rem[u] - 1;                    // cur stops being an unvisited neighbour of u
+            if (valid) {
+              const int r = (int)rem[u] - 1;                      // cur stops being an unvisited neighbour of u
               rem[u] = (unsigned short)r;
-              if (vu >= 0 && u != cur) {
-                if (r == 0) { z = true; atomicAnd(&openb[u >> 5], ~(1u << (u & 31))); }
-                if (u != prev) {
-                  atomicOr(&bits[vu >> 5], 1u << (vu & 31));
-                  if (LABELED) ent[vu] = e;
+              z = vu >= 0 && r == 0;
+              if (z) atomicAnd(&openb[u >> 5], ~(1u << (u & 31)));
+            }
+            nopen -= __popc(__ballot_sync(kFull, z));
+            const bool member = valid && vu >= 0 && u != prev;
+            const unsigned mm = __ballot_sync(kFull, member);
+            if (mm) {
+              const int M = __popc(mm);
+              int rank = 0;
+              for (unsigned t = mm; t; t &= t - 1) rank += (__shfl_sync(kFull, vu, __ffs(t) - 1) < vu) ? 1 : 0;
+              if (member) {
+                const int pos = len + 1 + rank * per;
+                if (LABELED) {
+                  put(pos, cfg.edge_idx_offset + eav + cfg.edge_label_shift);
+                  put(pos + 1, cfg.idx_offset + vu);
+                } else {
+                  put(pos, cfg.idx_offset + vu);
                 }
               }
+              if (lane == 0) { put(len, LADJ); put(len + 1 + M * per, RADJ); }
+              len += 2 + M * per;
             }
-            closed += __popc(__ballot_sync(kFull, z));
-          }
-          nopen -= closed;
-          __syncwarp();
-          if (rem[cur] > 0) {                                   // cur joins the restart candidates
-            if (lane == 0) openb[cur >> 5] |= 1u << (cur & 31);
-            ++nopen;
-          }
-          int M = 0;
-          for (int w0 = 0; w0 < nwords; w0 += kWarp) {
-            unsigned word = (w0 + lane < nwords) ? bits[w0 + lane] : 0u;
-            const int cw = __popc(word);
-            int incl = cw;
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-              const int o = __shfl_up_sync(kFull, incl, dd);
-              if (lane >= dd) incl += o;
-            }
-            int j = M + incl - cw;
-            while (word) {
-              const int bpos = __ffs(word) - 1;
-              word &= word - 1;
-              const int vi = ((w0 + lane) << 5) + bpos;
-              const int pos = len + 1 + j * per;
-              if (LABELED) {
-                put(pos, cfg.edge_idx_offset + EA(ent[vi]) + cfg.edge_label_shift);
-                put(pos + 1, cfg.idx_offset + vi);
-              } else {
-                put(pos, cfg.idx_offset + vi);
-              }
-              ++j;
-            }
-            M += __shfl_sync(kFull, incl, 31);
-          }
-          if (M > 0) {
-            if (lane == 0) { put(len, LADJ); put(len + 1 + M * per, RADJ); }
-            len += 2 + M * per;
-          }
-        } else {
-          if (lane == 0) put(len, cfg.idx_offset + vc);  // head of a new segment at a visited node
-          len += 1;
-        }
-        __syncwarp();
-        const int cnt = rem[cur];
-        if (cnt > 0) {
-          // ---- trail step to the k-th unvisited neighbour (CSR order)
-          const int k = pick(cnt);
-          int seen = 0, ne = -1;
-          for (int e0 = lo; e0 < hi && ne < 0; e0 += kWarp) {
-            const int e = e0 + lane;
-            const bool f = e < hi && vis[COL(e)] < 0;
-            const unsigned m = __ballot_sync(kFull, f);
-            const int cch = __popc(m);
-            if (k < seen + cch) {
-              const unsigned sel = __ballot_sync(kFull, f && (__popc(m & ((1u << lane) - 1)) == k - seen));
-              ne = e0 + __ffs(sel) - 1;
-            }
-            seen += cch;
-          }
-          if (LABELED) {
-            if (lane == 0) put(len, cfg.edge_idx_offset + EA(ne) + cfg.edge_label_shift);
+          } else {
+            if (lane == 0) put(len, cfg.idx_offset + vc);        // head of a new segment at a visited node
             len += 1;
           }
-          prev = cur;
-          cur = COL(ne);
-        } else {
+          const unsigned fm = __ballot_sync(kFull, valid && vu < 0);   // unvisited neighbours, CSR order
+          const int cnt = __popc(fm);                                  // == rem[cur]
+          if (cnt > 0) {
+            if (vc < 0) {                                              // cur joins the restart candidates
+              if (lane == 0) openb[cur >> 5] |= 1u << (cur & 31);
+              ++nopen;
+            }
+            if (CSRG && ((fm >> lane) & 1u)) {
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(g_col + rlo));
+              if (LABELED) asm volatile("prefetch.global.L1 [%0];" ::"l"(g_ea + rlo));
+            }
+            const int sl = select32(fm, pick(cnt));
+            if (LABELED) {
+              const int eas = __shfl_sync(kFull, eav, sl);
+              if (lane == 0) put(len, cfg.edge_idx_offset + eas + cfg.edge_label_shift);
+              len += 1;
+            }
+            prev = cur;
+            cur = __shfl_sync(kFull, u, sl);
+            lo = __shfl_sync(kFull, rlo, sl);
+            hi = __shfl_sync(kFull, rhi, sl);
+            __syncwarp();
+            continue;
+          }
+          __syncwarp();
           if (nvis == N) break;
           // ---- restart: visited nodes with unvisited neighbours, else unvisited nodes
           int nxt;
@@ -316,6 +298,120 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
           len += 1;
           cur = nxt;
           prev = -1;
+          lo = RP(cur); hi = RP(cur + 1);
+          continue;
+        }
+        // ---- rows longer than a warp: chunked row scans, bracket members ranked through a visit-index bitmap
+        {
+          if (vc < 0) {
+            // ---- first visit: node token [+ label], then bracketed neighbourhood set
+            const int nv = nvis;
+            const int nwords = (nv + 31) >> 5;
+            for (int i = lane; i < nwords; i += kWarp) bits[i] = 0u;
+            if (lane == 0) {
+              vis[cur] = (short)nv;
+              visb[cur >> 5] |= 1u << (cur & 31);
+              put(len, cfg.idx_offset + nv);
+              if (LABELED) put(len + 1, cfg.node_idx_offset + __ldg(c.x + n0 + cur));
+            }
+            len += per;
+            ++nvis;
+            __syncwarp();
+            int closed = 0;
+            for (int e0 = lo; e0 < hi; e0 += kWarp) {
+              const int e = e0 + lane;
+              bool z = false;
+              if (e < hi) {
+                const int u = COL(e);
+                const int vu = vis[u];
+                const int r = (int)rem[u] - 1;                    // cur stops being an unvisited neighbour of u
+                rem[u] = (unsigned short)r;
+                if (vu >= 0 && u != cur) {
+                  if (r == 0) { z = true; atomicAnd(&openb[u >> 5], ~(1u << (u & 31))); }
+                  if (u != prev) {
+                    atomicOr(&bits[vu >> 5], 1u << (vu & 31));
+                    if (LABELED) ent[vu] = e;
+                  }
+                }
+              }
+              closed += __popc(__ballot_sync(kFull, z));
+            }
+            nopen -= closed;
+            __syncwarp();
+            if (rem[cur] > 0) {                                   // cur joins the restart candidates
+              if (lane == 0) openb[cur >> 5] |= 1u << (cur & 31);
+              ++nopen;
+            }
+            int M = 0;
+            for (int w0 = 0; w0 < nwords; w0 += kWarp) {
+              unsigned word = (w0 + lane < nwords) ? bits[w0 + lane] : 0u;
+              const int cw = __popc(word);
+              int incl = cw;
+  #pragma unroll
+              for (int dd = 1; dd < 32; dd <<= 1) {
+                const int o = __shfl_up_sync(kFull, incl, dd);
+                if (lane >= dd) incl += o;
+              }
+              int j = M + incl - cw;
+              while (word) {
+                const int bpos = __ffs(word) - 1;
+                word &= word - 1;
+                const int vi = ((w0 + lane) << 5) + bpos;
+                const int pos = len + 1 + j * per;
+                if (LABELED) {
+                  put(pos, cfg.edge_idx_offset + EA(ent[vi]) + cfg.edge_label_shift);
+                  put(pos + 1, cfg.idx_offset + vi);
+                } else {
+                  put(pos, cfg.idx_offset + vi);
+                }
+                ++j;
+              }
+              M += __shfl_sync(kFull, incl, 31);
+            }
+            if (M > 0) {
+              if (lane == 0) { put(len, LADJ); put(len + 1 + M * per, RADJ); }
+              len += 2 + M * per;
+            }
+          } else {
+            if (lane == 0) put(len, cfg.idx_offset + vc);  // head of a new segment at a visited node
+            len += 1;
+          }
+          __syncwarp();
+          const int cnt = rem[cur];
+          if (cnt > 0) {
+            // ---- trail step to the k-th unvisited neighbour (CSR order)
+            const int k = pick(cnt);
+            int seen = 0, ne = -1;
+            for (int e0 = lo; e0 < hi && ne < 0; e0 += kWarp) {
+              const int e = e0 + lane;
+              const bool f = e < hi && vis[COL(e)] < 0;
+              const unsigned m = __ballot_sync(kFull, f);
+              const int cch = __popc(m);
+              if (k < seen + cch) {
+                const unsigned sel = __ballot_sync(kFull, f && (__popc(m & ((1u << lane) - 1)) == k - seen));
+                ne = e0 + __ffs(sel) - 1;
+              }
+              seen += cch;
+            }
+            if (LABELED) {
+              if (lane == 0) put(len, cfg.edge_idx_offset + EA(ne) + cfg.edge_label_shift);
+              len += 1;
+            }
+            prev = cur;
+            cur = COL(ne);
+            lo = RP(cur); hi = RP(cur + 1);
+          } else {
+            if (nvis == N) break;
+            // ---- restart: visited nodes with unvisited neighbours, else unvisited nodes
+            int nxt;
+            if (nopen > 0) nxt = locate(openb, false, pick(nopen));
+            else nxt = locate(visb, true, pick(N - nvis));
+            if (lane == 0) put(len, RESET);
+            len += 1;
+            cur = nxt;
+            prev = -1;
+            lo = RP(cur); hi = RP(cur + 1);
+          }
         }
       }
     }
