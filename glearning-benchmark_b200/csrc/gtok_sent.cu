@@ -56,6 +56,12 @@ __device__ __forceinline__ int remap_zinc(int t, int idx_off, int node_off, int 
   return 22 + t;
 }
 
+__device__ __forceinline__ int ld_keep_l2(const int32_t* p, unsigned long long policy) {
+  int v;
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+  return v;
+}
+
 struct SentSmemLayout {
   int rp, stage, ea, ent, bits, openb, visb, vis, rem, col, total;  // byte offsets inside one warp's slice
 };
@@ -104,6 +110,8 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
   const int Lcap = cfg.max_length;
   const int per = LABELED ? 2 : 1;
   const unsigned k0 = (unsigned)(ch.seed & 0xffffffffu), k1 = (unsigned)(ch.seed >> 32);
+  unsigned long long l2_keep = 0;
+  if (CSRG) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2_keep));
 
   for (int64_t g = warp0; g < c.num_graphs; g += nwarps) {
     const int64_t n0 = __ldg(c.node_off + g);
@@ -115,9 +123,11 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
     const int32_t* __restrict__ g_rp = c.rowptr + n0;
     const int32_t* __restrict__ g_col = c.col + z0;
     const int32_t* __restrict__ g_ea = LABELED ? c.eattr + z0 : nullptr;
-    auto RP = [&](int i) -> int { return CSRG ? __ldg(g_rp + i) - z0 : rp[i]; };
-    auto COL = [&](int e) -> int { return CSRG ? __ldg(g_col + e) : (int)col[e]; };
-    auto EA = [&](int e) -> int { return CSRG ? __ldg(g_ea + e) : ea[e]; };
+    // CSR in HBM: the row pointers of the resident graphs (4 bytes per node) are the one array the walk revisits
+    // at random - keep them in L2 (evict_last) and let neighbour lists / labels stream through (evict_first)
+    auto RP = [&](int i) -> int { return CSRG ? ld_keep_l2(g_rp + i, l2_keep) - z0 : rp[i]; };
+    auto COL = [&](int e) -> int { return CSRG ? __ldcs(g_col + e) : (int)col[e]; };
+    auto EA = [&](int e) -> int { return CSRG ? __ldcs(g_ea + e) : ea[e]; };
     if (!CSRG) for (int i = lane; i <= N; i += kWarp) rp[i] = __ldg(g_rp + i) - z0;
     for (int i = lane; i < N; i += kWarp) { vis[i] = -1; }
     for (int i = lane; i < ((N + 31) >> 5); i += kWarp) { openb[i] = 0u; visb[i] = 0u; }
@@ -158,7 +168,7 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
     auto put = [&](int pos, int t) {
       if (pos < Lcap) {
         if (STAGED) stage[pos] = t;
-        else row[pos] = cfg.remap_zinc ? remap_zinc(t, cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset) : t;
+        else __stcs(row + pos, (int64_t)(cfg.remap_zinc ? remap_zinc(t, cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset) : t));
       }
     };
     // k-th (0-based) set bit of an N-bit bitmap (or of its complement), ascending node id; the caller knows
@@ -247,7 +257,13 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
             if (mm) {
               const int M = __popc(mm);
               int rank = 0;
-              for (unsigned t = mm; t; t &= t - 1) rank += (__shfl_sync(kFull, vu, __ffs(t) - 1) < vu) ? 1 : 0;
+              for (unsigned t = mm; t;) {                         // four independent shuffles per trip
+                int sl4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { sl4[j] = t ? __ffs(t) - 1 : lane; t &= t - 1; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rank += (__shfl_sync(kFull, vu, sl4[j]) < vu) ? 1 : 0;
+              }
               if (member) {
                 const int pos = len + 1 + rank * per;
                 if (LABELED) {
@@ -471,11 +487,24 @@ int sent_small_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const Gto
                         int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
 int sent_mid_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
                       int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
+int sent_big_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
+                      int64_t* out, int64_t stride, void* ws, size_t ws_bytes, int64_t total_nodes, cudaStream_t st,
+                      bool* handled);
 
 }  // namespace gtok
 
+extern "C" size_t gtok_sent_workspace_bytes(int64_t total_nodes, int32_t max_nodes) {
+  return (max_nodes > 256 && total_nodes > 0) ? (size_t)total_nodes * 4 : 0;
+}
+
 extern "C" int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cfg, const GtokChoice* choice,
                                   int32_t* len_out, int64_t* tok_out, int64_t stride, void* stream) {
+  return gtok_sent_tokenize_ws(csr, cfg, choice, len_out, tok_out, stride, 0, nullptr, 0, stream);
+}
+
+extern "C" int gtok_sent_tokenize_ws(const GtokCsrBatch* csr, const GtokSentCfg* cfg, const GtokChoice* choice,
+                                     int32_t* len_out, int64_t* tok_out, int64_t stride, int64_t total_nodes, void* ws,
+                                     size_t ws_bytes, void* stream) {
   using namespace gtok;
   GTOK_REQUIRE(csr && cfg && choice, GTOK_EINVAL, "sent: null csr/cfg/choice");
   GTOK_REQUIRE(csr->num_graphs >= 0, GTOK_EINVAL, "sent: negative graph count");
@@ -500,6 +529,9 @@ extern "C" int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cf
     if (rc != GTOK_OK || handled) return rc;
     // 65..256 nodes: the same scheme on 2 or 4 mask words (gtok_sent_mid.cu)
     rc = sent_mid_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);
+    if (rc != GTOK_OK || handled) return rc;
+    // larger graphs with a caller-provided workspace: walk state in HBM scratch, 3-5x the occupancy (gtok_sent_big.cu)
+    rc = sent_big_dispatch(csr, cfg, choice, len_out, tok_out, stride, ws, ws_bytes, total_nodes, st, &handled);
     if (rc != GTOK_OK || handled) return rc;
   }
   const bool staged = cfg->max_length <= 2048;

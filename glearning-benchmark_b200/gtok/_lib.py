@@ -94,6 +94,9 @@ PROTOTYPES = {
     "gtok_zinc_collate_packed": (C.c_int, [C.POINTER(PackedMolBatchC), C.POINTER(ZincVocabC), i64, i64, vp, vp, vp, vp, vp, i64,
                                            vp, C.c_size_t, vp]),
     "gtok_sent_tokenize": (C.c_int, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), C.POINTER(ChoiceC), vp, vp, i64, vp]),
+    "gtok_sent_workspace_bytes": (C.c_size_t, [i64, i32]),
+    "gtok_sent_tokenize_ws": (C.c_int, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), C.POINTER(ChoiceC), vp, vp, i64, i64, vp,
+                                        C.c_size_t, vp]),
     "gtok_pad_mask": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp]),
     "gtok_batch_extents": (C.c_int, [vp, vp, i64, i64, vp, vp, vp]),
     "gtok_pad_mask_batched": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, vp]),

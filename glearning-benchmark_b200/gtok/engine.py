@@ -444,6 +444,7 @@ class CsrBatch:
     adj64: Optional[torch.Tensor] = None   # int64[N_total * adj_words] adjacency bit rows (graphs of <= 256 nodes)
     adj_words: int = 1                     # 64-bit words per adjacency row (1: <= 64 nodes, 2: <= 128, 4: <= 256)
     order: Optional[torch.Tensor] = None   # int32[G] processing order (graphs sorted by work)
+    scratch: Optional[torch.Tensor] = None # walk-state workspace of the large-graph SENT kernel (lazily allocated)
 
     @property
     def num_graphs(self) -> int:
@@ -548,8 +549,10 @@ class SentConfig:
 
 def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: int = 0,
                   choice_words: Optional[torch.Tensor] = None, choice_off: Optional[torch.Tensor] = None,
-                  out: Optional[torch.Tensor] = None, stride: Optional[int] = None):
-    """-> (tokens int64[G, stride], lengths int32[G]); row g valid up to lengths[g]."""
+                  out: Optional[torch.Tensor] = None, stride: Optional[int] = None, use_workspace: bool = True):
+    """-> (tokens int64[G, stride], lengths int32[G]); row g valid up to lengths[g].
+    use_workspace: graphs above 256 nodes walk with their per-node state in an HBM scratch array (4 bytes per node,
+    allocated once per CsrBatch); False keeps the state in shared memory (gtok_sent_tokenize, fewer graphs in flight)."""
     _require_cuda(csr.node_off, csr.rowptr, csr.col)
     dev = csr.node_off.device
     G = csr.num_graphs
@@ -563,7 +566,15 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
     sc = _lib.SentCfgC(cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset, cfg.max_length, int(cfg.labeled),
                        cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query))
     ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))
-    check(lib.gtok_sent_tokenize(C.byref(cc), C.byref(sc), C.byref(ch), _ptr(lengths), _ptr(out), int(stride), _stream()))
+    n_total = int(csr.rowptr.numel()) - 1
+    nbytes = lib.gtok_sent_workspace_bytes(n_total, max(1, csr.max_nodes)) if use_workspace else 0
+    if nbytes:
+        if csr.scratch is None or csr.scratch.numel() < nbytes:
+            csr.scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)      # kept with the CSR: every epoch reuses it
+        check(lib.gtok_sent_tokenize_ws(C.byref(cc), C.byref(sc), C.byref(ch), _ptr(lengths), _ptr(out), int(stride), n_total,
+                                        _ptr(csr.scratch), nbytes, _stream()))
+    else:
+        check(lib.gtok_sent_tokenize(C.byref(cc), C.byref(sc), C.byref(ch), _ptr(lengths), _ptr(out), int(stride), _stream()))
     return out, lengths
 
 

@@ -932,3 +932,61 @@ def test_generate_er_matches_oracle_and_shards(dev):
             assert n2[g] == wn and list(zip(s2[eo2[g]:eo2[g + 1]], d2[eo2[g]:eo2[g + 1]])) == we, (buckets, g)
             assert (int(b2.query_u[g]), int(b2.query_v[g])) == wq
     assert engine.generate_er(0, device=dev).num_graphs == 0
+
+
+@pytest.mark.parametrize("labeled", [False, True])
+def test_sent_workspace_kernel_equals_shared_memory_kernel(dev, labeled):
+    """> 256 nodes: the walk with its per-node state in the HBM workspace (gtok_sent_tokenize_ws) and the one with the
+    state in shared memory (gtok_sent_tokenize) are the same function of (graph, choice words), rows longer than a
+    warp included; both equal the oracle on a sample.  Also: truncation, query append, explicit choice stream."""
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    rng = np.random.default_rng(17 + labeled)
+    mols = []
+    for i in range(36):
+        n = int(rng.integers(257, 1400))
+        if i % 6 == 0:
+            m = int(min(n * 40, 60000))                   # hubs: rows of 80+ entries (chunked path)
+        elif i % 6 == 1:
+            m = n // 3                                    # many components, isolated nodes, restarts at unvisited nodes
+        else:
+            m = 4 * n
+        s_, d_ = rng.integers(0, n, m), rng.integers(0, n, m)
+        if i % 6 == 2:
+            d_[: m // 4] = 0                              # one node of very high degree
+        mols.append({"n": n, "src": s_.tolist(), "dst": d_.tolist(), "x": rng.integers(0, 12, n).tolist(),
+                     "attr": rng.integers(1, 6, m).tolist()})
+    gb = GraphBatch.from_lists([m["n"] for m in mols], [list(zip(m["src"], m["dst"])) for m in mols],
+                               x_lists=[m["x"] for m in mols], attr_lists=[m["attr"] for m in mols],
+                               queries=[(int(rng.integers(0, m["n"])), int(rng.integers(0, m["n"]))) for m in mols]).to(dev)
+    csr = engine.build_csr(gb)
+    assert csr.adj64 is None
+    nmax = max(m["n"] for m in mols)
+    words = [rng.integers(0, 2 ** 32, 3 * m["n"], dtype=np.uint64).astype(np.uint32) for m in mols]
+    woff = np.zeros(len(mols) + 1, dtype=np.int64)
+    woff[1:] = np.cumsum([len(w) for w in words])
+    cw = torch.from_numpy(np.concatenate(words).view(np.int32)).to(dev)
+    coff = torch.from_numpy(woff).to(dev)
+    for max_length, append, stream in ((60000, False, False), (2000, True, False), (777, False, True), (60000, True, True)):
+        cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 12, max_length=max_length,
+                                labeled=labeled, remap_zinc=labeled and max_length == 2000, append_query=append)
+        kw = dict(choice_words=cw, choice_off=coff) if stream else dict(seed=9, graph_id_base=5)
+        ta, la = engine.tokenize_sent(csr, cfg, use_workspace=True, **kw)
+        tb, lb = engine.tokenize_sent(csr, cfg, use_workspace=False, **kw)
+        assert csr.scratch is not None
+        assert torch.equal(la, lb)
+        la_h = la.cpu().tolist()
+        ta, tb = ta.cpu(), tb.cpu()
+        for g in range(len(mols)):
+            assert torch.equal(ta[g, :la_h[g]], tb[g, :la_h[g]]), (max_length, g)
+        ocfg = S.SentConfig(6, 6 + nmax, 6 + nmax + 12, max_length, labeled)
+        for g in (0, 1, 2, 7, 35):
+            m = mols[g]
+            rp, col, ea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"])
+            wsrc = S.StreamWords(words[g]) if stream else S.PhiloxWords(9, 5 + g)
+            want = S.sent_tokenize(m["n"], rp, col, ocfg, wsrc, x=m["x"] if labeled else None, eattr=ea if labeled else None)
+            if cfg.remap_zinc:
+                want = O.remap_zinc(want, 6, 6 + nmax, 6 + nmax + 12)
+            if append:
+                want = O.append_query(want, 6, m["n"], int(gb.query_u[g]), int(gb.query_v[g]))
+            assert ta[g, :la_h[g]].tolist() == np.asarray(want).tolist(), (max_length, g)
