@@ -256,13 +256,13 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
             const unsigned mm = __ballot_sync(kFull, member);
             if (mm) {
               const int M = __popc(mm);
+              // rank among the members by ascending visit index: one warp min-reduction per member (visit indices
+              // are distinct), the lane that holds the minimum takes the next rank and drops out
               int rank = 0;
-              for (unsigned t = mm; t;) {                         // four independent shuffles per trip
-                int sl4[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { sl4[j] = t ? __ffs(t) - 1 : lane; t &= t - 1; }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rank += (__shfl_sync(kFull, vu, sl4[j]) < vu) ? 1 : 0;
+              unsigned key = member ? (unsigned)vu : 0xffffffffu;
+              for (int j = 0; j < M; ++j) {
+                const unsigned mn = __reduce_min_sync(kFull, key);
+                if (key == mn) { rank = j; key = 0xffffffffu; }
               }
               if (member) {
                 const int pos = len + 1 + rank * per;
@@ -291,7 +291,8 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
               asm volatile("prefetch.global.L1 [%0];" ::"l"(g_col + rlo));
               if (LABELED) asm volatile("prefetch.global.L1 [%0];" ::"l"(g_ea + rlo));
             }
-            const int sl = select32(fm, pick(cnt));
+            const int kth = pick(cnt);                                  // lane holding the kth candidate
+            const int sl = __ffs(__ballot_sync(kFull, ((fm >> lane) & 1u) && __popc(fm & ((1u << lane) - 1u)) == kth)) - 1;
             if (LABELED) {
               const int eas = __shfl_sync(kFull, eav, sl);
               if (lane == 0) put(len, cfg.edge_idx_offset + eas + cfg.edge_label_shift);
@@ -494,7 +495,7 @@ int sent_big_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokC
 }  // namespace gtok
 
 extern "C" size_t gtok_sent_workspace_bytes(int64_t total_nodes, int32_t max_nodes) {
-  return (max_nodes > 256 && total_nodes > 0) ? (size_t)total_nodes * 4 : 0;
+  return (max_nodes > 256 && total_nodes > 0) ? (size_t)total_nodes * 8 : 0;
 }
 
 extern "C" int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cfg, const GtokChoice* choice,

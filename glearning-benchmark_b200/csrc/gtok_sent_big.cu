@@ -10,6 +10,11 @@
 // both fields, so "is u visited, what is its index, did it just lose its last unvisited neighbour" cost a single
 // L2 round trip per neighbour, issued for the whole row at once (lane <-> neighbour).  Shared memory holds only the
 // three bitmaps (3 * N / 8 bytes per warp), so up to 64 warps per SM hide each other's latency.
+// Up to 4096 nodes per graph the word is 64 bits wide and also carries the node's CSR row:
+//     state[u] = row start << 37 | degree << 25 | (visit index + 1) << 12 | unvisited neighbours left,
+// so the one atomic per neighbour returns the extents of the next row as well (ncu on the 32-bit variant: all
+// graphs of a batch walk concurrently, the working set is the whole batch, L2 hit rate 26 %, and the separate
+// rowptr reads were 38 % of all stall samples and a third of the 1.2 KB of DRAM sectors touched per step).
 // Row extents of all neighbours are requested with the row and the rows of the candidates are prefetched, as in
 // the fast path of gtok_sent.cu.  Rows longer than a warp take a chunked path (bracket ranks through a visit-index
 // bitmap + word prefix).  Walk semantics, random words, remap and query append: identical to gtok_sent.cu / the
@@ -35,11 +40,38 @@ BigLayout big_layout(int nmax) {
   return L;
 }
 
-__device__ __forceinline__ unsigned ld_cg_u32(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_cg(const unsigned* p) {
   unsigned v;
   asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long ld_cg(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// field access of the per-node state word (32-bit: vis+1 | rem; 64-bit: row start | degree | vis+1 | rem)
+template <bool P64> struct St;
+template <> struct St<false> {
+  using T = unsigned;
+  static __device__ __forceinline__ int vis(T w) { return (int)(w >> 16) - 1; }
+  static __device__ __forceinline__ bool last(T w) { return (w & 0xffffu) == 1u; }       // rem == 1 before the decrement
+  static __device__ __forceinline__ bool unvisited(T w) { return (w >> 16) == 0u; }
+  // (the graph belongs to this warp alone and the neighbours of a row are distinct: plain load + store, no atomic)
+  static __device__ __forceinline__ T dec(T* p) { const T w = ld_cg(p); __stcg(p, w - 1u); return w; }
+  static __device__ __forceinline__ void set_vis(T* p, int nv) { __stcg(p, ld_cg(p) + ((unsigned)(nv + 1) << 16)); }
+};
+template <> struct St<true> {
+  using T = unsigned long long;
+  static __device__ __forceinline__ int vis(T w) { return (int)((w >> 12) & 0x1fffu) - 1; }
+  static __device__ __forceinline__ bool last(T w) { return (w & 0xfffu) == 1u; }
+  static __device__ __forceinline__ bool unvisited(T w) { return ((w >> 12) & 0x1fffu) == 0u; }
+  static __device__ __forceinline__ T dec(T* p) { const T w = ld_cg(p); __stcg(p, w - 1ull); return w; }   // rem >= 1: no borrow
+  static __device__ __forceinline__ void set_vis(T* p, int nv) { __stcg(p, ld_cg(p) + ((unsigned long long)(nv + 1) << 12)); }
+  static __device__ __forceinline__ int lo(T w) { return (int)(w >> 37); }
+  static __device__ __forceinline__ int hi(T w) { return (int)(w >> 37) + (int)((w >> 25) & 0xfffu); }
+};
 
 // k-th (0-based) set bit of an N-bit bitmap (or of its complement); the caller knows there are more than k
 __device__ __forceinline__ int locate_bit(const unsigned* bm, bool invert, int k, int N, int lane) {
@@ -72,10 +104,13 @@ __device__ __forceinline__ int locate_bit(const unsigned* bm, bool invert, int k
   return found;
 }
 
-template <bool LABELED>
+template <bool LABELED, bool P64>
 __global__ void __launch_bounds__(kBigWarps * 32)
 sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch, const BigLayout lay,
-                unsigned* __restrict__ state, int32_t* __restrict__ len_out, int64_t* __restrict__ out, int64_t stride) {
+                typename St<P64>::T* __restrict__ state, int32_t* __restrict__ len_out, int64_t* __restrict__ out,
+                int64_t stride) {
+  using S = St<P64>;
+  using W = typename S::T;
   extern __shared__ __align__(16) unsigned char b_smem[];
   const int lane = lane_id();
   unsigned char* base = b_smem + (size_t)(threadIdx.x >> 5) * lay.total;
@@ -99,12 +134,27 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
     const int32_t* __restrict__ g_rp = c.rowptr + n0;
     const int32_t* __restrict__ g_col = c.col + z0;
     const int32_t* __restrict__ g_ea = LABELED ? c.eattr + z0 : nullptr;
-    unsigned* __restrict__ st = state + n0;
+    W* __restrict__ st = state + n0;
     auto RP = [&](int i) -> int { return __ldg(g_rp + i) - z0; };
     auto COL = [&](int e) -> int { return __ldcs(g_col + e); };
     auto EA = [&](int e) -> int { return __ldcs(g_ea + e); };
 
-    for (int i = lane; i < N; i += kWarp) __stcg(st + i, (unsigned)(__ldg(g_rp + i + 1) - __ldg(g_rp + i)));
+    for (int i = lane; i < N; i += kWarp) {
+      const unsigned r0 = (unsigned)(__ldg(g_rp + i) - z0), deg = (unsigned)(__ldg(g_rp + i + 1) - z0) - r0;
+      if constexpr (P64) __stcg(st + i, (unsigned long long)r0 << 37 | (unsigned long long)deg << 25 | deg);
+      else __stcg(st + i, deg);
+    }
+    // row extents of a node: from its state word (64-bit layout) or from rowptr
+    auto extents = [&](int node, int& lo_, int& hi_, int* vis_) {
+      if constexpr (P64) {
+        const W w = ld_cg(st + node);
+        lo_ = S::lo(w); hi_ = S::hi(w);
+        if (vis_) *vis_ = S::vis(w);
+      } else {
+        lo_ = RP(node); hi_ = RP(node + 1);
+        if (vis_) *vis_ = S::vis(ld_cg(st + node));
+      }
+    };
     for (int i = lane; i < ((N + 31) >> 5); i += kWarp) { openb[i] = 0u; visb[i] = 0u; }
     __syncwarp();
 
@@ -139,7 +189,8 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
       int nvis = 0, prev = -1, nopen = 0;
       int cur = pick(N);
       int vc = -1;                                   // visit index of cur, -1 = first visit
-      int lo = RP(cur), hi = RP(cur + 1);
+      int lo, hi;
+      extents(cur, lo, hi, nullptr);
       while (len < Lcap) {
         int cnt = 0;
         if (hi - lo <= kWarp) {
@@ -148,36 +199,37 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
           const bool valid = e < hi;
           const int u = valid ? COL(e) : 0;
           int rlo = 0, rhi = 0, eav = 0;
-          unsigned old = 0;
+          W old = 0;
           if (valid) {
-            old = vc < 0 ? atomicSub(st + u, 1u) : ld_cg_u32(st + u);   // cur stops being an unvisited neighbour of u
-            rlo = RP(u); rhi = RP(u + 1);
+            old = vc < 0 ? S::dec(st + u) : ld_cg(st + u);              // cur stops being an unvisited neighbour of u
+            if constexpr (!P64) { rlo = RP(u); rhi = RP(u + 1); }
             if (LABELED) eav = EA(e);
           }
-          const int vu = (int)(old >> 16) - 1;
+          if constexpr (P64) { rlo = S::lo(old); rhi = S::hi(old); }
+          const int vu = S::vis(old);
           if (vc < 0) {
             const int nv = nvis++;
             if (lane == 0) {
-              atomicAdd(st + cur, (unsigned)(nv + 1) << 16);
+              S::set_vis(st + cur, nv);
               visb[cur >> 5] |= 1u << (cur & 31);
               put(len, cfg.idx_offset + nv);
               if (LABELED) put(len + 1, cfg.node_idx_offset + __ldg(c.x + n0 + cur));
             }
             len += per;
-            const bool z = valid && vu >= 0 && (old & 0xffffu) == 1u;   // u just lost its last unvisited neighbour
+            const bool z = valid && vu >= 0 && S::last(old);            // u just lost its last unvisited neighbour
             if (z) atomicAnd(&openb[u >> 5], ~(1u << (u & 31)));
             nopen -= __popc(__ballot_sync(kFull, z));
             const bool member = valid && vu >= 0 && u != prev;
             const unsigned mm = __ballot_sync(kFull, member);
             if (mm) {
               const int M = __popc(mm);
+              // rank among the members by ascending visit index: one warp min-reduction per member (visit indices
+              // are distinct), the lane that holds the minimum takes the next rank and drops out
               int rank = 0;
-              for (unsigned t = mm; t;) {                               // four independent shuffles per trip
-                int sl4[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { sl4[j] = t ? __ffs(t) - 1 : lane; t &= t - 1; }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rank += (__shfl_sync(kFull, vu, sl4[j]) < vu) ? 1 : 0;
+              unsigned key = member ? (unsigned)vu : 0xffffffffu;
+              for (int j = 0; j < M; ++j) {
+                const unsigned mn = __reduce_min_sync(kFull, key);
+                if (key == mn) { rank = j; key = 0xffffffffu; }
               }
               if (member) {
                 const int pos = len + 1 + rank * per;
@@ -206,7 +258,8 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
               asm volatile("prefetch.global.L2 [%0];" ::"l"(g_col + rlo));
               if (LABELED) asm volatile("prefetch.global.L2 [%0];" ::"l"(g_ea + rlo));
             }
-            const int sl = select32(fm, pick(cnt));
+            const int kth = pick(cnt);                                  // lane holding the kth candidate
+            const int sl = __ffs(__ballot_sync(kFull, ((fm >> lane) & 1u) && __popc(fm & ((1u << lane) - 1u)) == kth)) - 1;
             if (LABELED) {
               const int eas = __shfl_sync(kFull, eav, sl);
               if (lane == 0) put(len, cfg.edge_idx_offset + eas + cfg.edge_label_shift);
@@ -227,7 +280,7 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
             const int nwb = (nv + 31) >> 5;
             for (int i = lane; i < nwb; i += kWarp) bits[i] = 0u;
             if (lane == 0) {
-              atomicAdd(st + cur, (unsigned)(nv + 1) << 16);
+              S::set_vis(st + cur, nv);
               visb[cur >> 5] |= 1u << (cur & 31);
               put(len, cfg.idx_offset + nv);
               if (LABELED) put(len + 1, cfg.node_idx_offset + __ldg(c.x + n0 + cur));
@@ -240,11 +293,11 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
               bool z = false, unv = false;
               if (e < hi) {
                 const int u = COL(e);
-                const unsigned old = atomicSub(st + u, 1u);
-                const int vu = (int)(old >> 16) - 1;
+                const W old = S::dec(st + u);
+                const int vu = S::vis(old);
                 unv = vu < 0;
                 if (vu >= 0) {
-                  z = (old & 0xffffu) == 1u;
+                  z = S::last(old);
                   if (z) atomicAnd(&openb[u >> 5], ~(1u << (u & 31)));
                   if (u != prev) atomicOr(&bits[vu >> 5], 1u << (vu & 31));
                 }
@@ -273,7 +326,7 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
                 const int e = e0 + lane;
                 if (e < hi) {
                   const int u = COL(e);
-                  const int vu = (int)(ld_cg_u32(st + u) >> 16) - 1;
+                  const int vu = S::vis(ld_cg(st + u));
                   if (vu >= 0 && u != prev) {
                     const int rank = (int)pref[vu >> 5] + __popc(bits[vu >> 5] & ((1u << (vu & 31)) - 1u));
                     const int pos = len + 1 + rank * per;
@@ -298,7 +351,7 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
             len += 1;
             for (int e0 = lo; e0 < hi; e0 += kWarp) {
               const int e = e0 + lane;
-              const bool unv = e < hi && (ld_cg_u32(st + COL(e)) >> 16) == 0u;
+              const bool unv = e < hi && S::unvisited(ld_cg(st + COL(e)));
               cnt += __popc(__ballot_sync(kFull, unv));
             }
           }
@@ -309,7 +362,7 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
             for (int e0 = lo; e0 < hi && nxt < 0; e0 += kWarp) {
               const int e = e0 + lane;
               const int u = e < hi ? COL(e) : 0;
-              const bool f = e < hi && (ld_cg_u32(st + u) >> 16) == 0u;
+              const bool f = e < hi && S::unvisited(ld_cg(st + u));
               const unsigned m = __ballot_sync(kFull, f);
               const int cch = __popc(m);
               if (k < seen + cch) {
@@ -325,7 +378,7 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
             }
             prev = cur;
             cur = nxt;
-            lo = RP(cur); hi = RP(cur + 1);
+            extents(cur, lo, hi, nullptr);
             vc = -1;
             __syncwarp();
             continue;
@@ -334,19 +387,13 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
         __syncwarp();
         if (nvis == N) break;
         // ---- restart: visited nodes with unvisited neighbours, else unvisited nodes
-        int nxt;
-        if (nopen > 0) {
-          nxt = locate_bit(openb, false, pick(nopen), N, lane);
-          vc = (int)(ld_cg_u32(st + nxt) >> 16) - 1;
-        } else {
-          nxt = locate_bit(visb, true, pick(N - nvis), N, lane);
-          vc = -1;
-        }
+        const bool reopen = nopen > 0;
+        cur = reopen ? locate_bit(openb, false, pick(nopen), N, lane) : locate_bit(visb, true, pick(N - nvis), N, lane);
+        extents(cur, lo, hi, &vc);
+        if (!reopen) vc = -1;
         if (lane == 0) put(len, RESET);
         len += 1;
-        cur = nxt;
         prev = -1;
-        lo = RP(cur); hi = RP(cur + 1);
       }
     }
     if (lane == 0) put(len, EOS);
@@ -363,11 +410,12 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
   }
 }
 
-template <bool LABELED>
+template <bool LABELED, bool P64>
 int big_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out, int64_t* out,
-               int64_t stride, unsigned* state, cudaStream_t st, bool* handled) {
+               int64_t stride, void* ws, cudaStream_t st, bool* handled) {
   const BigLayout lay = big_layout(c->max_nodes);
-  auto k = sent_big_kernel<LABELED>;
+  auto k = sent_big_kernel<LABELED, P64>;
+  auto* state = static_cast<typename St<P64>::T*>(ws);
   int dev = 0, max_optin = 0;
   GTOK_CUDA_TRY(cudaGetDevice(&dev));
   GTOK_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -389,11 +437,16 @@ int sent_big_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokC
                       bool* handled) {
   *handled = false;
   if (ws == nullptr || c->max_nodes <= 256) return GTOK_OK;
-  GTOK_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 3) == 0, GTOK_EINVAL, "sent: workspace must be 4-byte aligned");
-  GTOK_REQUIRE(total_nodes >= 0 && ws_bytes >= (size_t)total_nodes * 4, GTOK_EWORKSPACE,
-               "sent: workspace %zu < %lld bytes (4 per node)", ws_bytes, (long long)total_nodes * 4);
-  return cfg->labeled ? big_launch<true>(c, cfg, ch, len_out, out, stride, static_cast<unsigned*>(ws), st, handled)
-                      : big_launch<false>(c, cfg, ch, len_out, out, stride, static_cast<unsigned*>(ws), st, handled);
+  GTOK_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, GTOK_EINVAL, "sent: workspace must be 8-byte aligned");
+  GTOK_REQUIRE(total_nodes >= 0 && ws_bytes >= (size_t)total_nodes * 8, GTOK_EWORKSPACE,
+               "sent: workspace %zu < %lld bytes (8 per node)", ws_bytes, (long long)total_nodes * 8);
+  // 64-bit state words need: visit index + 1 <= 4096 (13 bits), degree <= 4095 (12 bits), row start < 2^27
+  const bool p64 = c->max_nodes <= 4096 && c->max_nnz < (1 << 27);
+  if (p64)
+    return cfg->labeled ? big_launch<true, true>(c, cfg, ch, len_out, out, stride, ws, st, handled)
+                        : big_launch<false, true>(c, cfg, ch, len_out, out, stride, ws, st, handled);
+  return cfg->labeled ? big_launch<true, false>(c, cfg, ch, len_out, out, stride, ws, st, handled)
+                      : big_launch<false, false>(c, cfg, ch, len_out, out, stride, ws, st, handled);
 }
 
 }  // namespace gtok

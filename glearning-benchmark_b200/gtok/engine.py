@@ -549,10 +549,12 @@ class SentConfig:
 
 def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: int = 0,
                   choice_words: Optional[torch.Tensor] = None, choice_off: Optional[torch.Tensor] = None,
-                  out: Optional[torch.Tensor] = None, stride: Optional[int] = None, use_workspace: bool = True):
+                  out: Optional[torch.Tensor] = None, stride: Optional[int] = None, use_workspace: Optional[bool] = None):
     """-> (tokens int64[G, stride], lengths int32[G]); row g valid up to lengths[g].
-    use_workspace: graphs above 256 nodes walk with their per-node state in an HBM scratch array (4 bytes per node,
-    allocated once per CsrBatch); False keeps the state in shared memory (gtok_sent_tokenize, fewer graphs in flight)."""
+    use_workspace: graphs above 256 nodes can walk with their per-node state in an HBM scratch array (8 bytes per node,
+    allocated once per CsrBatch; gtok_sent_tokenize_ws) instead of shared memory (gtok_sent_tokenize).  None = by
+    measurement: the shared-memory kernel wins while its per-graph slice leaves >= ~16 graphs per SM (12 KB; 14.6 vs
+    15.8 ms per 32M nodes at 2048 nodes), the workspace kernel beyond (18.2 vs 28.7 ms at 4096 nodes)."""
     _require_cuda(csr.node_off, csr.rowptr, csr.col)
     dev = csr.node_off.device
     G = csr.num_graphs
@@ -567,6 +569,8 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
                        cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query))
     ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))
     n_total = int(csr.rowptr.numel()) - 1
+    if use_workspace is None:
+        use_workspace = csr.max_nodes * (4 * (2 if cfg.labeled else 1) + 0.375) > 12288
     nbytes = lib.gtok_sent_workspace_bytes(n_total, max(1, csr.max_nodes)) if use_workspace else 0
     if nbytes:
         if csr.scratch is None or csr.scratch.numel() < nbytes:
