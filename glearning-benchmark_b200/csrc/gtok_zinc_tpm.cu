@@ -69,11 +69,12 @@ __device__ __forceinline__ void put2(int32_t* rb, int idx, unsigned t0, unsigned
   *reinterpret_cast<int2*>(rb + idx) = make_int2((int)t0, (int)t1);
 }
 
-template <typename StageT, bool HAS_ATTR, bool PADDED>
+template <typename StageT, bool HAS_ATTR, bool PADDED, bool UNIQ = false>
 __global__ void __launch_bounds__(kTpmMaxT)
 zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v, const TpmLayout lay, const TpmOut o,
                 unsigned int* __restrict__ ticket, unsigned long long* __restrict__ status, const int vec_ok,
                 const int pf_dist, const uint16_t* __restrict__ p_col16, const uint8_t* __restrict__ p_x8) {
+  constexpr bool unique_cols = UNIQ;                     // the columns are already the first-seen undirected edges
   extern __shared__ __align__(16) unsigned char t_smem[];
   __shared__ StageT s_nt[64];
   __shared__ StageT s_atom[10];
@@ -137,7 +138,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
       e_lo = __ldg(b.edge_off + g0 + lane); e_hi = __ldg(b.edge_off + g0 + lane + 1);
       n_lo = __ldg(b.node_off + g0 + lane); n_hi = __ldg(b.node_off + g0 + lane + 1);
     }
-    for (int k = 0; k < lay.bm_words; ++k) s_bm[k * 32 + lane] = 0u;
+    if (!unique_cols) for (int k = 0; k < lay.bm_words; ++k) s_bm[k * 32 + lane] = 0u;
     const int last = nv > 0 ? nv - 1 : 0;
     const long long E0 = __shfl_sync(kFull, e_lo, 0), N0 = __shfl_sync(kFull, n_lo, 0);
     int Et = (int)(__shfl_sync(kFull, e_hi, last) - E0), Nt = (int)(__shfl_sync(kFull, n_hi, last) - N0);
@@ -249,7 +250,9 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
     // ---- 2. walk: thread per molecule, first-seen dedupe, in-place compaction ------------------
     uint16_t* colp = s_col + eo;
     int cnt = 0;
-    {
+    if (unique_cols) {
+      cnt = Ed;                                          // the caller sent every undirected edge once, in first-seen order
+    } else {
       unsigned* bm = s_bm + lane;
 #pragma unroll 1
       for (int i = 0; i < Ed; ++i) {
@@ -419,7 +422,8 @@ bool tpm_layout(int T, int max_nodes, int max_entries, int smem_optin, TpmLayout
 
 template <typename StageT, bool PADDED>
 int tpm_launch(const GtokGraphBatch* batch, const GtokZincVocab* vocab, const TpmOut& o, int T_fixed, void* ws,
-               size_t ws_bytes, cudaStream_t st, bool* handled, const uint16_t* col16 = nullptr, const uint8_t* x8 = nullptr) {
+               size_t ws_bytes, cudaStream_t st, bool* handled, const uint16_t* col16 = nullptr, const uint8_t* x8 = nullptr,
+               int unique_cols = 0) {
   *handled = false;
   int dev = 0, optin = 0;
   GTOK_CUDA_TRY(cudaGetDevice(&dev));
@@ -439,6 +443,7 @@ int tpm_launch(const GtokGraphBatch* batch, const GtokZincVocab* vocab, const Tp
   const size_t need = 16 + (size_t)tiles * 8;
   GTOK_REQUIRE(ws_bytes >= need, GTOK_EWORKSPACE, "zinc tokenizer: workspace %zu < %zu bytes", ws_bytes, need);
   auto k = (batch->edge_attr || x8) ? zinc_tpm_kernel<StageT, true, PADDED> : zinc_tpm_kernel<StageT, false, PADDED>;
+  if (PADDED && x8 && unique_cols) k = zinc_tpm_kernel<StageT, true, PADDED, PADDED>;   // (UNIQ only exists for the padded packed path)
   GTOK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem));
   GTOK_CUDA_TRY(cudaMemsetAsync(ws, 0, need, st));
   const int grid = persistent_grid(k, lay.T, (size_t)lay.smem, tiles);
@@ -589,9 +594,9 @@ extern "C" int gtok_zinc_collate_packed(const GtokPackedMolBatch* pk, const Gtok
   bool handled = false;
   int rc;
   if (vocab->max_token_id > 0 && vocab->max_token_id < 65536)
-    rc = tpm_launch<uint16_t, true>(&b, vocab, o, (int)batch_size, ws, ws_bytes, st, &handled, pk->col16, pk->x8);
+    rc = tpm_launch<uint16_t, true>(&b, vocab, o, (int)batch_size, ws, ws_bytes, st, &handled, pk->col16, pk->x8, pk->unique_columns != 0);
   else
-    rc = tpm_launch<int32_t, true>(&b, vocab, o, (int)batch_size, ws, ws_bytes, st, &handled, pk->col16, pk->x8);
+    rc = tpm_launch<int32_t, true>(&b, vocab, o, (int)batch_size, ws, ws_bytes, st, &handled, pk->col16, pk->x8, pk->unique_columns != 0);
   if (rc != GTOK_OK) return rc;
   GTOK_REQUIRE(handled, GTOK_EUNSUPPORTED, "zinc_collate_packed: a tile of %lld molecules with these bounds does not fit shared memory",
                (long long)batch_size);

@@ -33,7 +33,7 @@ class GraphBatchC(C.Structure):
 
 class PackedMolBatchC(C.Structure):
     _fields_ = [("num_graphs", i64), ("node_off", vp), ("edge_off", vp), ("col16", vp), ("x8", vp),
-                ("max_nodes", i32), ("max_entries", i32)]
+                ("max_nodes", i32), ("max_entries", i32), ("unique_columns", i32), ("reserved_", i32)]
 
 
 class IbttRulesC(C.Structure):

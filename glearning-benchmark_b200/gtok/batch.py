@@ -213,6 +213,7 @@ class PackedGraphBatch:
     num_entries_total: int = 0
     col16: Optional[torch.Tensor] = None      # src | dst << 6 | edge_attr << 12 per column (int16 storage); replaces src/dst/edge_attr
     max_id: int = 0                           # largest local node id (the kernels size their pair bitmaps from it)
+    unique_columns: bool = False              # col16 holds each undirected edge ONCE, in first-seen order (see from_batch)
 
     ARRAYS = ("node_cnt", "entry_cnt", "src", "dst", "x", "edge_attr", "query_u", "query_v", "col16")
 
@@ -221,10 +222,37 @@ class PackedGraphBatch:
         return int(self.node_cnt.numel())
 
     @staticmethod
-    def from_batch(b: GraphBatch, fuse_columns: bool = False) -> "PackedGraphBatch":
+    def _canonical_half(b: GraphBatch) -> Optional[torch.Tensor]:
+        """Mask of the src < dst columns if `b` is a canonical PyG undirected edge_index - per graph: both directions
+        of every edge, no self loops, no repeats, columns sorted by (src, dst), edge_attr equal on both directions -
+        else None.  In such a list the undirected pair {u, v}, u < v, is FIRST seen at column (u, v) (it sorts before
+        (v, u)), so the src < dst columns in order are exactly tokenize_molecule's first-seen edges with the
+        orientation and bond type it would use (zinc_dataset_indexbase.py:170-184): the other half carries nothing."""
+        E = int(b.src.numel())
+        if E == 0 or E % 2 or b.src.is_cuda:
+            return None
+        s_, d_ = b.src.to(torch.int64), b.dst.to(torch.int64)
+        if bool((s_ == d_).any()):
+            return None
+        g = torch.repeat_interleave(torch.arange(b.num_graphs, dtype=torch.int64), b.num_entries())
+        key, rkey = (g * 64 + s_) * 64 + d_, (g * 64 + d_) * 64 + s_
+        if not bool((key[1:] > key[:-1]).all()):
+            return None
+        pos = torch.searchsorted(key, rkey).clamp_(max=E - 1)
+        if not bool((key[pos] == rkey).all()):
+            return None
+        if b.edge_attr is not None and not bool((b.edge_attr[pos] == b.edge_attr).all()):
+            return None
+        return s_ < d_
+
+    @staticmethod
+    def from_batch(b: GraphBatch, fuse_columns: bool = False, drop_mirror_columns: bool = False) -> "PackedGraphBatch":
         """fuse_columns: molecule-sized graphs (local ids < 64, edge_attr in 0..15, atom types < 256) travel as ONE
         16-bit word per edge_index column (GtokPackedMolBatch, include/gtok.h) - the layout the thread-per-molecule
-        ZINC kernel stages anyway; falls back to separate arrays when a value does not fit."""
+        ZINC kernel stages anyway; falls back to separate arrays when a value does not fit.
+        drop_mirror_columns (with fuse_columns): if the batch is a canonical undirected PyG edge_index (verified
+        here, see _canonical_half) only its src < dst columns travel, flagged unique_columns: half the column bytes
+        over PCIe and no dedupe on the device.  Any other batch keeps all its columns."""
         if fuse_columns and b.num_graphs and b.src.numel():
             mid = max(int(b.src.max()), int(b.dst.max()))
             lo = min(int(b.src.min()), int(b.dst.min()))
@@ -236,9 +264,13 @@ class PackedGraphBatch:
                 if ea is not None:
                     w = w | (ea.to(torch.int32) << 12)
                 col16 = (w & 0xFFFF).to(torch.int16)
-                return PackedGraphBatch(_narrowest(b.num_nodes()), _narrowest(b.num_entries()), None, None,
+                entries = b.num_entries()
+                keep = PackedGraphBatch._canonical_half(b) if drop_mirror_columns else None
+                if keep is not None:
+                    col16, entries = col16[keep].contiguous(), entries // 2
+                return PackedGraphBatch(_narrowest(b.num_nodes()), _narrowest(entries), None, None,
                                         b.x.to(torch.uint8), None, _narrowest(b.query_u), _narrowest(b.query_v),
-                                        int(b.node_off[-1]), int(b.edge_off[-1]), col16, mid)
+                                        int(b.node_off[-1]), int(col16.numel()), col16, mid, keep is not None)
         return PackedGraphBatch(_narrowest(b.num_nodes()), _narrowest(b.num_entries()), _narrowest(b.src),
                                 _narrowest(b.dst), _narrowest(b.x), _narrowest(b.edge_attr), _narrowest(b.query_u),
                                 _narrowest(b.query_v), int(b.node_off[-1]) if b.num_graphs else 0,
@@ -247,7 +279,7 @@ class PackedGraphBatch:
     def pin_memory(self) -> "PackedGraphBatch":
         kw = {n: (None if getattr(self, n) is None else getattr(self, n).pin_memory()) for n in self.ARRAYS}
         return PackedGraphBatch(num_nodes_total=self.num_nodes_total, num_entries_total=self.num_entries_total,
-                                max_id=self.max_id, **kw)
+                                max_id=self.max_id, unique_columns=self.unique_columns, **kw)
 
     def nbytes(self) -> int:
         return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in self.ARRAYS

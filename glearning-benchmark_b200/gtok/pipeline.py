@@ -126,13 +126,19 @@ class _PipelineBase:
         self._h2d_packed = host.nbytes()
         w = self._wire[slot]
         st = _stream()
-        for cnt, off in (("node_cnt", "node_off"), ("entry_cnt", "edge_off")):
-            check(lib.gtok_counts_to_offsets(_ptr(w[cnt]), w[cnt].element_size(), self.G, _ptr(self.dev_in[off]),
+        edge_off = self.dev_in["edge_off"]
+        if host.unique_columns:
+            # offsets of the de-mirrored column list live in their own buffer: dev_in keeps describing the int32 layout
+            if getattr(self, "_uniq_edge_off", None) is None:
+                self._uniq_edge_off = torch.empty(self.G + 1, dtype=torch.int64, device=self.device)
+            edge_off = self._uniq_edge_off
+        for cnt, off in (("node_cnt", self.dev_in["node_off"]), ("entry_cnt", edge_off)):
+            check(lib.gtok_counts_to_offsets(_ptr(w[cnt]), w[cnt].element_size(), self.G, _ptr(off),
                                              _ptr(self._cnt_tmp), _ptr(self.ws), self.ws_bytes, st))
         self._packed_dev = None
         if "col16" in w and getattr(self, "mode", None) == "collate" and w["x"].dtype == torch.uint8:
             # fused 16-bit columns: the collate kernel reads the wire buffers directly (gtok_zinc_collate_packed)
-            self._packed_dev = (w["col16"], w["x"], host.max_id)
+            self._packed_dev = (w["col16"], w["x"], host.max_id, bool(host.unique_columns), edge_off)
         else:
             if "col16" in w:
                 raise ValueError("fused 16-bit columns are only consumed by the ZINC pipeline in collate mode")
@@ -239,10 +245,10 @@ class ZincIbttPipeline(_PipelineBase):
         bc = self._batch_c()
         st = _stream()
         if self.mode == "collate" and getattr(self, "_packed_dev", None) is not None:
-            col16, x8, max_id = self._packed_dev
+            col16, x8, max_id, unique, edge_off = self._packed_dev
             d = self.dev_in
-            pk = _lib.PackedMolBatchC(self.G, _ptr(d["node_off"]), _ptr(d["edge_off"]), _ptr(col16), _ptr(x8),
-                                      max(1, self.max_nodes, max_id + 1), max(1, self.max_entries))
+            pk = _lib.PackedMolBatchC(self.G, _ptr(d["node_off"]), _ptr(edge_off), _ptr(col16), _ptr(x8),
+                                      max(1, self.max_nodes, max_id + 1), max(1, self.max_entries), int(unique), 0)
             self._timed("zinc_collate_packed", lambda: check(lib.gtok_zinc_collate_packed(
                 C.byref(pk), C.byref(self.zv), self.B, self.pad_id, _ptr(self.lengths), _ptr(self.lmax), _ptr(self.xoff),
                 _ptr(self.X), _ptr(self.attn), min(self.X.numel(), self.attn.numel()), _ptr(self.ws), self.ws_bytes, st)))

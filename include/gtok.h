@@ -262,6 +262,11 @@ typedef struct GtokPackedMolBatch {
   const uint8_t* x8;         /* [N] */
   int32_t max_nodes;         /* bound on atoms per molecule AND on every local id + 1 (<= 64) */
   int32_t max_entries;       /* bound on columns per molecule (<= 256) */
+  int32_t unique_columns;    /* 1: the columns already ARE the first-seen undirected edges, in order (what remains of
+                                a canonical PyG edge_index - both directions, sorted by (src, dst), symmetric
+                                edge_attr - when only its src < dst half is kept; gtok/batch.py verifies that before
+                                it drops the other half).  The kernel then skips the dedupe.  0: any column list */
+  int32_t reserved_;
 } GtokPackedMolBatch;
 GTOK_API int gtok_zinc_collate_packed(const GtokPackedMolBatch* batch, const GtokZincVocab* vocab, int64_t batch_size,
                                       int64_t pad_id, int32_t* len_out, int32_t* lmax_out, int64_t* xoff_out, int64_t* X,

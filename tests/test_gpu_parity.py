@@ -990,3 +990,45 @@ def test_sent_workspace_kernel_equals_shared_memory_kernel(dev, labeled):
             if append:
                 want = O.append_query(want, 6, m["n"], int(gb.query_u[g]), int(gb.query_v[g]))
             assert ta[g, :la_h[g]].tolist() == np.asarray(want).tolist(), (max_length, g)
+
+
+def test_zinc_collate_packed_unique_columns(dev, golden_zinc):
+    """De-mirrored wire format: a canonical undirected edge_index travels as its src < dst half, the kernel skips the
+    dedupe, and the batches equal the oracle's / the int32 path's bit for bit; a non-canonical shard through the same
+    pipeline keeps all its columns (and the dedupe)."""
+    from gtok import engine, synth
+    from gtok.batch import PackedGraphBatch
+    from gtok.pipeline import ZincIbttPipeline
+    vocab = O.zinc_extend_vocab(O.zinc_fixed_vocab(), [str(k) for k in range(37)] + ["X", "unknown"])
+    shards = [synth.zinc_shaped(3000, seed=s_) for s_ in (21, 22)]
+    rng = np.random.default_rng(5)
+    perm = torch.from_numpy(rng.permutation(int(shards[1].src.numel())))
+    # shard 3: shard 2 with its columns shuffled inside each graph (not canonical any more)
+    g_of = torch.repeat_interleave(torch.arange(3000), shards[1].num_entries())
+    order = torch.argsort(g_of[perm], stable=True)
+    idx = perm[order]
+    import dataclasses
+    shards.append(dataclasses.replace(shards[1], src=shards[1].src[idx], dst=shards[1].dst[idx], edge_attr=shards[1].edge_attr[idx]))
+    for max_len in (1024, 90):
+        pipe = ZincIbttPipeline(shards[0], vocab, max_len, 128, dev, mode="collate", max_nodes=37, max_entries=90,
+                                node_capacity=max(int(s_.node_off[-1]) for s_ in shards),
+                                entry_capacity=max(int(s_.edge_off[-1]) for s_ in shards))
+        pks = [PackedGraphBatch.from_batch(s_, fuse_columns=True, drop_mirror_columns=True).pin_memory() for s_ in shards]
+        assert [p.unique_columns for p in pks] == [True, True, False]
+        assert pks[1].nbytes() < 0.66 * pks[2].nbytes()
+        for i, (sh, pk_) in enumerate(zip(shards, pks)):
+            r = pipe.run(pk_, prefetch=pks[i + 1] if i + 1 < len(pks) else None)
+            want = [O.zinc_ids(*[t.tolist() for t in (sh.graph(g)[3], sh.graph(g)[1], sh.graph(g)[2], sh.graph(g)[4])], vocab, max_len, max_len)
+                    for g in range(3000)]
+            assert r.host_lengths.tolist() == [len(w_) for w_ in want]
+            ep = r.padded
+            for k in (0, 7, ep.num_batches - 1):
+                Xw, Aw, _ = O.collate(want[k * 128:(k + 1) * 128], [0] * len(want[k * 128:(k + 1) * 128]), vocab["<pad>"])
+                X, A = ep.batch(k)
+                assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw), (max_len, i, k)
+            ref = engine.zinc_collate_epoch(sh.to(dev), vocab, max_len, 128)[0]
+            tot = int(ref.xoff[-1])
+            assert int(r.host_xoff[-1]) == tot and torch.equal(r.padded.X[:tot], ref.X[:tot]) and torch.equal(r.padded.attn[:tot], ref.attn[:tot])
+        # the int32 layout of the pipeline was not disturbed by the de-mirrored offsets
+        r = pipe.run(shards[0].pin_memory())
+        assert int(r.host_xoff[-1]) == int(engine.zinc_collate_epoch(shards[0].to(dev), vocab, max_len, 128)[0].xoff[-1])
