@@ -1032,3 +1032,32 @@ def test_zinc_collate_packed_unique_columns(dev, golden_zinc):
         # the int32 layout of the pipeline was not disturbed by the de-mirrored offsets
         r = pipe.run(shards[0].pin_memory())
         assert int(r.host_xoff[-1]) == int(engine.zinc_collate_epoch(shards[0].to(dev), vocab, max_len, 128)[0].xoff[-1])
+
+
+def test_sent_workspace_kernel_above_4096_nodes(dev):
+    """> 4096 nodes per graph the workspace kernel falls back to 32-bit state words + rowptr reads: same rows as the
+    shared-memory kernel and the oracle."""
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    rng = np.random.default_rng(3)
+    recs = []
+    for n in (4097, 5000, 6100, 300):
+        m = 3 * n
+        s_, d_ = rng.integers(0, n, m), rng.integers(0, n, m)
+        recs.append((n, list(zip(s_.tolist(), d_.tolist()))))
+    gb = GraphBatch.from_lists([r[0] for r in recs], [r[1] for r in recs]).to(dev)
+    csr = engine.build_csr(gb)
+    cfg = engine.SentConfig(idx_offset=6, max_length=40000)
+    ta, la = engine.tokenize_sent(csr, cfg, seed=2, use_workspace=True)
+    tb, lb = engine.tokenize_sent(csr, cfg, seed=2, use_workspace=False)
+    assert torch.equal(la, lb)
+    for g, (n, edges) in enumerate(recs):
+        L = int(la[g])
+        assert torch.equal(ta[g, :L], tb[g, :L])
+        if g in (0, 3):
+            rp, col, _ = S.canonical_csr(n, [e[0] for e in edges], [e[1] for e in edges])
+            want = S.sent_tokenize(n, rp, col, S.SentConfig(idx_offset=6, max_length=40000), S.PhiloxWords(2, g))
+            assert ta[g, :L].cpu().tolist() == want.tolist()
+    # automatic choice: workspace kernel for these sizes, shared-memory kernel for 1000-node graphs
+    tc, lc = engine.tokenize_sent(csr, cfg, seed=2)
+    assert torch.equal(lc, la) and torch.equal(tc[0, :int(la[0])], ta[0, :int(la[0])])
