@@ -29,11 +29,21 @@ def zinc_round():
     G = int(rng.choice([1, 31, 127, 128, 129, 257, 1000, 3001]))
     dense = rng.random() < 0.3
     mols = []
+    canonical = rng.random() < 0.35            # a PyG-style undirected edge_index: both directions, sorted, symmetric types
     for i in range(G):
         n = int(rng.integers(1, nmax + 1))
         m = 0 if rng.random() < 0.05 else int(rng.integers(1, 257 if dense else 90))
         s = rng.integers(0, n, m)
         d = rng.integers(0, n, m) if rng.random() < 0.7 else (s + 1) % n
+        if canonical:
+            pairs = sorted({(int(min(a, b)), int(max(a, b))) for a, b in zip(s, d) if a != b})[:128]
+            at = {p_: int(rng.integers(0, 16)) for p_ in pairs}
+            cols = sorted(pairs + [(b, a) for a, b in pairs])
+            if cols and i % 50 == 49 and rng.random() < 0.5:
+                cols = cols[::-1]              # one graph breaks the order: the whole batch must keep all its columns
+            mols.append({"n": n, "src": [c[0] for c in cols], "dst": [c[1] for c in cols], "x": rng.integers(-2, 40, n).tolist(),
+                         "attr": [at[(min(c), max(c))] for c in cols]})
+            continue
         mols.append({"n": n, "src": s.tolist(), "dst": d.tolist(), "x": rng.integers(-2, 40, n).tolist(),
                      "attr": rng.integers(-1, 16, m).tolist()})
     names = [str(k) for k in rng.permutation(70)[: int(rng.integers(1, 70))]] + (["X"] if rng.random() < 0.7 else []) + \
@@ -63,12 +73,13 @@ def zinc_round():
         a = pipe.run(gc.pin_memory())
         tot = int(a.host_xoff[-1])
         Xa, Aa, la = a.padded.X[:tot].clone(), a.padded.attn[:tot].clone(), a.host_lengths.clone()
-        b = pipe.run(pf.pin_memory())
-        ok = ok and int(b.host_xoff[-1]) == tot and torch.equal(b.host_lengths, la) and torch.equal(b.padded.X[:tot], Xa) \
-            and torch.equal(b.padded.attn[:tot], Aa)
+        for pk_ in (pf, PackedGraphBatch.from_batch(gc, fuse_columns=True, drop_mirror_columns=True)):
+            b = pipe.run(pk_.pin_memory())
+            ok = ok and int(b.host_xoff[-1]) == tot and torch.equal(b.host_lengths, la) and torch.equal(b.padded.X[:tot], Xa) \
+                and torch.equal(b.padded.attn[:tot], Aa)
     if not ok:
         bad += 1
-    print(f"zinc   G={G:5d} nmax={nmax:2d} dense={int(dense)} max_len={max_len:4d} B={B:3d}: {'ok' if ok else 'MISMATCH'}")
+    print(f"zinc   G={G:5d} nmax={nmax:2d} dense={int(dense)} canonical={int(canonical)} max_len={max_len:4d} B={B:3d}: {'ok' if ok else 'MISMATCH'}")
 
 
 def gt_round():
@@ -109,7 +120,7 @@ def gt_round():
 
 def sent_round():
     global bad
-    nmax = int(rng.choice([5, 32, 64, 100, 128, 200, 256, 300]))
+    nmax = int(rng.choice([5, 32, 64, 100, 128, 200, 256, 300, 900]))
     G = int(rng.choice([1, 33, 120]))
     labeled = rng.random() < 0.5
     mols = []
@@ -128,7 +139,8 @@ def sent_round():
     seed = int(rng.integers(0, 2 ** 40))
     cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + mx, edge_idx_offset=6 + mx + 12, max_length=max_length, labeled=labeled,
                             remap_zinc=remap, append_query=append)
-    tok, ln = engine.tokenize_sent(csr, cfg, seed=seed, graph_id_base=5)
+    use_ws = [None, True, False][int(rng.integers(0, 3))]       # above 256 nodes: HBM-workspace or shared-memory walk state
+    tok, ln = engine.tokenize_sent(csr, cfg, seed=seed, graph_id_base=5, use_workspace=use_ws)
     tok, ln = tok.cpu(), ln.cpu().tolist()
     ocfg = S.SentConfig(6, 6 + mx, 6 + mx + 12, max_length, labeled)
     ok = True
