@@ -28,18 +28,8 @@ class ZINCDatasetForAutoGraph(Dataset):
     @property
     def graph_batch(self):
         if self._gb is None:
-            from gtok.batch import GraphBatch
-
-            class _V:
-                pass
-            items = []
-            for i in range(len(self.zinc_dataset)):
-                d = self.zinc_dataset[i]
-                v = _V()
-                v.x, v.edge_index, v.edge_attr, v.y = d.x, d.edge_index, d.edge_attr.reshape(-1), d.y
-                v.num_nodes = int(d.x.shape[0])
-                items.append(v)
-            self._gb = GraphBatch.from_data_list(items)
+            from gtok.batch import graph_batch_from_dataset
+            self._gb = graph_batch_from_dataset(self.zinc_dataset)      # InMemoryDataset storage converts without a Python loop
         return self._gb
 
     def __getitem__(self, idx):

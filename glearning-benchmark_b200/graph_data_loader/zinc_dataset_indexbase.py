@@ -48,18 +48,8 @@ class ZINCTokenizationDataset(Dataset):
     def graph_batch(self):
         """All molecules as one flat GraphBatch (host); built once, uploaded by TokenDataset."""
         if self._gb is None:
-            from gtok.batch import GraphBatch
-
-            class _V:      # view with num_nodes for from_data_list
-                pass
-            items = []
-            for i in range(len(self.zinc_dataset)):
-                d = self.zinc_dataset[i]
-                v = _V()
-                v.x, v.edge_index, v.edge_attr, v.y = d.x, d.edge_index, d.edge_attr, d.y
-                v.num_nodes = int(d.x.shape[0])
-                items.append(v)
-            self._gb = GraphBatch.from_data_list(items)
+            from gtok.batch import graph_batch_from_dataset
+            self._gb = graph_batch_from_dataset(self.zinc_dataset)      # InMemoryDataset storage converts without a Python loop
         return self._gb
 
     # ---- host rendering of the text (API compatibility only) ---------------------------------

@@ -155,6 +155,31 @@ class GraphBatch:
         return GraphBatch(node_off, edge_off, src, dst, xs, at, qu, qv, yy)
 
     @staticmethod
+    def from_collated(data, slices, indices: Optional[torch.Tensor] = None) -> "GraphBatch":
+        """From the storage of a PyG InMemoryDataset: `data` holds every graph's tensors concatenated
+        (x [N_total, 1] or [N_total], edge_index [2, E_total] with LOCAL node ids - InMemoryDataset.collate does not
+        increment them -, edge_attr [E_total(, 1)], y [G]) and `slices[key]` the G+1 boundaries per key.  No per-graph
+        Python: the offsets ARE the slices.  `indices` (dataset._indices of a shuffled / subset view) gathers afterwards."""
+        node_off = torch.as_tensor(slices["x"], dtype=torch.int64).clone()
+        edge_off = torch.as_tensor(slices["edge_index"], dtype=torch.int64).clone()
+        if node_off.numel() != edge_off.numel():
+            raise ValueError("slices['x'] and slices['edge_index'] describe different graph counts")
+        x = data.x
+        if x.dim() == 2:
+            if x.shape[1] != 1:
+                raise ValueError("one integer feature per node expected (ZINC atom types)")
+            x = x[:, 0]
+        ei = data.edge_index
+        if int(node_off[-1]) != x.shape[0] or int(edge_off[-1]) != ei.shape[1]:
+            raise ValueError("slices do not cover the stored tensors")
+        ea = getattr(data, "edge_attr", None)
+        y = getattr(data, "y", None)
+        gb = GraphBatch(node_off, edge_off, ei[0].to(torch.int32).contiguous(), ei[1].to(torch.int32).contiguous(),
+                        x.to(torch.int32).contiguous(), None if ea is None else ea.reshape(-1).to(torch.int32).contiguous(),
+                        None, None, None if y is None else y.reshape(-1)[: node_off.numel() - 1].clone())
+        return gb if indices is None else gb.select(indices)
+
+    @staticmethod
     def from_data_list(data_list: Sequence) -> "GraphBatch":
         """From PyG-style ``Data`` objects (duck-typed: edge_index[2,E], num_nodes,
         optional x, edge_attr, query_u, query_v, y)."""
@@ -178,6 +203,31 @@ class GraphBatch:
             qv = torch.as_tensor([int(d.query_v) for d in data_list], dtype=torch.int32)
         y = torch.cat([d.y.reshape(-1)[:1] for d in data_list]) if has("y") else None
         return GraphBatch(node_off, edge_off, ei[0].contiguous(), ei[1].contiguous(), x, ea, qu, qv, y)
+
+
+def graph_batch_from_dataset(ds) -> "GraphBatch":
+    """All graphs of a PyG-style dataset as one GraphBatch.  A PyG InMemoryDataset already holds its graphs
+    concatenated (`ds._data` / `ds.data` + `ds.slices`, optional `ds._indices`): that storage converts with a
+    handful of tensor ops (GraphBatch.from_collated); anything else goes item by item (from_data_list)."""
+    store = getattr(ds, "_data", None)
+    if store is None:
+        store = getattr(ds, "data", None)
+    slices = getattr(ds, "slices", None)
+    if store is not None and isinstance(slices, dict) and "x" in slices and "edge_index" in slices:
+        idx = getattr(ds, "_indices", None)
+        return GraphBatch.from_collated(store, slices, None if idx is None else torch.as_tensor(list(idx), dtype=torch.int64))
+
+    class _V:
+        pass
+    items = []
+    for i in range(len(ds)):
+        d = ds[i]
+        v = _V()
+        v.x, v.edge_index, v.y = d.x, d.edge_index, getattr(d, "y", None)
+        v.edge_attr = None if getattr(d, "edge_attr", None) is None else d.edge_attr.reshape(-1)
+        v.num_nodes = int(d.x.shape[0])
+        items.append(v)
+    return GraphBatch.from_data_list(items)
 
 
 def _narrowest(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:

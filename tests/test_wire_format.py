@@ -93,3 +93,53 @@ def test_non_canonical_batches_keep_every_column():
     assert pk.col16.numel() == E and pk.entry_cnt.to(torch.int64).tolist() == gb.num_entries().tolist()
     # without the flag nothing is dropped, whatever the batch looks like
     assert not PackedGraphBatch.from_batch(gb, fuse_columns=True).unique_columns
+
+
+def test_inmemory_dataset_storage_converts_without_a_python_loop():
+    """a PyG InMemoryDataset keeps its graphs concatenated (`_data` + `slices`, local node ids in
+    edge_index); GraphBatch.from_collated must equal the item-by-item conversion, with and without `_indices`."""
+    import types
+    from gtok.batch import graph_batch_from_dataset
+    rng = np.random.default_rng(4)
+    mols = _mols(rng, 60)
+    per_item = _batch(mols)
+    per_item.y = torch.arange(60, dtype=torch.float32) * 0.5
+
+    class FakeInMemory:
+        def __init__(self, indices=None):
+            self._data = types.SimpleNamespace(
+                x=per_item.x.to(torch.int64).reshape(-1, 1),
+                edge_index=torch.stack([per_item.src, per_item.dst]).to(torch.int64),
+                edge_attr=per_item.edge_attr.to(torch.int64), y=per_item.y)
+            self.slices = {"x": per_item.node_off.clone(), "edge_index": per_item.edge_off.clone(),
+                           "edge_attr": per_item.edge_off.clone(), "y": torch.arange(61)}
+            self._indices = indices
+
+        def __len__(self):
+            return 60 if self._indices is None else len(self._indices)
+
+        def __getitem__(self, i):
+            raise AssertionError("the collated storage must be used, not per-item access")
+
+    def same(a, b):
+        for f in ("node_off", "edge_off", "src", "dst", "x", "edge_attr", "y"):
+            assert torch.equal(getattr(a, f), getattr(b, f)), f
+        assert a.src.dtype == torch.int32 and a.x.dtype == torch.int32 and a.node_off.dtype == torch.int64
+
+    same(graph_batch_from_dataset(FakeInMemory()), per_item)
+    idx = [5, 3, 59, 0, 3]
+    same(graph_batch_from_dataset(FakeInMemory(idx)), per_item.select(torch.tensor(idx)))
+    # a plain sequence of Data-like items still converts item by item
+    items = []
+    for g in range(60):
+        n, s_, d_, x_, a_ = per_item.graph(g)
+        items.append(types.SimpleNamespace(x=x_.reshape(-1, 1), edge_index=torch.stack([s_, d_]), edge_attr=a_.reshape(-1, 1),
+                                           y=per_item.y[g:g + 1]))
+    same(graph_batch_from_dataset(items), per_item)
+    bad = FakeInMemory()
+    bad.slices["x"] = bad.slices["x"][:-1]
+    try:
+        graph_batch_from_dataset(bad)
+        assert False
+    except ValueError:
+        pass
