@@ -228,11 +228,28 @@ er_kernel(GtokErSpec s, int64_t G, int32_t* __restrict__ nn_out, int32_t* __rest
       const long long blk = b0 + lane;
       unsigned bits = 0;
       if (blk < blocks) {
-        unsigned o0, o1, o2, o3;
-        philox10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(2 + blk), 1u, k0, k1, o0, o1, o2, o3);
+        unsigned o[4];
+        philox10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(2 + blk), 1u, k0, k1, o[0], o[1], o[2], o[3]);
         const long long kk = blk << 2;
-        bits = (o0 < h.thr ? 1u : 0u) | (kk + 1 < P && o1 < h.thr ? 2u : 0u) | (kk + 2 < P && o2 < h.thr ? 4u : 0u) |
-               (kk + 3 < P && o3 < h.thr ? 8u : 0u);
+        if (s.kind == GTOK_GEN_ER) {
+          bits = (o[0] < h.thr ? 1u : 0u) | (kk + 1 < P && o[1] < h.thr ? 2u : 0u) | (kk + 2 < P && o[2] < h.thr ? 4u : 0u) |
+                 (kk + 3 < P && o[3] < h.thr ? 8u : 0u);
+        } else {                                         // the other families decide per (u, v)
+          int u, v;
+          er_pair(kk, h.n, u, v);
+          const unsigned thr_out = (unsigned)(((unsigned long long)h.thr * s.out_ratio_q16) >> 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            bool keep;
+            if (s.kind == GTOK_GEN_SBM)
+              keep = o[i] < (((long long)u * s.num_blocks) / h.n == ((long long)v * s.num_blocks) / h.n ? h.thr : thr_out);
+            else if (s.kind == GTOK_GEN_COMPLETE) keep = true;
+            else if (s.kind == GTOK_GEN_STAR) keep = u == 0;
+            else keep = v == u + 1;
+            if (kk + i < P && keep) bits |= 1u << i;
+            if (++v == h.n) { ++u; v = u + 1; }
+          }
+        }
       }
       const int cnt = __popc(bits);
       int incl = cnt;
@@ -278,6 +295,9 @@ static int er_check(const GtokErSpec* s, int64_t G, const char* who) {
     GTOK_REQUIRE(s->n_lo[b] >= 1 && s->n_lo[b] < s->n_hi[b] && s->n_hi[b] <= 32768, GTOK_EINVAL,
                  "%s: bucket %d needs 1 <= n_lo < n_hi <= 32768 (got [%d, %d))", who, b, s->n_lo[b], s->n_hi[b]);
   GTOK_REQUIRE(s->thr_lo <= s->thr_hi, GTOK_EINVAL, "%s: thr_lo > thr_hi", who);
+  GTOK_REQUIRE(s->kind >= GTOK_GEN_ER && s->kind <= GTOK_GEN_PATH, GTOK_EINVAL, "%s: unknown generator kind %d", who, s->kind);
+  GTOK_REQUIRE(s->kind != GTOK_GEN_SBM || (s->num_blocks >= 1 && s->num_blocks <= 16 && s->out_ratio_q16 <= 65536u), GTOK_EINVAL,
+               "%s: sbm needs 1..16 blocks and out_ratio_q16 <= 65536", who);
   return GTOK_OK;
 }
 

@@ -61,7 +61,7 @@ class SentCfgC(C.Structure):
 
 class ErSpecC(C.Structure):
     _fields_ = [("num_buckets", i32), ("n_lo", i32 * 4), ("n_hi", i32 * 4), ("thr_lo", C.c_uint32), ("thr_hi", C.c_uint32),
-                ("reserved_", i32), ("seed", u64), ("graph_id_base", i64)]
+                ("kind", i32), ("num_blocks", i32), ("out_ratio_q16", C.c_uint32), ("seed", u64), ("graph_id_base", i64)]
 
 
 class ChoiceC(C.Structure):

@@ -618,29 +618,37 @@ def graph_labels(csr: CsrBatch, edge_off: Optional[torch.Tensor] = None, cycle: 
 ER_BUCKETS = ((10, 20), (20, 40), (40, 50))        # docs/synthetic_data.md:130-138
 
 
-def er_spec(seed: int, graph_id_base: int = 0, buckets=ER_BUCKETS, p_min: float = 0.1, p_max: float = 0.2) -> _lib.ErSpecC:
+GEN_KINDS = {"er": 0, "sbm": 1, "complete": 2, "star": 3, "path": 4}      # include/gtok.h GTOK_GEN_*
+
+
+def er_spec(seed: int, graph_id_base: int = 0, buckets=ER_BUCKETS, p_min: float = 0.1, p_max: float = 0.2,
+            kind: str = "er", num_blocks: int = 2, out_ratio: float = 0.25) -> _lib.ErSpecC:
     if not 1 <= len(buckets) <= 4:
         raise ValueError("1..4 size buckets expected")
+    if kind not in GEN_KINDS:
+        raise ValueError(f"unknown generator {kind!r} (have {sorted(GEN_KINDS)}; ba / sfn are not provided)")
     thr = lambda p: max(0, min(0xFFFFFFFF, int(math.floor(float(p) * 4294967296.0))))
     s = _lib.ErSpecC()
     s.num_buckets = len(buckets)
     for i, (lo, hi) in enumerate(buckets):
         s.n_lo[i], s.n_hi[i] = int(lo), int(hi)
     s.thr_lo, s.thr_hi = thr(p_min), thr(p_max)
+    s.kind, s.num_blocks, s.out_ratio_q16 = GEN_KINDS[kind], int(num_blocks), max(0, min(65536, int(round(out_ratio * 65536))))
     s.seed, s.graph_id_base = int(seed) & (2 ** 64 - 1), int(graph_id_base)
     return s
 
 
 def generate_er(num_graphs: int, seed: int = 0, graph_id_base: int = 0, buckets=ER_BUCKETS, p_min: float = 0.1,
-                p_max: float = 0.2, device="cuda") -> GraphBatch:
-    """Graph-token-shaped Erdos-Renyi graphs generated ON the device (docs/synthetic_data.md:93-94,130-138
-    distribution; stream = oracle/tasks_oracle.py er_graph): every undirected edge once, u < v ascending, plus a
-    query pair per graph.  Keyed by the global graph id, so shards of a larger job generate their own slice."""
+                p_max: float = 0.2, device="cuda", kind: str = "er", num_blocks: int = 2, out_ratio: float = 0.25) -> GraphBatch:
+    """Graph-token-shaped graphs generated ON the device (docs/synthetic_data.md:93-94,130-138 distribution; stream =
+    oracle/tasks_oracle.py er_graph): every undirected edge once, u < v ascending, plus a query pair per graph.
+    kind: "er" (default), "sbm" (num_blocks contiguous blocks, p inside / p * out_ratio across), "complete", "star",
+    "path".  Keyed by the global graph id, so shards of a larger job generate their own slice."""
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("gtok has no CPU path: a CUDA device is required")
     G = int(num_graphs)
-    spec = er_spec(seed, graph_id_base, buckets, p_min, p_max)
+    spec = er_spec(seed, graph_id_base, buckets, p_min, p_max, kind, num_blocks, out_ratio)
     nn = torch.empty(G, dtype=torch.int32, device=dev)
     ne = torch.empty(G, dtype=torch.int32, device=dev)
     qu = torch.empty(G, dtype=torch.int32, device=dev)

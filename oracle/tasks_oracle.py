@@ -115,12 +115,13 @@ def prob_threshold(p: float) -> int:
 
 
 def er_graph(seed: int, gid: int, buckets: Sequence[Tuple[int, int]] = ((10, 20), (20, 40), (40, 50)),
-             p_min: float = 0.1, p_max: float = 0.2):
+             p_min: float = 0.1, p_max: float = 0.2, kind: str = "er", num_blocks: int = 2, out_ratio: float = 0.25):
     """-> (n, edges [(u, v)] with u < v ascending, (query_u, query_v)).
     word 0: bucket = mulhi(w, len(buckets));  word 1: n = lo + mulhi(w, hi - lo);
     word 2: thr = t_lo + mulhi(w, t_hi - t_lo);  word 3: query_u = mulhi(w, n);
     word 4: query_v = (query_u + 1 + mulhi(w, n - 1)) % n  (n == 1: query_v = query_u);
-    pair k (row-major over u < v) is an edge iff word(8 + k) < thr."""
+    pair k (row-major over u < v) is an edge iff word(8 + k) < thr (kind "er"); "sbm": < thr inside a block,
+    < thr * out_ratio across blocks; "complete" / "star" (centre 0) / "path" (i - i+1): the deterministic shapes."""
     w = _Words(seed, gid)
     lo, hi = buckets[(w(0) * len(buckets)) >> 32]
     n = lo + ((w(1) * (hi - lo)) >> 32)
@@ -128,11 +129,25 @@ def er_graph(seed: int, gid: int, buckets: Sequence[Tuple[int, int]] = ((10, 20)
     thr = t_lo + ((w(2) * (t_hi - t_lo)) >> 32)
     qu = (w(3) * n) >> 32
     qv = (qu + 1 + ((w(4) * (n - 1)) >> 32)) % n if n > 1 else qu
+    thr_out = (thr * max(0, min(65536, int(round(out_ratio * 65536))))) >> 16
     edges = []
     k = 0
     for u in range(n):
         for v in range(u + 1, n):
-            if w(ER_PAIR_WORD0 + k) < thr:
+            word = w(ER_PAIR_WORD0 + k)
+            if kind == "er":
+                keep = word < thr
+            elif kind == "sbm":        # contiguous blocks: block(i) = i * num_blocks // n
+                keep = word < (thr if (u * num_blocks) // n == (v * num_blocks) // n else thr_out)
+            elif kind == "complete":
+                keep = True
+            elif kind == "star":
+                keep = u == 0
+            elif kind == "path":
+                keep = v == u + 1
+            else:
+                raise ValueError(kind)
+            if keep:
                 edges.append((u, v))
             k += 1
     return n, edges, (qu, qv)

@@ -31,7 +31,7 @@ def test_version_and_struct_sizes():
     assert ctypes.sizeof(_lib.CsrBatchC) == 96
     assert ctypes.sizeof(_lib.SentCfgC) == 32
     assert ctypes.sizeof(_lib.ChoiceC) == 32
-    assert ctypes.sizeof(_lib.ErSpecC) == 64 and _lib.ErSpecC.seed.offset == 48
+    assert ctypes.sizeof(_lib.ErSpecC) == 72 and _lib.ErSpecC.seed.offset == 56
 
 
 def test_no_cpu_fallback():

@@ -1061,3 +1061,31 @@ def test_sent_workspace_kernel_above_4096_nodes(dev):
     # automatic choice: workspace kernel for these sizes, shared-memory kernel for 1000-node graphs
     tc, lc = engine.tokenize_sent(csr, cfg, seed=2)
     assert torch.equal(lc, la) and torch.equal(tc[0, :int(la[0])], ta[0, :int(la[0])])
+
+
+@pytest.mark.parametrize("kind", ["sbm", "complete", "star", "path"])
+def test_generator_families_match_oracle(dev, kind):
+    """The other generator families of docs/synthetic_data.md:93-94 on the device == oracle/tasks_oracle.py er_graph,
+    and their labels follow from the shape (star / path: no cycle; complete on >= 3 nodes: cycle)."""
+    from gtok import engine
+    from oracle import tasks_oracle as T
+    kw = dict(kind=kind, num_blocks=3, out_ratio=0.2, p_min=0.15, p_max=0.5, buckets=((1, 6), (10, 50), (60, 90)))
+    okw = dict(kw)
+    gb = engine.generate_er(150, seed=8, graph_id_base=40, device=dev, **kw)
+    n, eo = gb.num_nodes().cpu().tolist(), gb.edge_off.cpu().tolist()
+    src, dst = gb.src.cpu().tolist(), gb.dst.cpu().tolist()
+    recs = []
+    for g in range(150):
+        wn, we, wq = T.er_graph(8, 40 + g, **okw)
+        assert n[g] == wn and list(zip(src[eo[g]:eo[g + 1]], dst[eo[g]:eo[g + 1]])) == we, (kind, g)
+        assert (int(gb.query_u[g]), int(gb.query_v[g])) == wq
+        recs.append((wn, we, wq))
+    cyc, dist = engine.graph_labels(engine.build_csr(gb), edge_off=gb.edge_off, distance=True)
+    assert cyc.cpu().tolist() == [int(T.has_cycle_dfs(a, e)) for a, e, _ in recs]
+    assert dist.cpu().tolist() == [T.shortest_distance(a, e, u, v) for a, e, (u, v) in recs]
+    if kind in ("star", "path"):
+        assert int(cyc.sum()) == 0 and int((dist < 0).sum()) == 0
+    if kind == "complete":
+        assert cyc.cpu().tolist() == [int(a >= 3) for a, _, _ in recs]
+    with pytest.raises(ValueError):
+        engine.generate_er(4, kind="ba", device=dev)

@@ -113,3 +113,26 @@ def test_oracle_matches_reference_golden():
         assert (len(edges) > c["n"] - _components(c["n"], edges)) == c["has_cycle"]
     for r in gold["query_rows"]:
         assert T.first_token_pos(r["row"], r["q"]) == r["pos"]
+
+
+def test_generator_families():
+    n, e, _ = T.er_graph(3, 1, kind="complete")
+    assert e == [(u, v) for u in range(n) for v in range(u + 1, n)]
+    n, e, _ = T.er_graph(3, 2, kind="star")
+    assert e == [(0, v) for v in range(1, n)] and not T.has_cycle_dfs(n, e)
+    n, e, _ = T.er_graph(3, 3, kind="path")
+    assert e == [(i, i + 1) for i in range(n - 1)] and T.shortest_distance(n, e, 0, n - 1) == n - 1
+    inside = across = pin = pac = 0
+    for gid in range(300):
+        n, e, _ = T.er_graph(5, gid, kind="sbm", num_blocks=3, out_ratio=0.1, p_min=0.4, p_max=0.4)
+        blk = lambda i: (i * 3) // n
+        es = set(e)
+        for u in range(n):
+            for v in range(u + 1, n):
+                if blk(u) == blk(v):
+                    pin += 1; inside += (u, v) in es
+                else:
+                    pac += 1; across += (u, v) in es
+    assert 0.37 < inside / pin < 0.43 and 0.03 < across / pac < 0.05
+    # same header stream for every family: sizes and queries do not depend on the kind
+    assert T.er_graph(9, 4, kind="sbm")[0] == T.er_graph(9, 4)[0] and T.er_graph(9, 4, kind="path")[2] == T.er_graph(9, 4)[2]
