@@ -179,7 +179,7 @@ labels_warp_kernel(GtokCsrBatch c, const int64_t* __restrict__ edge_off, int32_t
 }
 
 // ------------------------------------------------------------------------------------------------- ER generator
-struct ErHeader { int n; unsigned thr; int qu, qv; };
+struct ErHeader { int n; unsigned thr; int qu, qv; int m; };
 
 __device__ __forceinline__ unsigned mulhi_u32(unsigned a, unsigned b) { return __umulhi(a, b); }
 
@@ -194,6 +194,8 @@ __device__ __forceinline__ ErHeader er_header(const GtokErSpec& s, unsigned long
   h.thr = s.thr_lo + mulhi_u32(w2, s.thr_hi - s.thr_lo);
   h.qu = (int)mulhi_u32(w3, (unsigned)h.n);
   h.qv = h.n > 1 ? (h.qu + 1 + (int)mulhi_u32(w4, (unsigned)(h.n - 1))) % h.n : h.qu;
+  h.m = 0;
+  if (s.kind == GTOK_GEN_BA) h.m = min(1 + (int)mulhi_u32(w2, (unsigned)s.num_blocks), h.n - 1);   // attachments per new node
   return h;
 }
 
@@ -222,8 +224,8 @@ er_kernel(GtokErSpec s, int64_t G, int32_t* __restrict__ nn_out, int32_t* __rest
     const unsigned long long gid = (unsigned long long)(s.graph_id_base + g);
     const ErHeader h = er_header(s, gid);
     const long long P = (long long)h.n * (h.n - 1) / 2;
-    const long long blocks = (P + 3) >> 2;
-    long long base = FILL ? __ldg(edge_off + g) : 0;
+    const long long blocks = s.kind == GTOK_GEN_BA ? 0 : (P + 3) >> 2;     // ba: closed-form count, filled by ba_fill_kernel
+    long long base = FILL ? __ldg(edge_off + g) : (s.kind == GTOK_GEN_BA ? (long long)h.m * (h.n - h.m) : 0);
     for (long long b0 = 0; b0 < blocks; b0 += kWarp) {
       const long long blk = b0 + lane;
       unsigned bits = 0;
@@ -279,6 +281,62 @@ er_kernel(GtokErSpec s, int64_t G, int32_t* __restrict__ nn_out, int32_t* __rest
   }
 }
 
+// Barabasi-Albert graphs (preferential attachment is sequential per graph): a thread per graph, adjacency as 64-bit
+// rows in shared memory (so the edges come out sorted like every other family), degree-proportional targets drawn by
+// walking the cumulative degrees.  Stream definition: oracle/tasks_oracle.py er_graph(kind="ba").
+constexpr int kBaThreads = 64;
+__global__ void __launch_bounds__(kBaThreads)
+ba_fill_kernel(GtokErSpec s, int64_t G, const int64_t* __restrict__ edge_off, int32_t* __restrict__ src,
+               int32_t* __restrict__ dst) {
+  __shared__ unsigned long long rows[64][kBaThreads];
+  __shared__ unsigned char deg[64][kBaThreads];
+  const int t = threadIdx.x;
+  const unsigned k0 = (unsigned)s.seed, k1 = (unsigned)(s.seed >> 32);
+  for (int64_t g = (int64_t)blockIdx.x * kBaThreads + t; g < G; g += (int64_t)gridDim.x * kBaThreads) {
+    const unsigned long long gid = (unsigned long long)(s.graph_id_base + g);
+    const ErHeader h = er_header(s, gid);
+    const int n = h.n, m = h.m;
+    for (int i = 0; i < n; ++i) { rows[i][t] = 0ull; deg[i][t] = 0; }
+    auto add_edge = [&](int a, int b) {
+      rows[a][t] |= 1ull << b; rows[b][t] |= 1ull << a;
+      ++deg[a][t]; ++deg[b][t];
+    };
+    for (int i = 1; i <= m; ++i) add_edge(0, i);                 // star on nodes 0..m
+    unsigned e2 = 2u * (unsigned)m;                              // sum of degrees
+    unsigned d = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0, have = 0xffffffffu;
+    for (int source = m + 1; source < n; ++source) {
+      unsigned long long tm = 0ull;
+      int cnt = 0;
+      while (cnt < m) {
+        const unsigned wi = 8u + d, blk = wi >> 2;
+        ++d;
+        if (blk != have) { philox10((unsigned)gid, (unsigned)(gid >> 32), blk, 1u, k0, k1, b0, b1, b2, b3); have = blk; }
+        const unsigned word = (wi & 2u) ? ((wi & 1u) ? b3 : b2) : ((wi & 1u) ? b1 : b0);
+        const unsigned r = __umulhi(word, e2);
+        int x = 0;
+        unsigned acc = deg[0][t];
+        while (acc <= r) { ++x; acc += deg[x][t]; }
+        if (!((tm >> x) & 1ull)) { tm |= 1ull << x; ++cnt; }
+      }
+      while (tm) {
+        const int x = __ffsll((long long)tm) - 1;
+        tm &= tm - 1;
+        add_edge(x, source);
+      }
+      e2 += 2u * (unsigned)m;
+    }
+    long long at = __ldg(edge_off + g);
+    for (int u = 0; u < n; ++u) {
+      unsigned long long up = u < 63 ? (rows[u][t] >> (u + 1)) << (u + 1) : 0ull;
+      while (up) {
+        const int v = __ffsll((long long)up) - 1;
+        up &= up - 1;
+        src[at] = u; dst[at] = v; ++at;
+      }
+    }
+  }
+}
+
 static int task_grid(int64_t warps_needed) {
   const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 8;
   int64_t blocks = (warps_needed + kTaskThreads / 32 - 1) / (kTaskThreads / 32);
@@ -295,7 +353,12 @@ static int er_check(const GtokErSpec* s, int64_t G, const char* who) {
     GTOK_REQUIRE(s->n_lo[b] >= 1 && s->n_lo[b] < s->n_hi[b] && s->n_hi[b] <= 32768, GTOK_EINVAL,
                  "%s: bucket %d needs 1 <= n_lo < n_hi <= 32768 (got [%d, %d))", who, b, s->n_lo[b], s->n_hi[b]);
   GTOK_REQUIRE(s->thr_lo <= s->thr_hi, GTOK_EINVAL, "%s: thr_lo > thr_hi", who);
-  GTOK_REQUIRE(s->kind >= GTOK_GEN_ER && s->kind <= GTOK_GEN_PATH, GTOK_EINVAL, "%s: unknown generator kind %d", who, s->kind);
+  GTOK_REQUIRE(s->kind >= GTOK_GEN_ER && s->kind <= GTOK_GEN_BA, GTOK_EINVAL, "%s: unknown generator kind %d", who, s->kind);
+  if (s->kind == GTOK_GEN_BA) {
+    GTOK_REQUIRE(s->num_blocks >= 1 && s->num_blocks <= 8, GTOK_EINVAL, "%s: ba needs 1..8 attachments per node (num_blocks)", who);
+    for (int b = 0; b < s->num_buckets; ++b)
+      GTOK_REQUIRE(s->n_hi[b] <= 65, GTOK_EINVAL, "%s: ba graphs are limited to 64 nodes (bucket %d ends at %d)", who, b, s->n_hi[b]);
+  }
   GTOK_REQUIRE(s->kind != GTOK_GEN_SBM || (s->num_blocks >= 1 && s->num_blocks <= 16 && s->out_ratio_q16 <= 65536u), GTOK_EINVAL,
                "%s: sbm needs 1..16 blocks and out_ratio_q16 <= 65536", who);
   return GTOK_OK;
@@ -370,8 +433,15 @@ extern "C" int gtok_er_edges(const GtokErSpec* spec, int64_t num_graphs, const i
   if (int rc = er_check(spec, num_graphs, "er_edges")) return rc;
   if (num_graphs == 0) return GTOK_OK;
   GTOK_REQUIRE(edge_off != nullptr, GTOK_EINVAL, "er_edges: null edge_off");          // src / dst may be null without edges
-  er_kernel<true><<<task_grid(num_graphs), kTaskThreads, 0, (cudaStream_t)stream>>>(
-      *spec, num_graphs, nullptr, nullptr, nullptr, nullptr, edge_off, src_out, dst_out);
+  if (spec->kind == GTOK_GEN_BA) {
+    const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 4;
+    const int64_t blocks = (num_graphs + kBaThreads - 1) / kBaThreads;
+    ba_fill_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kBaThreads, 0, (cudaStream_t)stream>>>(*spec, num_graphs, edge_off,
+                                                                                                   src_out, dst_out);
+  } else {
+    er_kernel<true><<<task_grid(num_graphs), kTaskThreads, 0, (cudaStream_t)stream>>>(
+        *spec, num_graphs, nullptr, nullptr, nullptr, nullptr, edge_off, src_out, dst_out);
+  }
   GTOK_CUDA_TRY(cudaGetLastError());
   return GTOK_OK;
 }

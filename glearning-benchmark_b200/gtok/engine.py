@@ -618,7 +618,7 @@ def graph_labels(csr: CsrBatch, edge_off: Optional[torch.Tensor] = None, cycle: 
 ER_BUCKETS = ((10, 20), (20, 40), (40, 50))        # docs/synthetic_data.md:130-138
 
 
-GEN_KINDS = {"er": 0, "sbm": 1, "complete": 2, "star": 3, "path": 4}      # include/gtok.h GTOK_GEN_*
+GEN_KINDS = {"er": 0, "sbm": 1, "complete": 2, "star": 3, "path": 4, "ba": 5}      # include/gtok.h GTOK_GEN_*
 
 
 def er_spec(seed: int, graph_id_base: int = 0, buckets=ER_BUCKETS, p_min: float = 0.1, p_max: float = 0.2,
@@ -626,7 +626,7 @@ def er_spec(seed: int, graph_id_base: int = 0, buckets=ER_BUCKETS, p_min: float 
     if not 1 <= len(buckets) <= 4:
         raise ValueError("1..4 size buckets expected")
     if kind not in GEN_KINDS:
-        raise ValueError(f"unknown generator {kind!r} (have {sorted(GEN_KINDS)}; ba / sfn are not provided)")
+        raise ValueError(f"unknown generator {kind!r} (have {sorted(GEN_KINDS)}; sfn is not provided)")
     thr = lambda p: max(0, min(0xFFFFFFFF, int(math.floor(float(p) * 4294967296.0))))
     s = _lib.ErSpecC()
     s.num_buckets = len(buckets)
@@ -643,7 +643,7 @@ def generate_er(num_graphs: int, seed: int = 0, graph_id_base: int = 0, buckets=
     """Graph-token-shaped graphs generated ON the device (docs/synthetic_data.md:93-94,130-138 distribution; stream =
     oracle/tasks_oracle.py er_graph): every undirected edge once, u < v ascending, plus a query pair per graph.
     kind: "er" (default), "sbm" (num_blocks contiguous blocks, p inside / p * out_ratio across), "complete", "star",
-    "path".  Keyed by the global graph id, so shards of a larger job generate their own slice."""
+    "path", "ba" (Barabasi-Albert, m ~ U{1..num_blocks} attachments per new node, graphs of at most 64 nodes).  Keyed by the global graph id, so shards of a larger job generate their own slice."""
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("gtok has no CPU path: a CUDA device is required")

@@ -334,21 +334,22 @@ GTOK_API int gtok_graph_labels(const GtokCsrBatch* csr, const int64_t* edge_off,
                                int32_t* dist_out, void* stream);
 
 /*      On-device graphs of the docs' generator families er / sbm / complete / star / path with the docs' size /
- *      sparsity distribution (docs/synthetic_data.md:93-94,130-138; ba and sfn, sequential preferential attachment,
- *      are not provided);
+ *      sparsity distribution (docs/synthetic_data.md:93-94,130-138; ba too, up to 64 nodes; sfn is not provided);
  *      the stream definition is oracle/tasks_oracle.py er_graph (Philox-4x32-10 keyed by seed, counter = global
  *      graph id, so output is invariant to sharding).  gtok_er_sizes writes per-graph node / edge counts and a
  *      query pair; the caller scans the counts (gtok_counts_to_offsets) and gtok_er_edges fills src / dst
  *      (each edge once, u < v ascending - the order graph-token texts list them in). */
 enum { GTOK_GEN_ER = 0,        /* every pair with probability p */
        GTOK_GEN_SBM = 1,       /* stochastic block model: p inside a block, p_out across */
-       GTOK_GEN_COMPLETE = 2, GTOK_GEN_STAR = 3 /* centre 0 */, GTOK_GEN_PATH = 4 /* i - (i+1) */ };
+       GTOK_GEN_COMPLETE = 2, GTOK_GEN_STAR = 3 /* centre 0 */, GTOK_GEN_PATH = 4 /* i - (i+1) */,
+       GTOK_GEN_BA = 5         /* Barabasi-Albert preferential attachment, m ~ U{1..num_blocks} new edges per node, N <= 64 */ };
 typedef struct GtokErSpec {
   int32_t num_buckets;       /* 1..4 size buckets, one drawn uniformly per graph */
   int32_t n_lo[4], n_hi[4];  /* N uniform in [n_lo, n_hi), 1 <= n_lo < n_hi <= 32768 */
   uint32_t thr_lo, thr_hi;   /* edge probability p ~ U(thr_lo, thr_hi) / 2^32 */
   int32_t kind;              /* GTOK_GEN_*: which of the docs' generator families (docs/synthetic_data.md:93-94) */
-  int32_t num_blocks;        /* GTOK_GEN_SBM: 1..16 contiguous blocks, block(i) = i * num_blocks / N */
+  int32_t num_blocks;        /* GTOK_GEN_SBM: 1..16 contiguous blocks, block(i) = i * num_blocks / N;
+                                GTOK_GEN_BA: largest attachment count m (1..8) */
   uint32_t out_ratio_q16;    /* GTOK_GEN_SBM: p_out = p * out_ratio_q16 / 65536 between different blocks */
   uint64_t seed;
   int64_t graph_id_base;

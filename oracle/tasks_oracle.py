@@ -114,6 +114,38 @@ def prob_threshold(p: float) -> int:
     return max(0, min(_MASK, int(np.floor(float(p) * 4294967296.0))))
 
 
+def _ba_edges(w, n: int, m: int):
+    """Barabasi-Albert after networkx.barabasi_albert_graph: a star on nodes 0..m, then every new node attaches to m
+    DISTINCT existing nodes drawn with probability proportional to their degree (degrees as they were before this
+    node's own edges).  Draw d reads word 8 + d: r = mulhi(word, sum of degrees), target = first node whose
+    cumulative degree exceeds r; repeats are redrawn.  Edges returned sorted (u < v ascending)."""
+    deg = [0] * n
+    es = set()
+
+    def add(a, b):
+        es.add((min(a, b), max(a, b)))
+        deg[a] += 1
+        deg[b] += 1
+    for i in range(1, m + 1):
+        add(0, i)
+    e2, d = 2 * m, 0
+    for source in range(m + 1, n):
+        targets = []
+        while len(targets) < m:
+            r = (w(ER_PAIR_WORD0 + d) * e2) >> 32
+            d += 1
+            x, acc = 0, deg[0]
+            while acc <= r:
+                x += 1
+                acc += deg[x]
+            if x not in targets:
+                targets.append(x)
+        for x in targets:
+            add(x, source)
+        e2 += 2 * m
+    return sorted(es)
+
+
 def er_graph(seed: int, gid: int, buckets: Sequence[Tuple[int, int]] = ((10, 20), (20, 40), (40, 50)),
              p_min: float = 0.1, p_max: float = 0.2, kind: str = "er", num_blocks: int = 2, out_ratio: float = 0.25):
     """-> (n, edges [(u, v)] with u < v ascending, (query_u, query_v)).
@@ -129,6 +161,8 @@ def er_graph(seed: int, gid: int, buckets: Sequence[Tuple[int, int]] = ((10, 20)
     thr = t_lo + ((w(2) * (t_hi - t_lo)) >> 32)
     qu = (w(3) * n) >> 32
     qv = (qu + 1 + ((w(4) * (n - 1)) >> 32)) % n if n > 1 else qu
+    if kind == "ba":
+        return n, _ba_edges(w, n, min(1 + ((w(2) * num_blocks) >> 32), n - 1)), (qu, qv)
     thr_out = (thr * max(0, min(65536, int(round(out_ratio * 65536))))) >> 16
     edges = []
     k = 0

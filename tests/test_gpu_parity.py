@@ -1063,13 +1063,15 @@ def test_sent_workspace_kernel_above_4096_nodes(dev):
     assert torch.equal(lc, la) and torch.equal(tc[0, :int(la[0])], ta[0, :int(la[0])])
 
 
-@pytest.mark.parametrize("kind", ["sbm", "complete", "star", "path"])
+@pytest.mark.parametrize("kind", ["sbm", "complete", "star", "path", "ba"])
 def test_generator_families_match_oracle(dev, kind):
     """The other generator families of docs/synthetic_data.md:93-94 on the device == oracle/tasks_oracle.py er_graph,
     and their labels follow from the shape (star / path: no cycle; complete on >= 3 nodes: cycle)."""
     from gtok import engine
     from oracle import tasks_oracle as T
     kw = dict(kind=kind, num_blocks=3, out_ratio=0.2, p_min=0.15, p_max=0.5, buckets=((1, 6), (10, 50), (60, 90)))
+    if kind == "ba":
+        kw.update(num_blocks=5, buckets=((1, 6), (10, 50), (60, 65)))       # attachments m ~ U{1..5}, at most 64 nodes
     okw = dict(kw)
     gb = engine.generate_er(150, seed=8, graph_id_base=40, device=dev, **kw)
     n, eo = gb.num_nodes().cpu().tolist(), gb.edge_off.cpu().tolist()
@@ -1087,5 +1089,10 @@ def test_generator_families_match_oracle(dev, kind):
         assert int(cyc.sum()) == 0 and int((dist < 0).sum()) == 0
     if kind == "complete":
         assert cyc.cpu().tolist() == [int(a >= 3) for a, _, _ in recs]
+    if kind == "ba":
+        assert gb.num_entries().cpu().tolist() == [len(e) for _, e, _ in recs] and int((dist < 0).sum()) == 0   # connected
+        from gtok._lib import GtokError
+        with pytest.raises(GtokError):
+            engine.generate_er(4, kind="ba", buckets=((10, 80),), device=dev)                                   # > 64 nodes
     with pytest.raises(ValueError):
-        engine.generate_er(4, kind="ba", device=dev)
+        engine.generate_er(4, kind="sfn", device=dev)

@@ -136,3 +136,21 @@ def test_generator_families():
     assert 0.37 < inside / pin < 0.43 and 0.03 < across / pac < 0.05
     # same header stream for every family: sizes and queries do not depend on the kind
     assert T.er_graph(9, 4, kind="sbm")[0] == T.er_graph(9, 4)[0] and T.er_graph(9, 4, kind="path")[2] == T.er_graph(9, 4)[2]
+
+
+def test_ba_generator_shape():
+    """Barabasi-Albert family: m * (n - m) edges, connected, every node past the initial star has degree >= m, and the
+    early nodes collect the high degrees (preferential attachment)."""
+    hub = tail = 0
+    for gid in range(300):
+        n, e, _ = T.er_graph(2, gid, kind="ba", num_blocks=3)
+        m = min(1 + ((T._Words(2, gid)(2) * 3) >> 32), n - 1)
+        assert len(e) == m * (n - m) and e == sorted(set(e))
+        deg = [0] * n
+        for u, v in e:
+            deg[u] += 1
+            deg[v] += 1
+        assert all(deg[i] >= m for i in range(m + 1, n)) and T.shortest_distance(n, e, 0, n - 1) > 0
+        hub += deg[0]
+        tail += deg[n - 1]
+    assert hub > 3 * tail
