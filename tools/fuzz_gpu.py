@@ -4,7 +4,8 @@
 ZINC: molecules up to 64 atoms / 256 columns, shuffled / duplicated / self-loop columns, out-of-range atom and bond
 types, random max_len (all truncation branches), batch sizes 32..256, graph counts around tile multiples; ragged,
 padded and packed-layout kernels.  Graph-token: random tasks / max_len / OOV vocabularies, fused collate with shuffled
-row order.  SENT: graphs up to 256 nodes (all three thread-per-graph word counts), labeled / remap / query / truncation."""
+row order.  SENT: graphs up to 900 nodes (thread-per-graph word counts, both warp-per-graph kernels), labeled / remap / query /
+truncation.  Around the path: all device generator families, task labels, query positions."""
 import os
 import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -158,9 +159,49 @@ def sent_round():
           f"{'ok' if ok else 'MISMATCH'}")
 
 
+def tasks_round():
+    """device generators (all families) + task labels + query positions vs oracle/tasks_oracle.py"""
+    global bad
+    from oracle import tasks_oracle as T
+    kind = str(rng.choice(["er", "sbm", "complete", "star", "path", "ba"]))
+    nb = int(rng.integers(1, 5))
+    lows = sorted(int(v) for v in rng.integers(1, 60, nb))
+    buckets = tuple((lo, lo + int(rng.integers(1, 6))) for lo in lows)            # at most 64 nodes (ba)
+    p0 = float(rng.uniform(0, 0.4))
+    kw = dict(kind=kind, buckets=buckets, p_min=p0, p_max=p0 + float(rng.uniform(0, 0.5)),
+              num_blocks=int(rng.integers(1, 9)), out_ratio=float(rng.uniform(0, 1)))
+    G, seed, base = int(rng.choice([1, 33, 257])), int(rng.integers(0, 2 ** 62)), int(rng.integers(0, 2 ** 40))
+    gb = engine.generate_er(G, seed=seed, graph_id_base=base, device=dev, **kw)
+    n, eo = gb.num_nodes().cpu().tolist(), gb.edge_off.cpu().tolist()
+    src, dst = gb.src.cpu().tolist(), gb.dst.cpu().tolist()
+    ok, recs = True, []
+    for g in range(G):
+        wn, we, wq = T.er_graph(seed, base + g, **kw)
+        ok = ok and n[g] == wn and list(zip(src[eo[g]:eo[g + 1]], dst[eo[g]:eo[g + 1]])) == we \
+            and (int(gb.query_u[g]), int(gb.query_v[g])) == wq
+        recs.append((wn, we, wq))
+    cyc, dist = engine.graph_labels(engine.build_csr(gb), edge_off=gb.edge_off, distance=True)
+    ok = ok and cyc.cpu().tolist() == [int(T.has_cycle_dfs(a, e)) for a, e, _ in recs]
+    ok = ok and dist.cpu().tolist() == [T.shortest_distance(a, e, u, v) for a, e, (u, v) in recs]
+    vocab = {t: i for i, t in enumerate(O.SPECIAL)}
+    for k in range(70):
+        vocab[str(k)] = len(vocab)
+    vocab["shortest_distance"] = len(vocab)
+    max_len = int(rng.choice([600, 40, 4000]))
+    ep, _ = engine.ibtt_collate_epoch(gb, vocab, "shortest_path", max_len, 16)
+    qp = engine.query_positions(ep, vocab["<q>"]).cpu().tolist()
+    want = [T.first_token_pos(O.ibtt_ids(a, np.asarray([u for u, _ in e], dtype=np.int64), np.asarray([v for _, v in e], dtype=np.int64),
+                                         "shortest_path", vocab, max_len, q).tolist(), vocab["<q>"]) for a, e, q in recs]
+    ok = ok and qp == want
+    if not ok:
+        bad += 1
+    print(f"tasks  G={G:5d} kind={kind:8s} buckets={buckets} max_len={max_len:4d}: {'ok' if ok else 'MISMATCH'}")
+
+
 for r in range(rounds):
     zinc_round()
     gt_round()
     sent_round()
+    tasks_round()
 print("mismatching rounds:", bad)
 sys.exit(1 if bad else 0)
