@@ -863,6 +863,14 @@ def test_graph_labels_larger_graphs_vs_oracle(dev, N):
     cyc, dist = engine.graph_labels(csr, edge_off=gb.edge_off, distance=True)
     assert cyc.cpu().tolist() == [int(T.has_cycle_dfs(n, e)) for n, e, _ in recs]
     assert dist.cpu().tolist() == [T.shortest_distance(n, e, u, v) for n, e, (u, v) in recs]
+    # queries that are not nodes of their graph: distance -1 (INF), on both kernels; graphs without nodes / edges
+    import dataclasses
+    bad_q = dataclasses.replace(csr, query_u=csr.query_u.clone().fill_(-3), query_v=csr.query_v + 100000)
+    assert engine.graph_labels(bad_q, distance=True)[1].cpu().tolist() == [-1] * len(recs)
+    assert engine.graph_labels(dataclasses.replace(bad_q, adj64=None), distance=True)[1].cpu().tolist() == [-1] * len(recs)
+    empty = engine.build_csr(GraphBatch.from_lists([0, 1, 3], [[], [], []], queries=[(0, 0), (0, 0), (2, 2)]).to(dev))
+    c0, d0 = engine.graph_labels(empty, distance=True)
+    assert c0.cpu().tolist() == [0, 0, 0] and d0.cpu().tolist() == [-1, 0, 0]
     simple, _ = engine.graph_labels(csr)                                   # edge_off None: M = CSR entries / 2
     assert simple.cpu().tolist() == [int(T.has_cycle_dfs(n, sorted(set(e)))) for n, e, _ in recs]
 
