@@ -284,7 +284,7 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
           const int cnt = __popc(fm);                                  // == rem[cur]
           if (cnt > 0) {
             if (vc < 0) {                                              // cur joins the restart candidates
-              if (lane == 0) openb[cur >> 5] |= 1u << (cur & 31);
+              if (lane == 0) atomicOr(&openb[cur >> 5], 1u << (cur & 31));   // (other lanes update this map with atomics in the same step)
               ++nopen;
             }
             if (CSRG && ((fm >> lane) & 1u)) {
@@ -356,7 +356,7 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
             nopen -= closed;
             __syncwarp();
             if (rem[cur] > 0) {                                   // cur joins the restart candidates
-              if (lane == 0) openb[cur >> 5] |= 1u << (cur & 31);
+              if (lane == 0) atomicOr(&openb[cur >> 5], 1u << (cur & 31));   // (other lanes update this map with atomics in the same step)
               ++nopen;
             }
             int M = 0;

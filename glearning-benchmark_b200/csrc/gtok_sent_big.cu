@@ -251,7 +251,7 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
           cnt = __popc(fm);
           if (cnt > 0) {
             if (vc < 0) {                                               // cur joins the restart candidates
-              if (lane == 0) openb[cur >> 5] |= 1u << (cur & 31);
+              if (lane == 0) atomicOr(&openb[cur >> 5], 1u << (cur & 31));   // (other lanes update this map with atomics in the same step)
               ++nopen;
             }
             if ((fm >> lane) & 1u) {
@@ -343,7 +343,7 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
               len += 2 + M * per;
             }
             if (cnt > 0) {
-              if (lane == 0) openb[cur >> 5] |= 1u << (cur & 31);
+              if (lane == 0) atomicOr(&openb[cur >> 5], 1u << (cur & 31));   // (other lanes update this map with atomics in the same step)
               ++nopen;
             }
           } else {
