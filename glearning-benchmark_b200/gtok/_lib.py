@@ -100,6 +100,8 @@ PROTOTYPES = {
     "gtok_pad_mask": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp]),
     "gtok_batch_extents": (C.c_int, [vp, vp, i64, i64, vp, vp, vp]),
     "gtok_pad_mask_batched": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, vp]),
+    "gtok_csr_adjacency": (C.c_int, [C.POINTER(GraphBatchC), i32, i64, vp, vp, vp]),
+    "gtok_csr_fill": (C.c_int, [C.POINTER(GraphBatchC), i32, i64, vp, vp, i64, vp, vp, vp, vp, vp]),
     "gtok_find_token": (C.c_int, [vp, vp, vp, i64, i64, vp, i64, vp, vp]),
     "gtok_graph_labels": (C.c_int, [C.POINTER(CsrBatchC), vp, vp, vp, vp]),
     "gtok_er_sizes": (C.c_int, [C.POINTER(ErSpecC), i64, vp, vp, vp, vp, vp]),

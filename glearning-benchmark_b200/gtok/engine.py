@@ -468,13 +468,67 @@ class CsrBatch:
         return b
 
 
-def build_csr(batch: GraphBatch, balance_window: int = 0) -> CsrBatch:
-    """edge_index (any orientation, duplicates allowed) -> canonical undirected CSR.
-    One-off ingest per dataset (what to_undirected/coalesce does inside AutoGraph per
-    call); plain torch ops - plumbing, not the hot path.  The label of {u,v} is the
-    edge_attr of its FIRST directed entry in caller order (oracle: canonical_csr)."""
+def _finish_csr(batch: GraphBatch, rowptr, col_local, eattr, adj64, adj_words, balance_window: int) -> CsrBatch:
+    G = batch.num_graphs
+    dev = batch.device
+    n = batch.num_nodes()
+    nnz_g = (rowptr[batch.node_off[1:]] - rowptr[batch.node_off[:-1]]).to(torch.int64)
+    max_label = 0
+    if batch.x is not None and eattr is not None and batch.x.numel() and eattr.numel():
+        lo = min(int(batch.x.min()), int(eattr.min()))
+        hi = max(int(batch.x.max()), int(eattr.max()))
+        max_label = hi if lo >= 0 else 0
+    order = None
+    if adj64 is not None and G and balance_window > 1:
+        # one thread walks one graph: give the 32 lanes of a warp graphs of similar work, but only reorder
+        # inside windows of consecutive graphs - a global sort scatters a warp's reads and rows over the whole
+        # buffers and was measured 10-30 % SLOWER than natural order (DESIGN.md section 9)
+        w = torch.arange(G, device=dev) // int(balance_window)
+        order = torch.argsort(w * (1 << 40) + n * 4096 + nnz_g, stable=True).to(torch.int32)
+    return CsrBatch(batch.node_off, rowptr.to(torch.int32), col_local, eattr, batch.x, batch.query_u, batch.query_v,
+                    int(n.max()) if G else 1, int(nnz_g.max()) if G else 0, max_label, adj64, adj_words, order)
+
+
+def _build_csr_native(batch: GraphBatch, balance_window: int) -> CsrBatch:
+    """K7 (csrc/gtok_csr.cu): graphs of at most 256 nodes - adjacency bit rows by atomicOr, row pointers by popcount +
+    K0 scan, neighbour lists by bit enumeration, labels from the first column of every pair (atomicMin)."""
     dev = batch.device
     G = batch.num_graphs
+    Ntot = int(batch.node_off[-1]) if G else 0
+    max_nodes = int(batch.num_nodes().max()) if G else 1
+    W = 1 if max_nodes <= 64 else (2 if max_nodes <= 128 else 4)
+    bc = _batch_c(batch, max(1, max_nodes), 1)
+    adj64 = torch.empty(Ntot * W, dtype=torch.int64, device=dev)
+    degree = torch.empty(Ntot, dtype=torch.int32, device=dev)
+    check(lib.gtok_csr_adjacency(C.byref(bc), W, Ntot, _ptr(adj64), _ptr(degree), _stream()))
+    rowptr64 = scan_offsets(degree)
+    nnz = int(rowptr64[-1]) if Ntot else 0
+    rowptr = torch.empty(Ntot + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    labeled = batch.edge_attr is not None
+    eattr = torch.empty(nnz, dtype=torch.int32, device=dev) if labeled else None
+    ws = torch.empty(nnz, dtype=torch.int64, device=dev) if labeled else None
+    check(lib.gtok_csr_fill(C.byref(bc), W, Ntot, _ptr(adj64), _ptr(rowptr64), nnz, _ptr(rowptr), _ptr(col), _ptr(eattr),
+                            _ptr(ws), _stream()))
+    return _finish_csr(batch, rowptr, col, eattr, adj64, W, balance_window)
+
+
+def build_csr(batch: GraphBatch, balance_window: int = 0, native: Optional[bool] = None) -> CsrBatch:
+    """edge_index (any orientation, duplicates allowed) -> canonical undirected CSR (+ adjacency bit rows up to 256
+    nodes per graph).  One-off ingest per dataset (what to_undirected/coalesce does inside AutoGraph per call).  The
+    label of {u,v} is the edge_attr of its FIRST directed entry in caller order (oracle: canonical_csr).
+    Graphs of at most 256 nodes: library kernels (K7, `native`); larger graphs: a sort-based build with torch ops
+    (plumbing, not the hot path).  native=False forces the torch build (tests compare the two)."""
+    dev = batch.device
+    G = batch.num_graphs
+    max_nodes_ = int(batch.num_nodes().max()) if G else 1
+    if native is None:
+        native = max_nodes_ <= 256 and batch.node_off.is_cuda        # (host tensors: the torch build, used by CPU tests)
+    if native:
+        _require_cuda(batch.node_off, batch.src)
+        if max_nodes_ > 256:
+            raise ValueError("the native CSR build covers graphs of at most 256 nodes")
+        return _build_csr_native(batch, balance_window)
     E = batch.src.numel()
     n = batch.num_nodes()
     Ntot = int(batch.node_off[-1]) if G else 0
@@ -504,12 +558,6 @@ def build_csr(batch: GraphBatch, balance_window: int = 0) -> CsrBatch:
     gnode = torch.repeat_interleave(torch.arange(G, device=dev), n)
     col_local = (cols - batch.node_off[gnode[rows]]).to(torch.int32)
     eattr = None if attr is None else torch.cat([attr, attr])[o2].to(torch.int32)
-    nnz_g = rowptr[batch.node_off[1:]] - rowptr[batch.node_off[:-1]]
-    max_label = 0
-    if batch.x is not None and eattr is not None and batch.x.numel() and eattr.numel():
-        lo = min(int(batch.x.min()), int(eattr.min()))
-        hi = max(int(batch.x.max()), int(eattr.max()))
-        max_label = hi if lo >= 0 else 0
     max_nodes = int(n.max()) if G else 1
     adj64, adj_words = None, 1
     if max_nodes <= 256:
@@ -518,15 +566,7 @@ def build_csr(batch: GraphBatch, balance_window: int = 0) -> CsrBatch:
         cl = col_local.to(torch.int64)
         adj64 = torch.zeros(Ntot * adj_words, dtype=torch.int64, device=dev)
         adj64.scatter_add_(0, rows * adj_words + (cl >> 6), torch.ones_like(rows) << (cl & 63))
-    order = None
-    if adj64 is not None and G and balance_window > 1:
-        # one thread walks one graph: give the 32 lanes of a warp graphs of similar work, but only reorder
-        # inside windows of consecutive graphs - a global sort scatters a warp's reads and rows over the whole
-        # buffers and was measured 10-30 % SLOWER than natural order (DESIGN.md section 9)
-        w = torch.arange(G, device=dev) // int(balance_window)
-        order = torch.argsort(w * (1 << 40) + n * 4096 + nnz_g, stable=True).to(torch.int32)
-    return CsrBatch(batch.node_off, rowptr.to(torch.int32), col_local, eattr, batch.x, batch.query_u, batch.query_v,
-                    max_nodes, int(nnz_g.max()) if G else 0, max_label, adj64, adj_words, order)
+    return _finish_csr(batch, rowptr, col_local, eattr, adj64, adj_words, balance_window)
 
 
 def _csr_c(csr: CsrBatch) -> _lib.CsrBatchC:

@@ -272,6 +272,20 @@ GTOK_API int gtok_zinc_collate_packed(const GtokPackedMolBatch* batch, const Gto
                                       int64_t pad_id, int32_t* len_out, int32_t* lmax_out, int64_t* xoff_out, int64_t* X,
                                       uint8_t* attn, int64_t x_capacity, void* ws, size_t ws_bytes, void* stream);
 
+/* K7   ingest for K3: the canonical undirected CSR of GtokCsrBatch (+ its adjacency bit rows) from the caller's
+ *      edge_index columns, graphs of at most 64 * adj_words <= 256 nodes - what to_undirected + coalesce do inside
+ *      AutoGraph's tokenizer on every call (call site trainer/train_agtt.py:250), once per dataset here.
+ *      gtok_csr_adjacency zeroes and fills adj64 [total_nodes * adj_words] (self loops dropped, repeats collapse) and
+ *      writes the node degrees; the caller scans them into rowptr64 [total_nodes + 1] (gtok_scan_offsets) and
+ *      gtok_csr_fill writes rowptr_out int32 [total_nodes + 1], col_out [nnz] (rows ascending) and, when eattr_out is
+ *      given, the label of every entry = edge_attr of the FIRST column of its pair in caller order, either direction
+ *      (first_col_ws: nnz * 8 bytes of scratch).  batch->max_nodes must be set. */
+GTOK_API int gtok_csr_adjacency(const GtokGraphBatch* batch, int32_t adj_words, int64_t total_nodes, uint64_t* adj64,
+                                int32_t* degree_out, void* stream);
+GTOK_API int gtok_csr_fill(const GtokGraphBatch* batch, int32_t adj_words, int64_t total_nodes, const uint64_t* adj64,
+                           const int64_t* rowptr64, int64_t nnz, int32_t* rowptr_out, int32_t* col_out,
+                           int32_t* eattr_out, uint64_t* first_col_ws, void* stream);
+
 /* K3   Graph2TrailTokenizer.__call__ (external AutoGraph; spec in
  *      oracle/sent_oracle.py) + remap_zinc_tokens + query append
  *      (train_agtt.py:171-273).  Row g is written at tok_out[g*stride ..], its

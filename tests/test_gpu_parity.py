@@ -1104,3 +1104,46 @@ def test_generator_families_match_oracle(dev, kind):
             engine.generate_er(4, kind="ba", buckets=((10, 80),), device=dev)                                   # > 64 nodes
     with pytest.raises(ValueError):
         engine.generate_er(4, kind="sfn", device=dev)
+
+
+@pytest.mark.parametrize("nmax", [1, 40, 64, 65, 128, 200, 256])
+def test_native_csr_build_equals_sort_based_build(dev, nmax):
+    """K7: the library's CSR builder (bit rows by atomicOr, popcount row pointers, first-column labels by atomicMin)
+    produces exactly the canonical CSR of the sort-based torch build and of the oracle, with repeated columns in
+    both directions, self loops, isolated nodes, empty graphs and conflicting labels on repeats."""
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    rng = np.random.default_rng(100 + nmax)
+    mols = []
+    for i in range(90):
+        n = int(rng.integers(0 if i % 17 == 0 else 1, nmax + 1))
+        m = 0 if (n < 1 or i % 11 == 0) else int(rng.integers(0, 6 * n + 1))
+        s_ = rng.integers(0, max(n, 1), m)
+        d_ = rng.integers(0, max(n, 1), m)
+        if m > 4:                                            # repeats in both directions with different labels
+            s_[1], d_[1] = d_[0], s_[0]
+            s_[3], d_[3] = s_[2], d_[2]
+        mols.append({"n": n, "src": s_.tolist(), "dst": d_.tolist(), "x": rng.integers(0, 12, n).tolist(),
+                     "attr": rng.integers(1, 9, m).tolist()})
+    for labeled in (True, False):
+        gb = GraphBatch.from_lists([m["n"] for m in mols], [list(zip(m["src"], m["dst"])) for m in mols],
+                                   x_lists=[m["x"] for m in mols] if labeled else None,
+                                   attr_lists=[m["attr"] for m in mols] if labeled else None).to(dev)
+        a = engine.build_csr(gb, native=True)
+        b = engine.build_csr(gb, native=False)
+        assert a.adj_words == b.adj_words == (1 if max(1, max(m["n"] for m in mols)) <= 64 else (2 if max(m["n"] for m in mols) <= 128 else 4))
+        for f in ("rowptr", "col", "adj64"):
+            assert torch.equal(getattr(a, f), getattr(b, f)), (nmax, labeled, f)
+        assert (a.eattr is None) == (not labeled) and (a.eattr is None or torch.equal(a.eattr, b.eattr))
+        assert (a.max_nodes, a.max_nnz, a.max_label) == (b.max_nodes, b.max_nnz, b.max_label)
+        rp, col = a.rowptr.cpu().numpy(), a.col.cpu().numpy()
+        ea = None if a.eattr is None else a.eattr.cpu().numpy()
+        n0 = 0
+        for m in mols[:25]:
+            wrp, wcol, wea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"] if labeled else None)
+            lo, hi = rp[n0], rp[n0 + m["n"]]
+            assert (rp[n0:n0 + m["n"] + 1] - lo).tolist() == wrp.tolist() and col[lo:hi].tolist() == wcol.tolist()
+            if labeled:
+                assert ea[lo:hi].tolist() == wea.tolist()
+            n0 += m["n"]
+    assert engine.build_csr(GraphBatch.from_lists([], []).to(dev)).num_graphs == 0
