@@ -135,6 +135,10 @@ def sent_round():
                                queries=[(int(rng.integers(0, m["n"])), int(rng.integers(0, m["n"]))) for m in mols]).to(dev)
     csr = engine.build_csr(gb, balance_window=int(rng.choice([0, 16])))
     mx = max(m["n"] for m in mols)
+    csr_ok = True
+    if mx <= 256:                                               # library CSR builder == sort-based torch build
+        ref_csr = engine.build_csr(gb, native=False)
+        csr_ok = all(torch.equal(getattr(csr, f), getattr(ref_csr, f)) for f in ("rowptr", "col", "eattr", "adj64"))
     max_length = int(rng.choice([1, 2, 17, 200, 30000]))
     remap, append = bool(labeled and rng.random() < 0.5), bool(rng.random() < 0.4)
     seed = int(rng.integers(0, 2 ** 40))
@@ -144,7 +148,7 @@ def sent_round():
     tok, ln = engine.tokenize_sent(csr, cfg, seed=seed, graph_id_base=5, use_workspace=use_ws)
     tok, ln = tok.cpu(), ln.cpu().tolist()
     ocfg = S.SentConfig(6, 6 + mx, 6 + mx + 12, max_length, labeled)
-    ok = True
+    ok = csr_ok
     for g, m in enumerate(mols):
         rp, col, ea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"])
         w = S.sent_tokenize(m["n"], rp, col, ocfg, S.PhiloxWords(seed, 5 + g), x=m["x"], eattr=ea)
