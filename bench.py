@@ -395,51 +395,68 @@ def run_gpu(args):
         assert torch.equal(alt.X[:padded_cells], pipe.X[:padded_cells]) and torch.equal(alt.attn[:padded_cells], pipe.attn[:padded_cells])
         del alt
 
-    # ---- end to end through the public call: pinned host graphs -> device batches + host metadata.
-    # Host arrays travel in the compact wire format (PackedGraphBatch: counts + narrowest lossless dtypes,
-    # widened on the device by gtok_widen_i32 / gtok_counts_to_offsets); the plain int32 layout is timed too.
-    from gtok.batch import PackedGraphBatch
+    # ---- end to end through the public call, starting from what the REFERENCE holds: pinned int64 PyG tensors
+    # (edge_index [2, E], x, edge_attr, slices; zinc_dataset_autograph.py:51-73).  Every conversion is inside the
+    # timed region and runs on the device (gtok_pyg_pack_mol); nothing is packed, narrowed or checked on the host.
+    from gtok.batch import PackedGraphBatch, PygStore
     e2e_steps = max(3, min(args.steps, 10))
-    # 16-bit columns + byte atoms; the synthetic molecules are a canonical undirected PyG edge_index (both directions,
-    # sorted, symmetric bond types - verified by from_batch), so only the src < dst half of the columns travels
-    packed = PackedGraphBatch.from_batch(host_batch, fuse_columns=True, drop_mirror_columns=True).pin_memory()
-    packed_full = PackedGraphBatch.from_batch(host_batch, fuse_columns=True).pin_memory()  # every column (any column list)
-    packed_arrays = PackedGraphBatch.from_batch(host_batch).pin_memory()                  # one narrow array per field
+    store = PygStore.from_batch(host_batch).pin_memory()
 
-    def time_e2e(src):
-        # every step uploads its inputs from pinned host memory; with the wire format the NEXT step's upload is
-        # started on a copy stream while this step's kernels run (a stream of shards, double buffered)
-        kw = {"prefetch": src} if isinstance(src, PackedGraphBatch) else {}
+    def time_loop(fn):
         for _ in range(2):
-            pipe.run(src, **kw)
+            fn()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for _ in range(e2e_steps):
-            r = pipe.run(src, **kw)
+            r = fn()
         f1.record()
         barrier()
         return f0.elapsed_time(f1), r
 
-    e2e_i32_ms, res = time_e2e(host_batch)
-    assert int(res.host_xoff[-1]) == padded_cells and int(res.host_lengths.sum()) == total_tokens
-    e2e_arr_ms, res = time_e2e(packed_arrays)
-    assert int(res.host_xoff[-1]) == padded_cells and int(res.host_lengths.sum()) == total_tokens
-    e2e_full_ms, res = time_e2e(packed_full)
-    assert int(res.host_xoff[-1]) == padded_cells and int(res.host_lengths.sum()) == total_tokens
-    assert torch.equal(res.padded.X[:padded_cells], X_ref) and torch.equal(res.padded.attn[:padded_cells], A_ref)
-    e2e_ms, res = time_e2e(packed)
-    assert int(res.host_xoff[-1]) == padded_cells and int(res.host_lengths.sum()) == total_tokens
-    assert torch.equal(res.padded.X[:padded_cells], X_ref) and torch.equal(res.padded.attn[:padded_cells], A_ref)
-    h2d_packed = packed.nbytes()
+    def same_output(r, full=True):
+        assert int(r.host_xoff[-1]) == padded_cells and int(r.host_lengths.sum()) == total_tokens
+        if full:
+            assert torch.equal(r.padded.X[:padded_cells], X_ref) and torch.equal(r.padded.attn[:padded_cells], A_ref)
+
+    e2e_ms, res = time_loop(lambda: pipe.run_pyg(store, chunks=args.e2e_chunks))
+    same_output(res)
+    h2d_pyg = store.nbytes()
+
+    # Pre-packed host layouts (a one-off ingest cost per dataset, measured here as pack_ms and NOT part of their
+    # timed loops): the resident int32 layout, one narrow array per field, 16-bit columns, and the de-mirrored half.
+    def time_prepacked(src):
+        kw = {"prefetch": src} if isinstance(src, PackedGraphBatch) else {}
+        return time_loop(lambda: pipe.run(src, **kw))
+
+    pre = {}
+    variants = (("int32_layout", lambda: host_batch, False),
+                ("narrow_arrays", lambda: PackedGraphBatch.from_batch(host_batch).pin_memory(), False),
+                ("col16", lambda: PackedGraphBatch.from_batch(host_batch, fuse_columns=True).pin_memory(), True),
+                ("col16_demirrored", lambda: PackedGraphBatch.from_batch(host_batch, fuse_columns=True,
+                                                                          drop_mirror_columns=True).pin_memory(), True))
+    for name, make, full in variants:
+        if name.startswith("col16") and pipe.mode != "collate":
+            continue                                      # 16-bit columns are consumed by the fused collate kernel only
+        t0 = time.perf_counter()
+        src = make()
+        pack_ms = 0.0 if name == "int32_layout" else (time.perf_counter() - t0) * 1e3
+        ms_v, r = time_prepacked(src)
+        same_output(r, full)
+        nb_ = pipe.h2d_bytes() if name == "int32_layout" else src.nbytes()
+        pre[name] = (ms_v, nb_, pack_ms)
+        del src
 
     extras = None
     if world == 1 and not args.no_extras:
         extras = run_extras(dev, args.graphs, peak_gbs())
-    t = torch.tensor([ms, e2e_ms, e2e_i32_ms, e2e_arr_ms, e2e_full_ms], dtype=torch.float64, device=dev)
+    names = list(pre)
+    t = torch.tensor([ms, e2e_ms] + [pre[n][0] for n in names], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, e2e_i32_ms, e2e_arr_ms, e2e_full_ms = (float(v) for v in t)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    for i, n in enumerate(names):
+        pre[n] = (float(t[2 + i]),) + pre[n][1:]
     # the one optional collective of the design: per-rank (graphs, tokens) -> global offsets
     from gtok import shard
     info = shard.global_offsets(G, total_tokens, device=dev)
@@ -486,25 +503,21 @@ def run_gpu(args):
                              ((pipe.h2d_bytes() + 8 * total_tokens + 9 * padded_cells) / 1e9),
                        "parallelism": f"graphs sharded by index over {world} GPU(s), no data-path collective"},
             "e2e": {"value": graphs_all / (e2e_ms / 1e3 / e2e_steps), "unit": UNIT,
-                    "h2d_bytes_per_step": h2d_packed, "d2h_bytes_per_step": pipe.d2h_bytes(),
+                    "h2d_bytes_per_step": h2d_pyg, "d2h_bytes_per_step": pipe.d2h_bytes() + 4,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "note": "pinned host graph arrays in the compact layout (per-graph counts, one 16-bit word per edge_index "
-                            "column = src | dst << 6 | edge_attr << 12, one byte per atom; lossless for molecule-sized graphs) "
-                            "copied H2D every step (double buffered: step i+1's copy overlaps step i's kernels) and consumed "
-                            "directly by the fused tokenize+collate kernel; row lengths + batch extents read back; X / attn "
-                            "checked byte-identical to the device-resident run.  " +
-                            ("The molecules are a canonical undirected PyG edge_index (both directions, sorted by (src, dst), "
-                             "symmetric bond types - verified on the host when the batch is packed), so only the src < dst "
-                             "half of the columns travels and the kernel skips the dedupe; all_columns is the same call with "
-                             "every column sent" if packed.unique_columns else "every edge_index column is sent"),
-                    "wire": "col16 src<dst half" if packed.unique_columns else "col16",
-                    "all_columns": {"value": graphs_all / (e2e_full_ms / 1e3 / e2e_steps), "ms_per_step": e2e_full_ms / e2e_steps,
-                                    "h2d_bytes_per_step": packed_full.nbytes()},
-                    "narrow_arrays": {"value": graphs_all / (e2e_arr_ms / 1e3 / e2e_steps), "ms_per_step": e2e_arr_ms / e2e_steps,
-                                      "h2d_bytes_per_step": packed_arrays.nbytes(),
-                                      "note": "one uint8/uint16 array per field, widened to int32 on the device"},
-                    "int32_layout": {"value": graphs_all / (e2e_i32_ms / 1e3 / e2e_steps), "ms_per_step": e2e_i32_ms / e2e_steps,
-                                     "h2d_bytes_per_step": pipe.h2d_bytes()}},
+                    "h2d_GBps_per_gpu": h2d_pyg / (e2e_ms / 1e3 / e2e_steps) / 1e9,
+                    "note": "ZincIbttPipeline.run_pyg: starts from what the reference holds - pinned int64 PyG tensors "
+                            "(edge_index [2, E], x, edge_attr, slices; 1.4 KB per molecule) - copied H2D every step in "
+                            f"{args.e2e_chunks} chunks; each chunk is narrowed on the device as it lands (gtok_pyg_pack_mol), "
+                            "the slices are used as offsets, then the fused tokenize+collate kernel runs; no host-side "
+                            "packing / checking anywhere.  Row lengths, batch extents and the range-check status are read "
+                            "back; the padded X / attn batches (1.9 GB) STAY ON THE DEVICE for the consumer (the trainer's "
+                            "X.to(device) becomes a no-op) and are checked byte-identical to the device-resident run.  "
+                            "PCIe-bound: the step is the H2D copy of the int64 tensors.",
+                    "prepacked": {n: {"value": graphs_all / (v[0] / 1e3 / e2e_steps), "ms_per_step": v[0] / e2e_steps,
+                                      "h2d_bytes_per_step": v[1], "pack_ms_untimed": v[2]} for n, v in pre.items()},
+                    "prepacked_note": "same public call fed with host arrays packed ONCE per dataset before the timed loop "
+                                      "(pack_ms_untimed = that host-side cost on this box, per shard); not the headline"},
             "gpu_launches": pipe.kernel_launches_per_pass * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                          "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
@@ -552,6 +565,7 @@ def main():
     ap.add_argument("--cpu-graphs-per-core", type=int, default=40000,
                     help="CPU arm sample: graphs per host core per step (default: ~25 core-seconds of reference work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="pieces the int64 PyG tensors travel in (copy / narrow overlap)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (graph-token IBTT, SENT)")
     ap.add_argument("--zinc-fused", type=int, default=-1, help="-1 auto, 0 three-kernel path, 1 fused single pass")
     ap.add_argument("--zinc-mode", default="auto", choices=["auto", "collate", "ragged"],

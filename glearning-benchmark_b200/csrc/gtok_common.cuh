@@ -115,6 +115,47 @@ __device__ __forceinline__ void warp_pad_row(int len, int Lmax, int64_t pad, int
   if (tail + lane < Lmax && lane < 16) arow[tail + lane] = (uint8_t)(tail + lane < len);
 }
 
+// Two consecutive rows of a padded batch are ONE contiguous run of 2*Lmax mask bytes: byte p is (p < len0) in the
+// first row, (p - Lmax < len1) in the second.  Same 16-byte streaming stores as warp_pad_row's mask half.
+__device__ __forceinline__ void warp_mask_run2(int len0, int len1, int Lmax, uint8_t* __restrict__ arow) {
+  const int lane = lane_id();
+  const int total = 2 * Lmax;
+  auto val = [&](int p) -> uint8_t { return (uint8_t)(p < Lmax ? (p < len0) : (p - Lmax < len1)); };
+  int mh = (int)((16 - (reinterpret_cast<uintptr_t>(arow) & 15)) & 15);
+  if (mh > total) mh = total;
+  if (lane < mh) arow[lane] = val(lane);
+  const int nvec = (total - mh) >> 4;
+  for (int q = lane; q < nvec; q += kWarp) {
+    const int p = mh + 16 * q;
+    const int a = len0 - p, b = Lmax + len1 - p, c = Lmax - p;       // ones below a, and in [c, b)
+    const unsigned long long lo = mask8(a) | (mask8(b) & ~mask8(c));
+    const unsigned long long hi = mask8(a - 8) | (mask8(b - 8) & ~mask8(c - 8));
+    __stcs(reinterpret_cast<ulonglong2*>(arow + p), make_ulonglong2(lo, hi));
+  }
+  const int tail = mh + 16 * nvec;
+  if (tail + lane < total && lane < 16) arow[tail + lane] = val(tail + lane);
+}
+
+// ---- bulk asynchronous copies (TMA engine, 1-D): shared memory -> global, tracked by bulk async-groups ---------------
+// The copy is issued by ONE thread and moves a whole 16-byte aligned run without touching a register; the issuing
+// thread's generic-proxy writes (and, after a __syncwarp / barrier, everybody else's) must be made visible to the async
+// proxy with fence_proxy_async_smem() before the copy is issued.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {   // at most N groups still READING their shared-memory source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {        // at most N groups not yet complete (writes performed)
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- decoupled look-back (single-pass chained scan) -------------------------
 // One 64-bit word per tile carries {flag (top 2 bits) | value (62 bits)}, so flag
 // and value can never be observed out of order; relaxed gpu-scope accesses suffice.

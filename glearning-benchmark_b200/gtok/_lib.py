@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libgtok.so")
 
 GTOK_OK, GTOK_EINVAL, GTOK_ECUDA, GTOK_EUNSUPPORTED, GTOK_EWORKSPACE = 0, -1, -2, -3, -4
 TASK_CYCLE_CHECK, TASK_SHORTEST_PATH = 0, 1
+PYG_BAD_NODE_ID, PYG_BAD_EDGE_ATTR, PYG_BAD_NODE_TYPE, PYG_BAD_RANGE = 1, 2, 4, 8
 
 i32, i64, u64, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -76,6 +77,8 @@ PROTOTYPES = {
     "gtok_device_sm_count": (C.c_int, []),
     "gtok_widen_i32": (C.c_int, [vp, i32, i64, vp, vp]),
     "gtok_counts_to_offsets": (C.c_int, [vp, i32, i64, vp, vp, vp, C.c_size_t, vp]),
+    "gtok_pyg_pack_mol": (C.c_int, [vp, vp, vp, i64, vp, i64, vp, vp, vp, vp]),
+    "gtok_pyg_narrow": (C.c_int, [vp, i64, vp, vp, vp]),
     "gtok_text_scan": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp, vp]),
     "gtok_text_edges": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]),
     "gtok_vocab_histogram": (C.c_int, [C.POINTER(GraphBatchC), i32, i32, vp, vp, vp]),

@@ -334,3 +334,52 @@ class PackedGraphBatch:
     def nbytes(self) -> int:
         return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in self.ARRAYS
                    if getattr(self, n) is not None)
+
+
+@dataclass
+class PygStore:
+    """The reference's OWN host storage of a molecule dataset: what a PyG InMemoryDataset keeps (`ds._data`, `ds.slices`)
+    and what ZINCDatasetForAutoGraph / ZINCTokenizationDataset read per item (zinc_dataset_autograph.py:51-73,
+    zinc_dataset_indexbase.py:63-70) - int64 tensors, LOCAL node ids, the slices are the per-graph boundaries.
+    ZincIbttPipeline.run_pyg() takes this object as it is: no host-side packing, narrowing or checking."""
+    edge_index: torch.Tensor       # int64 [2, E_total]
+    x: torch.Tensor                # int64 [N_total] (a [N_total, 1] tensor is viewed flat)
+    edge_attr: Optional[torch.Tensor]   # int64 [E_total]
+    node_slices: torch.Tensor      # int64 [G+1]
+    edge_slices: torch.Tensor      # int64 [G+1]
+
+    @property
+    def num_graphs(self) -> int:
+        return int(self.node_slices.numel()) - 1
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in
+                   (self.edge_index, self.x, self.edge_attr, self.node_slices, self.edge_slices) if t is not None)
+
+    def pin_memory(self) -> "PygStore":
+        p = lambda t: None if t is None else t.pin_memory()
+        return PygStore(p(self.edge_index), p(self.x), p(self.edge_attr), p(self.node_slices), p(self.edge_slices))
+
+    @staticmethod
+    def from_dataset(ds) -> "PygStore":
+        """The storage of a PyG InMemoryDataset, untouched (views, no copies)."""
+        store = getattr(ds, "_data", None)
+        if store is None:
+            store = getattr(ds, "data", None)
+        slices = getattr(ds, "slices", None)
+        if store is None or not isinstance(slices, dict):
+            raise TypeError("an InMemoryDataset (with ._data / .slices) is expected")
+        if getattr(ds, "_indices", None) is not None:
+            raise ValueError("the dataset is an index view; materialise it (ds.copy()) or use GraphBatch.from_collated")
+        x = store.x
+        ea = getattr(store, "edge_attr", None)
+        return PygStore(store.edge_index.contiguous(), x.reshape(-1) if x.dim() == 2 and x.shape[1] == 1 else x,
+                        None if ea is None else ea.reshape(-1), torch.as_tensor(slices["x"], dtype=torch.int64),
+                        torch.as_tensor(slices["edge_index"], dtype=torch.int64))
+
+    @staticmethod
+    def from_batch(b: GraphBatch) -> "PygStore":
+        """The int64 tensors PyG would hold for the graphs of `b` (synthetic benchmarks / tests)."""
+        ei = torch.stack([b.src.to(torch.int64), b.dst.to(torch.int64)]).contiguous()
+        return PygStore(ei, b.x.to(torch.int64), None if b.edge_attr is None else b.edge_attr.to(torch.int64),
+                        b.node_off.to(torch.int64).clone(), b.edge_off.to(torch.int64).clone())

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib, engine
 from ._lib import lib, check
-from .batch import GraphBatch, PackedGraphBatch
+from .batch import GraphBatch, PackedGraphBatch, PygStore
 from .engine import _ptr, _stream
 
 
@@ -69,6 +69,16 @@ class _PipelineBase:
         self.h_xoff = torch.empty(self.nb + 1, dtype=i64).pin_memory()
         self.kernel_launches_per_pass = 6
         self.timers = None      # optional list to collect (name, start_event, end_event)
+        self._n_cap, self._e_cap = int(n_total), int(e_total)
+
+    def _release_wire(self) -> None:
+        """Called after the kernels that read a wire slot were enqueued: the slot may be refilled once they ran."""
+        slot = getattr(self, "_wire_last", None)
+        if slot is not None:
+            evt = torch.cuda.Event()
+            evt.record(torch.cuda.current_stream())
+            self._wire_free[slot] = evt
+            self._wire_last = None
 
     # -- helpers ---------------------------------------------------------
     def h2d_bytes(self) -> int:
@@ -89,6 +99,7 @@ class _PipelineBase:
         key = tuple((n, getattr(host, n).dtype, getattr(host, n).numel()) for n in host.ARRAYS if getattr(host, n) is not None)
         if getattr(self, "_wire", None) is None:
             self._wire, self._wire_key, self._wire_evt, self._wire_src = [None, None], [None, None], [None, None], [None, None]
+            self._wire_free, self._wire_last = [None, None], None
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._cnt_tmp = torch.empty(max(1, self.G), dtype=torch.int32, device=self.device)
         if self._wire_key[slot] != key:
@@ -113,16 +124,29 @@ class _PipelineBase:
         staging slot right away, so its PCIe time hides behind this call's kernels; a later call with that object
         finds it already on the device."""
         main = torch.cuda.current_stream()
+        for h in (host, prefetch):
+            if h is None:
+                continue
+            if h.num_graphs != self.G:
+                raise ValueError(f"this pipeline was built for shards of {self.G} graphs, got {h.num_graphs}")
+            if h.num_nodes_total > self._n_cap or h.num_entries_total > self._e_cap:
+                raise ValueError(f"shard of {h.num_nodes_total} nodes / {h.num_entries_total} entries exceeds the pipeline's "
+                                 f"capacity ({self._n_cap} / {self._e_cap}); raise node_capacity / entry_capacity")
         self._wire_slot(host, 0)
         slot = next((s_ for s_ in (0, 1) if self._wire_src[s_] is host), None)
         if slot is None:                                  # not prefetched: copy now, on the main stream
             slot = 0 if self._wire_src[0] is None or self._wire_src[1] is not None else 1
+            if self._wire_evt[slot] is not None:          # an unconsumed prefetch into this slot may still be in flight
+                main.wait_event(self._wire_evt[slot])
             self._copy_packed(host, slot, main)
         if prefetch is not None:
             other = 1 - slot
-            # the other slot's last reader (the previous call's widen kernels) finished before that call returned
+            # the other slot's last readers (an earlier call's widen / collate kernels) were enqueued on the main stream
+            if self._wire_free[other] is not None:
+                self._copy_stream.wait_event(self._wire_free[other])
             self._copy_packed(prefetch, other, self._copy_stream)
         main.wait_event(self._wire_evt[slot])
+        self._wire_last = slot
         self._h2d_packed = host.nbytes()
         w = self._wire[slot]
         st = _stream()
@@ -280,9 +304,113 @@ class ZincIbttPipeline(_PipelineBase):
             self._packed_dev = None
             self.upload(host_batch)
         self.launch()
+        self._release_wire()
         self._packed_dev = None                  # launch() on resident int32 arrays again unless the next run() is packed
         self.download()
         torch.cuda.current_stream().synchronize()
+        return self._result(True)
+
+    # -- end to end from the reference's own storage ------------------------------------------------------------
+    def _pyg_buffers(self):
+        if getattr(self, "_pyg", None) is None:
+            d, i64 = self.device, torch.int64
+            e, n = self._e_cap + 16, self._n_cap + 16
+            self._pyg = {"src64": torch.empty(e, dtype=i64, device=d), "dst64": torch.empty(e, dtype=i64, device=d),
+                         "attr64": torch.empty(e, dtype=i64, device=d), "x64": torch.empty(n, dtype=i64, device=d),
+                         "col16": torch.empty(e, dtype=torch.int16, device=d), "x8": torch.empty(n, dtype=torch.uint8, device=d),
+                         "node_off": torch.empty(self.G + 1, dtype=i64, device=d),
+                         "edge_off": torch.empty(self.G + 1, dtype=i64, device=d),
+                         "status": torch.zeros(1, dtype=torch.int32, device=d)}
+            self._pyg_hstatus = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._pyg_free = None
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+        return self._pyg
+
+    def run_pyg(self, store: PygStore, chunks: int = 8) -> EpochResult:
+        """Public end-to-end call from the REFERENCE's storage: pinned int64 PyG tensors (`PygStore`: edge_index [2, E],
+        x, edge_attr, slices - zinc_dataset_autograph.py:51-73) -> device batches + host row metadata, every conversion
+        inside the call and on the device.  The int64 arrays cross PCIe as they are, in `chunks` pieces on a copy
+        stream; each piece is narrowed as soon as it has landed (gtok_pyg_pack_mol: 16-bit columns + byte atoms, or
+        gtok_pyg_narrow into the int32 layout when a value does not fit / the pipeline is not in collate mode); the
+        slices are the offsets.  Stands in for `[ds[i] for i in range(len(ds))] -> TokenDataset -> DataLoader(collate)`
+        (train_ibtt.py:231-233, :395-402) on the dataset object the reference already holds."""
+        if store.num_graphs != self.G:
+            raise ValueError(f"this pipeline was built for shards of {self.G} graphs, got {store.num_graphs}")
+        E, N = int(store.edge_index.shape[1]), int(store.x.numel())
+        if E > self._e_cap or N > self._n_cap:
+            raise ValueError(f"store of {N} nodes / {E} entries exceeds the pipeline's capacity ({self._n_cap} / {self._e_cap})")
+        w = self._pyg_buffers()
+        main, cs = torch.cuda.current_stream(), self._copy_stream
+        packed = self.mode == "collate"
+        has_attr = store.edge_attr is not None
+        w["status"].zero_()
+        if self._pyg_free is not None:
+            cs.wait_event(self._pyg_free)                 # the previous call's kernels have drained the staging arrays
+        cs.wait_stream(main)
+        with torch.cuda.stream(cs):
+            w["node_off"].copy_(store.node_slices, non_blocking=True)
+            w["edge_off"].copy_(store.edge_slices, non_blocking=True)
+        if not packed:
+            i32 = getattr(self, "_pyg_i32", None)
+            if i32 is None:
+                i32 = self._pyg_i32 = {k: torch.empty(self._e_cap + 16 if k != "x" else self._n_cap + 16, dtype=torch.int32,
+                                                       device=self.device) for k in ("src", "dst", "edge_attr", "x")}
+        st = _stream()
+        nch = max(1, int(chunks))
+        cut = lambda total, c: min(total, ((total * c // nch) + 15) & ~15)
+        x_flat = store.x.reshape(-1)
+        for c in range(nch):
+            e0, e1, n0, n1 = cut(E, c), cut(E, c + 1), cut(N, c), cut(N, c + 1)
+            if c == nch - 1:
+                e1, n1 = E, N
+            with torch.cuda.stream(cs):
+                if e1 > e0:
+                    w["src64"][e0:e1].copy_(store.edge_index[0, e0:e1], non_blocking=True)
+                    w["dst64"][e0:e1].copy_(store.edge_index[1, e0:e1], non_blocking=True)
+                    if has_attr:
+                        w["attr64"][e0:e1].copy_(store.edge_attr[e0:e1], non_blocking=True)
+                if n1 > n0:
+                    w["x64"][n0:n1].copy_(x_flat[n0:n1], non_blocking=True)
+                evt = torch.cuda.Event()
+                evt.record(cs)
+            main.wait_event(evt)
+            at = lambda t, o: t.data_ptr() + o * t.element_size()
+            if packed:
+                check(lib.gtok_pyg_pack_mol(at(w["src64"], e0), at(w["dst64"], e0), at(w["attr64"], e0) if has_attr else None,
+                                            e1 - e0, at(w["x64"], n0), n1 - n0, at(w["col16"], e0), at(w["x8"], n0),
+                                            _ptr(w["status"]), st))
+            else:
+                for k64, k32, a, b in (("src64", "src", e0, e1), ("dst64", "dst", e0, e1), ("x64", "x", n0, n1)) + \
+                        ((("attr64", "edge_attr", e0, e1),) if has_attr else ()):
+                    check(lib.gtok_pyg_narrow(at(w[k64], a), b - a, at(i32[k32], a), _ptr(w["status"]), st))
+        self._h2d_pyg = store.nbytes()
+        if packed:
+            self._packed_dev = (w["col16"], w["x8"], max(0, self.max_nodes - 1), False, w["edge_off"])
+            keep = self.dev_in["node_off"]
+            self.dev_in["node_off"] = w["node_off"]
+            self.launch()
+            self.dev_in["node_off"] = keep
+            self._packed_dev = None
+        else:
+            keep = dict(self.dev_in)
+            self.dev_in.update({"node_off": w["node_off"], "edge_off": w["edge_off"], "src": i32["src"][:E], "dst": i32["dst"][:E],
+                                "x": i32["x"][:N], "edge_attr": i32["edge_attr"][:E] if has_attr else None})
+            self.launch()
+            self.dev_in = keep
+        self._pyg_free = torch.cuda.Event()
+        self._pyg_free.record(main)
+        self.download()
+        self._pyg_hstatus.copy_(w["status"], non_blocking=True)
+        main.synchronize()
+        flags = int(self._pyg_hstatus[0])
+        if flags:
+            what = [n for b, n in ((_lib.PYG_BAD_NODE_ID, "a local node id outside 0..63"),
+                                   (_lib.PYG_BAD_EDGE_ATTR, "an edge_attr outside 0..15"),
+                                   (_lib.PYG_BAD_NODE_TYPE, "an atom type outside 0..255"),
+                                   (_lib.PYG_BAD_RANGE, "a value outside int32")) if flags & b]
+            raise ValueError("run_pyg: the store holds " + ", ".join(what) + "; build the pipeline with mode='ragged' "
+                             "(int32 layout) for graphs that are not molecule sized")
         return self._result(True)
 
     def algorithmic_bytes(self, total_tokens: int, padded_cells: int) -> Dict[str, int]:
@@ -353,6 +481,7 @@ class GraphTokenIbttPipeline(_PipelineBase):
         else:
             self.upload(host_batch)
         self.launch()
+        self._release_wire()
         self.download()
         torch.cuda.current_stream().synchronize()
         return self._result(True)

@@ -163,6 +163,25 @@ GTOK_API int gtok_widen_i32(const void* in, int32_t elem_bytes, int64_t n, int32
 GTOK_API int gtok_counts_to_offsets(const void* counts, int32_t elem_bytes, int64_t num_items, int64_t* off_out,
                                     int32_t* tmp_i32, void* ws, size_t ws_bytes, void* stream);
 
+/* Ingest  the reference's OWN storage -> resident layouts, on the device.  PyG keeps a dataset as int64 tensors on
+ *      the host (InMemoryDataset: edge_index int64[2, E_total] with LOCAL node ids, x int64[N_total(, 1)], edge_attr
+ *      int64[E_total], slices int64[G+1]; zinc_dataset_autograph.py:51-73, zinc_dataset_indexbase.py:63-70).  The
+ *      slices ARE node_off / edge_off; once the bytes are in HBM these calls narrow the rest, so an end-to-end step
+ *      that starts from the reference's tensors needs no host-side conversion:
+ *      gtok_pyg_pack_mol: src64 / dst64 (rows 0 / 1 of edge_index) and attr64 (may be NULL) -> col16[num_entries]
+ *      (GtokPackedMolBatch word), x64 -> x8[num_nodes]; gtok_pyg_narrow: int64[n] -> int32[n] (any graph size).
+ *      A value that does not fit its field is never silently truncated: the matching GTOK_PYG_* bit is OR-ed into
+ *      status[0] (device int32, zeroed by the caller).  Buffers 16-byte aligned; any sub-range of the arrays whose
+ *      start is a multiple of 16 elements is a valid call (chunks of a copy in flight). */
+enum { GTOK_PYG_BAD_NODE_ID = 1,    /* a local node id outside 0..63 */
+       GTOK_PYG_BAD_EDGE_ATTR = 2,  /* an edge_attr outside 0..15 */
+       GTOK_PYG_BAD_NODE_TYPE = 4,  /* an atom type outside 0..255 */
+       GTOK_PYG_BAD_RANGE = 8       /* a value outside int32 (gtok_pyg_narrow) */ };
+GTOK_API int gtok_pyg_pack_mol(const int64_t* src64, const int64_t* dst64, const int64_t* attr64, int64_t num_entries,
+                               const int64_t* x64, int64_t num_nodes, uint16_t* col16, uint8_t* x8, int32_t* status,
+                               void* stream);
+GTOK_API int gtok_pyg_narrow(const int64_t* in64, int64_t n, int32_t* out, int32_t* status, void* stream);
+
 /* Ingest  graph-token TEXTS -> graph arrays on the GPU: the inverse of the external serializer that the reference
  *      runs per text on the host (graph_token_dataset_autograph.py:14-54 parse_graph_from_text, data_loader.py:19-74
  *      query / label parsers) and that the drop-in TokenDataset needs before any tokenizer can run on plain
