@@ -68,21 +68,86 @@ def _cpu_shard(args):
     return count, ntok, time.perf_counter() - t0
 
 
-def cpu_pass(per_core: int, cores: int, seed0: int = 1000):
-    """One bounded sample on `cores` processes; wall-clock graphs/s over the whole sample."""
+def _ref_zinc_shard(args):
+    """The reference's OWN code on one host core (oracle/_ref, built by oracle/make_ref.py): ZINCTokenizationDataset
+    .__getitem__ -> TokenDataset -> collate per 128.  Returns (graphs, tokens, seconds)."""
+    seed, count = args
+    from oracle import ref_arm
+    return ref_arm.zinc_shard(seed, count, MAX_LEN, BATCH)
+
+
+def _ref_gt_shard(args):
+    seed, count = args
+    from oracle import ref_arm
+    return ref_arm.graph_token_shard(seed, count, 600, 600, BATCH)
+
+
+def _sent_shard(args):
+    """SENT on one host core: oracle port (AutoGraph is not part of the reference checkout) + remap + collate_fn."""
+    seed, count, kind = args
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from gtok import synth
+    from oracle import ibtt_oracle as O
+    from oracle import sent_oracle as S
+    if kind == "zinc":
+        gb = synth.zinc_shaped(count, seed=seed)
+        nmax = int(gb.num_nodes().max())
+        cfg = S.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 9, max_length=384, labeled=True)
+    else:
+        gb = synth.er_graph_token(count, seed=seed, device="cpu")
+        cfg = S.SentConfig(idx_offset=6, max_length=600)
+    no, eo = gb.node_off.tolist(), gb.edge_off.tolist()
+    src, dst = gb.src.tolist(), gb.dst.tolist()
+    x = gb.x.tolist() if gb.x is not None else None
+    ea = gb.edge_attr.tolist() if gb.edge_attr is not None else None
+    t0 = time.perf_counter()
+    rows, ntok = [], 0
+    for g in range(count):
+        n = no[g + 1] - no[g]
+        e0, e1 = eo[g], eo[g + 1]
+        rp, col, eattr = S.canonical_csr(n, src[e0:e1], dst[e0:e1], ea[e0:e1] if ea is not None else None)
+        t = S.sent_tokenize(n, rp, col, cfg, S.PhiloxWords(seed, g), x[no[g]:no[g + 1]] if x is not None else None, eattr)
+        if kind == "zinc":
+            t = np.asarray([O.remap_zinc_token(int(v), cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset) for v in t],
+                           dtype=np.int64)
+        rows.append(t)
+        ntok += len(t)
+    for b0 in range(0, count, BATCH):
+        O.collate(rows[b0:b0 + BATCH], [0] * len(rows[b0:b0 + BATCH]), 5)
+    return count, ntok, time.perf_counter() - t0
+
+
+def ref_available() -> bool:
+    from oracle import ref_arm
+    return ref_arm.available()
+
+
+def cpu_pass(per_core: int, cores: int, seed0: int = 1000, shard=None, extra=()):
+    """One bounded sample on `cores` processes; wall-clock graphs/s over the whole sample.
+    shard: worker function (default: the reference's own ZINC path when oracle/_ref exists, else the oracle port)."""
     import multiprocessing as mp
+    if shard is None:
+        shard = _ref_zinc_shard if ref_available() else _cpu_shard
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     if cores == 1:
-        res = [_cpu_shard((seed0, per_core))]
+        res = [shard((seed0, per_core) + tuple(extra))]
     else:
         with ctx.Pool(cores) as pool:
-            res = pool.map(_cpu_shard, [(seed0 + i, per_core) for i in range(cores)])
+            res = pool.map(shard, [(seed0 + i, per_core) + tuple(extra) for i in range(cores)])
     wall = time.perf_counter() - t0
     graphs = sum(r[0] for r in res)
     toks = sum(r[1] for r in res)
     busy = max(r[2] for r in res)      # excludes process start-up and synthetic-input generation
     return graphs, toks, busy, wall
+
+
+def cpu_kind():
+    return ("reference", "the reference's own graph_data_loader (oracle/_ref): ZINCTokenizationDataset.__getitem__ -> "
+            "TokenDataset -> collate") if ref_available() else \
+           ("port", "oracle port of tokenize_molecule + TokenDataset + collate (oracle/_ref absent)")
 
 
 def run_reference(args):
@@ -91,6 +156,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     per_core = args.cpu_graphs_per_core
+    kind, what = cpu_kind()
     times = []
     for i in range(args.warmup + args.steps):
         g, t, busy, _ = cpu_pass(per_core, cores, seed0=1000 + 97 * i)
@@ -100,16 +166,15 @@ def run_reference(args):
     toks = sum(x[1] for x in times)
     secs = sum(x[2] for x in times)
     val = graphs / secs
-    sample = f"{per_core} ZINC-shaped graphs per core x {cores} cores per step (same generator/distribution as the GPU arm)"
+    sample = f"{per_core} ZINC-shaped graphs per core x {cores} cores per step (same generator/distribution as the GPU arm); {what}"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "tokens_per_s": toks / secs,
         "config": {"workload": "ibtt_zinc: 1M ZINC-shaped graphs/GPU, max_len 1024, batch 128 (BASELINE configs[1])",
-                   "note": "reference arm = oracle port of the reference's pure-Python path (the reference is Python and "
-                           "absent on the GPU box); bounded sample per step"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                   "note": "reference arm = " + what + ", all host cores, bounded sample per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -323,11 +388,28 @@ def run_gpu(args):
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        g, t, busy, wall = cpu_pass(args.cpu_graphs_per_core, cores)        # before CUDA init (fork)
-        cpu_base = {"value": g / busy, "unit": UNIT, "cores": cores, "kind": "port",
+        kind, what = cpu_kind()
+        per = args.cpu_graphs_per_core if kind == "port" else max(1, args.cpu_graphs_per_core // 4)
+        g, t, busy, wall = cpu_pass(per, cores)                              # before CUDA init (fork)
+        cpu_base = {"value": g / busy, "unit": UNIT, "cores": cores, "kind": kind,
                     "tokens_per_s": t / busy,
-                    "sample": f"{args.cpu_graphs_per_core} ZINC-shaped graphs per core x {cores} processes, "
-                              f"oracle port of tokenize_molecule+TokenDataset+collate, {busy:.1f}s busy"}
+                    "sample": f"{per} ZINC-shaped graphs per core x {cores} processes, {what}, {busy:.1f}s busy"}
+        if not args.no_extras:
+            # the other BASELINE configs: graph-token IBTT through the reference's own
+            # TokenDataset + collate, SENT through the oracle port (AutoGraph is not in the reference checkout)
+            cpu_extra = {}
+            if ref_available():
+                g2, t2, b2, _ = cpu_pass(max(1, per // 2), cores, shard=_ref_gt_shard)
+                cpu_extra["ibtt_graph_token"] = {"value": g2 / b2, "unit": UNIT, "cores": cores, "kind": "reference",
+                                                 "tokens_per_s": t2 / b2,
+                                                 "sample": f"{max(1, per // 2)} ER graph-token texts per core x {cores}: the reference's "
+                                                           "build_vocab_from_texts + TokenDataset + collate"}
+            for key, knd, n_ in (("sent_graph_token", "er", max(1, per // 16)), ("sent_zinc", "zinc", max(1, per // 8))):
+                g3, t3, b3, _ = cpu_pass(n_, cores, shard=_sent_shard, extra=(knd,))
+                cpu_extra[key] = {"value": g3 / b3, "unit": UNIT, "cores": cores, "kind": "port", "tokens_per_s": t3 / b3,
+                                  "sample": f"{n_} graphs per core x {cores}: oracle/sent_oracle.py (canonical CSR + trail) "
+                                            "+ remap + collate_fn (AutoGraph absent from the reference checkout)"}
+            cpu_base["extras"] = cpu_extra
 
     import torch
     import torch.distributed as dist

@@ -10,9 +10,10 @@ on sys.path (the reference already inserts ``<repo>/AutoGraph``) and the trainer
 Tokenization follows the spec in oracle/sent_oracle.py (parity to AutoGraph itself is UNPINNED,
 see DESIGN.md) and runs in the K3 CUDA kernel.  The reference calls the tokenizer once per
 item per epoch from a Python loop; to keep the GPU busy this class tokenizes the WHOLE dataset
-an item belongs to in one launch and serves rows from that buffer; asking for an item that was
-already served starts a new epoch (new Philox seed, all rows re-sampled), which reproduces the
-reference's "fresh random trail every epoch" behaviour.
+an item belongs to in one launch and serves rows from that buffer; a new epoch (new Philox seed,
+all rows re-sampled) starts on new_epoch() or when a row is asked for again after at least half
+of the dataset has been served - the reference's "fresh random trail every epoch" behaviour,
+without re-tokenizing everything for an early peek at one item.
 """
 from __future__ import annotations
 
@@ -43,6 +44,10 @@ class Graph2TrailTokenizer:
         self.node_idx_offset = self.edge_idx_offset = None
         self.seed = int(seed)
         self.edge_label_shift = 0
+        # the open decisions of the specification the kernels implement (oracle.sent_oracle.SentSpec; a pin produced by
+        # tools/pin_autograph.py says which setting reproduces the real tokenizer)
+        self.restart = kwargs.pop("restart", "open_first")
+        self.bracket_order = kwargs.pop("bracket_order", "visit_asc")
         self.device = torch.device(device) if device is not None else None
         self._cache: Dict[int, dict] = {}
 
@@ -79,7 +84,8 @@ class Graph2TrailTokenizer:
             raise ValueError("labeled_graph=True needs set_num_nodes() and set_num_node_and_edge_types() first")
         return engine.SentConfig(idx_offset=self.idx_offset, node_idx_offset=self.node_idx_offset or 0,
                                  edge_idx_offset=self.edge_idx_offset or 0, max_length=self._limit(),
-                                 labeled=self.labeled_graph, edge_label_shift=self.edge_label_shift)
+                                 labeled=self.labeled_graph, edge_label_shift=self.edge_label_shift,
+                                 restart=self.restart, bracket_order=self.bracket_order)
 
     def tokenize_batch(self, graph_batch, seed: Optional[int] = None, graph_id_base: int = 0, csr=None):
         """Native entry point: GraphBatch (CUDA) -> (tokens int64[G, stride], lengths int32[G])."""
@@ -111,22 +117,39 @@ class Graph2TrailTokenizer:
         seed = (self.seed * 0x9E3779B97F4A7C15 + st["epoch"]) & (2 ** 64 - 1)
         tok, ln = engine.tokenize_sent(st["csr"], self._config(), seed=seed)
         # only the valid tokens cross PCIe: rows are compacted on the device (stride = max_length, mean row ~10 % of it)
-        keep = torch.arange(tok.shape[1], device=tok.device)[None, :] < ln[:, None]
-        flat = tok[keep].cpu()
-        lens = ln.cpu().to(torch.int64)
-        off = torch.zeros(lens.numel() + 1, dtype=torch.int64)
-        off[1:] = lens.cumsum(0)
-        st["flat"], st["off"] = flat, off.tolist()
-        st["served"] = bytearray(lens.numel())
+        flat, off = engine.compact_rows(tok, ln)
+        st["flat"], st["off"] = flat.cpu(), off.cpu().tolist()
+        st["served"] = bytearray(int(ln.numel()))
+        st["nserved"] = 0
+
+    def new_epoch(self, dataset=None) -> None:
+        """Explicit epoch boundary: the next item served from `dataset` (default: every dataset seen so far) comes from
+        freshly sampled trails.  Trainers that can be edited call this once per epoch; the unchanged reference trainer
+        relies on the automatic rule in __call__."""
+        for st in self._cache.values():
+            if dataset is None or st["ds"] is dataset:
+                st["served"] = None
 
     def __call__(self, data) -> torch.Tensor:
+        from torch.utils.data import get_worker_info
+        if get_worker_info() is not None:
+            raise RuntimeError("Graph2TrailTokenizer (gtok) runs CUDA kernels and cannot be called from a DataLoader worker "
+                               "process: set num_workers: 0 (the reference's AGTT configs already do, configs/agtt_*.yaml)")
         handle = getattr(data, "_gtok", None)
         if handle is not None:
             ds, idx = handle
             st = self._epoch(ds)
-            if st["served"] is None or st["served"][idx]:
-                self._sample(st)                       # first use, or this row was already served: new epoch
-            st["served"][idx] = 1
+            # Epoch rule: the reference draws a fresh trail whenever an item is read (train_agtt.py:246-250), i.e. every row
+            # is new in every epoch.  A row asked for a second time starts a new epoch (all rows re-sampled in one launch)
+            # once the current one has served at least half of the dataset; an early re-read (a peek such as
+            # log_graph_examples, a sanity batch) is answered from the current buffer instead of re-tokenizing everything.
+            if st["served"] is None:
+                self._sample(st)
+            elif st["served"][idx] and 2 * st["nserved"] >= len(st["served"]):
+                self._sample(st)
+            if not st["served"][idx]:
+                st["served"][idx] = 1
+                st["nserved"] += 1
             return st["flat"][st["off"][idx]:st["off"][idx + 1]].clone()
         # stand-alone object (no dataset handle): one-graph launch
         from gtok.batch import GraphBatch

@@ -136,6 +136,31 @@ __device__ __forceinline__ void warp_mask_run2(int len0, int len1, int Lmax, uin
   if (tail + lane < total && lane < 16) arow[tail + lane] = val(tail + lane);
 }
 
+// Table variant: tbl[k] (k = 0..16) is the 16-byte mask whose low k bytes are 0x01 (shared memory, filled once per CTA
+// with fill_mask_table): three 16-byte loads replace ~30 ALU instructions per vector.
+__device__ __forceinline__ void fill_mask_table(ulonglong2* tbl, int tid) {
+  if (tid <= 16) tbl[tid] = make_ulonglong2(mask8(tid), mask8(tid - 8));
+}
+__device__ __forceinline__ void warp_mask_run2(int len0, int len1, int Lmax, uint8_t* __restrict__ arow,
+                                               const ulonglong2* __restrict__ tbl) {
+  const int lane = lane_id();
+  const int total = 2 * Lmax;
+  auto val = [&](int p) -> uint8_t { return (uint8_t)(p < Lmax ? (p < len0) : (p - Lmax < len1)); };
+  int mh = (int)((16 - (reinterpret_cast<uintptr_t>(arow) & 15)) & 15);
+  if (mh > total) mh = total;
+  if (lane < mh) arow[lane] = val(lane);
+  const int nvec = (total - mh) >> 4;
+  for (int q = lane; q < nvec; q += kWarp) {
+    const int p = mh + 16 * q;
+    const ulonglong2 A = tbl[min(max(len0 - p, 0), 16)];
+    const ulonglong2 B = tbl[min(max(Lmax + len1 - p, 0), 16)];
+    const ulonglong2 C = tbl[min(max(Lmax - p, 0), 16)];
+    __stcs(reinterpret_cast<ulonglong2*>(arow + p), make_ulonglong2(A.x | (B.x & ~C.x), A.y | (B.y & ~C.y)));
+  }
+  const int tail = mh + 16 * nvec;
+  if (tail + lane < total && lane < 16) arow[tail + lane] = val(tail + lane);
+}
+
 // ---- bulk asynchronous copies (TMA engine, 1-D): shared memory -> global, tracked by bulk async-groups ---------------
 // The copy is issued by ONE thread and moves a whole 16-byte aligned run without touching a register; the issuing
 // thread's generic-proxy writes (and, after a __syncwarp / barrier, everybody else's) must be made visible to the async
@@ -144,6 +169,18 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+// same, with an L2 evict-first policy: the run is written once and never re-read by this kernel, so it must not push
+// the L2-prefetched inputs of the coming tiles out of the cache (what __stcs does for register stores)
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_store_s2g_hint(void* gdst, const void* ssrc, unsigned bytes, unsigned long long pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -159,6 +196,10 @@ __device__ __forceinline__ void bulk_wait() {        // at most N groups not yet
 // ---- decoupled look-back (single-pass chained scan) -------------------------
 // One 64-bit word per tile carries {flag (top 2 bits) | value (62 bits)}, so flag
 // and value can never be observed out of order; relaxed gpu-scope accesses suffice.
+#ifndef GTOK_LOOKBACK_SLEEP_NS
+#define GTOK_LOOKBACK_SLEEP_NS 64
+#endif
+constexpr unsigned kLookbackSleepNs = GTOK_LOOKBACK_SLEEP_NS;
 constexpr unsigned long long kFlagAgg = 1ull << 62;
 constexpr unsigned long long kFlagIncl = 2ull << 62;
 constexpr unsigned long long kValMask = (1ull << 62) - 1;
@@ -186,7 +227,7 @@ __device__ __forceinline__ long long lookback_exclusive(unsigned long long* stat
     if (idx >= 0) {
       w = ld_relaxed_u64(status + idx);
       while ((w >> 62) == 0) {                          // predecessor not published yet: back off instead of hammering L2
-        __nanosleep(64);
+        __nanosleep(kLookbackSleepNs);
         w = ld_relaxed_u64(status + idx);
       }
     } else {

@@ -92,6 +92,8 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
                             int64_t stride) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = lane_id();
+  const bool restart_unvisited = cfg.restart_policy == GTOK_SENT_RESTART_UNVISITED;
+  const bool bracket_desc = cfg.bracket_order == GTOK_SENT_BRACKET_VISIT_DESC;
   const int w = threadIdx.x >> 5;
   unsigned char* base = smem + (size_t)w * lay.total;
   int* rp = reinterpret_cast<int*>(base + lay.rp);
@@ -265,7 +267,7 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
                 if (key == mn) { rank = j; key = 0xffffffffu; }
               }
               if (member) {
-                const int pos = len + 1 + rank * per;
+                const int pos = len + 1 + (bracket_desc ? M - 1 - rank : rank) * per;
                 if (LABELED) {
                   put(pos, cfg.edge_idx_offset + eav + cfg.edge_label_shift);
                   put(pos + 1, cfg.idx_offset + vu);
@@ -309,7 +311,7 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
           if (nvis == N) break;
           // ---- restart: visited nodes with unvisited neighbours, else unvisited nodes
           int nxt;
-          if (nopen > 0) nxt = locate(openb, false, pick(nopen));
+          if (nopen > 0 && !restart_unvisited) nxt = locate(openb, false, pick(nopen));
           else nxt = locate(visb, true, pick(N - nvis));
           if (lane == 0) put(len, RESET);
           len += 1;
@@ -360,6 +362,11 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
               ++nopen;
             }
             int M = 0;
+            int Mtot = 0;                                         // descending brackets: positions count from the end
+            if (bracket_desc) {
+              for (int i = lane; i < nwords; i += kWarp) Mtot += __popc(bits[i]);
+              Mtot = __reduce_add_sync(kFull, Mtot);
+            }
             for (int w0 = 0; w0 < nwords; w0 += kWarp) {
               unsigned word = (w0 + lane < nwords) ? bits[w0 + lane] : 0u;
               const int cw = __popc(word);
@@ -374,7 +381,7 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
                 const int bpos = __ffs(word) - 1;
                 word &= word - 1;
                 const int vi = ((w0 + lane) << 5) + bpos;
-                const int pos = len + 1 + j * per;
+                const int pos = len + 1 + (bracket_desc ? Mtot - 1 - j : j) * per;
                 if (LABELED) {
                   put(pos, cfg.edge_idx_offset + EA(ent[vi]) + cfg.edge_label_shift);
                   put(pos + 1, cfg.idx_offset + vi);
@@ -421,7 +428,7 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
             if (nvis == N) break;
             // ---- restart: visited nodes with unvisited neighbours, else unvisited nodes
             int nxt;
-            if (nopen > 0) nxt = locate(openb, false, pick(nopen));
+            if (nopen > 0 && !restart_unvisited) nxt = locate(openb, false, pick(nopen));
             else nxt = locate(visb, true, pick(N - nvis));
             if (lane == 0) put(len, RESET);
             len += 1;
@@ -521,6 +528,10 @@ extern "C" int gtok_sent_tokenize_ws(const GtokCsrBatch* csr, const GtokSentCfg*
                "sent: labeled mode needs csr.x and csr.eattr");
   GTOK_REQUIRE(!cfg->append_query || (csr->query_u && csr->query_v), GTOK_EINVAL, "sent: append_query needs query_u/query_v");
   GTOK_REQUIRE(choice->stream == nullptr || choice->stream_off != nullptr, GTOK_EINVAL, "sent: choice stream without offsets");
+  GTOK_REQUIRE(cfg->restart_policy == GTOK_SENT_RESTART_OPEN_FIRST || cfg->restart_policy == GTOK_SENT_RESTART_UNVISITED,
+               GTOK_EUNSUPPORTED, "sent: restart_policy %d is not implemented by the kernels", cfg->restart_policy);
+  GTOK_REQUIRE(cfg->bracket_order == GTOK_SENT_BRACKET_VISIT_ASC || cfg->bracket_order == GTOK_SENT_BRACKET_VISIT_DESC,
+               GTOK_EUNSUPPORTED, "sent: bracket_order %d is not implemented by the kernels", cfg->bracket_order);
   GTOK_REQUIRE((reinterpret_cast<uintptr_t>(tok_out) & 15) == 0, GTOK_EINVAL, "sent: tok_out must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   {

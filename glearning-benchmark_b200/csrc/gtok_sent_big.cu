@@ -113,6 +113,8 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
   using W = typename S::T;
   extern __shared__ __align__(16) unsigned char b_smem[];
   const int lane = lane_id();
+  const bool restart_unvisited = cfg.restart_policy == GTOK_SENT_RESTART_UNVISITED;
+  const bool bracket_desc = cfg.bracket_order == GTOK_SENT_BRACKET_VISIT_DESC;
   unsigned char* base = b_smem + (size_t)(threadIdx.x >> 5) * lay.total;
   unsigned* bits = reinterpret_cast<unsigned*>(base + lay.bits);
   unsigned* openb = reinterpret_cast<unsigned*>(base + lay.openb);
@@ -232,7 +234,7 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
                 if (key == mn) { rank = j; key = 0xffffffffu; }
               }
               if (member) {
-                const int pos = len + 1 + rank * per;
+                const int pos = len + 1 + (bracket_desc ? M - 1 - rank : rank) * per;
                 if (LABELED) {
                   put(pos, cfg.edge_idx_offset + eav + cfg.edge_label_shift);
                   put(pos + 1, cfg.idx_offset + vu);
@@ -329,7 +331,7 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
                   const int vu = S::vis(ld_cg(st + u));
                   if (vu >= 0 && u != prev) {
                     const int rank = (int)pref[vu >> 5] + __popc(bits[vu >> 5] & ((1u << (vu & 31)) - 1u));
-                    const int pos = len + 1 + rank * per;
+                    const int pos = len + 1 + (bracket_desc ? M - 1 - rank : rank) * per;
                     if (LABELED) {
                       put(pos, cfg.edge_idx_offset + EA(e) + cfg.edge_label_shift);
                       put(pos + 1, cfg.idx_offset + vu);
@@ -387,7 +389,7 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
         __syncwarp();
         if (nvis == N) break;
         // ---- restart: visited nodes with unvisited neighbours, else unvisited nodes
-        const bool reopen = nopen > 0;
+        const bool reopen = nopen > 0 && !restart_unvisited;
         cur = reopen ? locate_bit(openb, false, pick(nopen), N, lane) : locate_bit(visb, true, pick(N - nvis), N, lane);
         extents(cur, lo, hi, &vc);
         if (!reopen) vc = -1;

@@ -51,6 +51,20 @@ struct Bits {
     for (int i = 0; i < W; ++i) c += __popcll(w[i]);
     return c;
   }
+  __device__ __forceinline__ int pop_highest() {         // index of the highest set bit, cleared; any() must hold
+    int r = 0;
+    bool got = false;
+#pragma unroll
+    for (int i = W - 1; i >= 0; --i) {
+      if (!got && w[i]) {
+        const int b = 63 - __clzll((long long)w[i]);
+        r = 64 * i + b;
+        w[i] &= ~(1ull << b);
+        got = true;
+      }
+    }
+    return r;
+  }
   __device__ __forceinline__ int pop_lowest() {          // index of the lowest set bit, cleared; any() must hold
     int r = 0;
     bool got = false;
@@ -141,6 +155,8 @@ sent_mid_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
   const int Lcap = cfg.max_length;
   const unsigned k0 = (unsigned)(ch.seed & 0xffffffffu), k1 = (unsigned)(ch.seed >> 32);
   const bool remap = cfg.remap_zinc != 0;
+  const bool restart_unvisited = cfg.restart_policy == GTOK_SENT_RESTART_UNVISITED;
+  const bool bracket_desc = cfg.bracket_order == GTOK_SENT_BRACKET_VISIT_DESC;
   const int idx_off = cfg.idx_offset, node_off = cfg.node_idx_offset, edge_off = cfg.edge_idx_offset;
   if (remap) {
     for (int t = threadIdx.x; t < kMidRemap; t += blockDim.x)
@@ -254,7 +270,7 @@ sent_mid_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
           if (V.any()) {
             emit(LADJ);
             do {
-              const int jv = V.pop_lowest();
+              const int jv = bracket_desc ? V.pop_highest() : V.pop_lowest();
               if (LABELED) emit(edge_label(rp_cur, (int)ord[jv * 32], a_cur));
               emit(idx_off + jv);
               flush_guard();
@@ -271,7 +287,7 @@ sent_mid_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
         } else {
           Bits<W> sel = C;
           if (!hasC) {
-            sel = open.any() ? open : b_andnot(nodemask, visited);
+            sel = (open.any() && !restart_unvisited) ? open : b_andnot(nodemask, visited);
             emit(RESET);
           }
           const int nsel = sel.count();

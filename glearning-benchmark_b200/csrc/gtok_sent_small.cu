@@ -92,6 +92,8 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
   const int Lcap = cfg.max_length;
   const unsigned k0 = (unsigned)(ch.seed & 0xffffffffu), k1 = (unsigned)(ch.seed >> 32);
   const bool remap = cfg.remap_zinc != 0;
+  const bool restart_unvisited = cfg.restart_policy == GTOK_SENT_RESTART_UNVISITED;
+  const bool bracket_desc = cfg.bracket_order == GTOK_SENT_BRACKET_VISIT_DESC;
   const int idx_off = cfg.idx_offset, node_off = cfg.node_idx_offset, edge_off = cfg.edge_idx_offset;
   __shared__ unsigned short s_remap[kRemapTable];
   if (remap) {
@@ -234,6 +236,22 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
                 if (jv < 32) vlo |= 1u << jv; else vhi |= 1u << (jv - 32);
               }
               const bool longb = __popc(vlo) + __popc(vhi) > 10;  // only a long bracket can outrun the ring
+              if (bracket_desc) {                                 // GTOK_SENT_BRACKET_VISIT_DESC: highest visit index first
+                while (vhi) {
+                  const int b = 31 - __clz((int)vhi);
+                  vhi &= ~(1u << b);
+                  if (LABELED) emit(edge_label(rp_cur, (int)ord[(32 + b) * 32], a_cur));
+                  emit(idx_off + 32 + b);
+                  if (longb) flush_guard();
+                }
+                while (vlo) {
+                  const int b = 31 - __clz((int)vlo);
+                  vlo &= ~(1u << b);
+                  if (LABELED) emit(edge_label(rp_cur, (int)ord[b * 32], a_cur));
+                  emit(idx_off + b);
+                  if (longb) flush_guard();
+                }
+              }
               while (vlo) {
                 const int jv = __ffs((int)vlo) - 1;
                 vlo &= vlo - 1;
@@ -261,7 +279,7 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
         } else {
           unsigned long long sel = C;
           if (!C) {                                               // stuck: restart at an open node, else at any unvisited node
-            sel = open ? open : (~visited & nodemask);
+            sel = (open && !restart_unvisited) ? open : (~visited & nodemask);
             emit(RESET);
           }
           const int nsel = __popcll(sel);

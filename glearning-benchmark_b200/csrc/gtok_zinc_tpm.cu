@@ -77,9 +77,10 @@ __device__ __forceinline__ void put2(int32_t* rb, int idx, unsigned t0, unsigned
 template <typename StageT, bool HAS_ATTR, bool PADDED, bool UNIQ = false, int TMA = 0>
 __global__ void __launch_bounds__(kTpmMaxT)
 zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v, const TpmLayout lay, const TpmOut o,
-                unsigned int* __restrict__ ticket, unsigned long long* __restrict__ status, const int vec_ok,
+                unsigned int* __restrict__ ticket, unsigned long long* __restrict__ status, const int flags,
                 const int pf_dist, const uint16_t* __restrict__ p_col16, const uint8_t* __restrict__ p_x8) {
   constexpr bool unique_cols = UNIQ;                     // the columns are already the first-seen undirected edges
+  const int vec_ok = flags & 1;                          // the int32 arrays are 16-byte aligned
   extern __shared__ __align__(16) unsigned char t_smem[];
   __shared__ StageT s_nt[64];
   __shared__ StageT s_atom[10];
@@ -88,6 +89,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
   __shared__ int s_wmax[2][kTpmMaxT / 32];
   __shared__ long long s_base[2];
   __shared__ unsigned int s_tile[2];
+  __shared__ ulonglong2 s_m16[17];
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int T = lay.T, nwarps = T >> 5;
@@ -109,6 +111,7 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
   if (tid == 9) s_atom[9] = (StageT)v.atom_oov;
   if (tid >= 16 && tid < 20) s_bond[tid - 16] = (StageT)v.bond_tok[tid - 16];
   if (tid == 20) s_bond[4] = (StageT)v.bond_oov;
+  if (TMA) fill_mask_table(s_m16, tid);
   if (tid == 0) s_tile[0] = atomicAdd(ticket, 1u);
   const long long E_total = __ldg(b.edge_off + G), N_total = __ldg(b.node_off + G);
   const unsigned tk_bos = (unsigned)v.tok_bos, tk_atom = (unsigned)v.tok_atom, tk_bond = (unsigned)v.tok_bond;
@@ -378,7 +381,11 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
       // earlier tile holds T rows, T even): 16-byte aligned, a multiple of 16 bytes long - what a bulk copy needs.
       int64_t* slots = reinterpret_cast<int64_t*>(s_row);
       const long long padv = o.pad;
-      auto build64 = [&](int j, int64_t* rb) {           // cells [0, lmax) of row j: tokens below len, pad beyond
+      const bool l2_hint = (flags & 2) != 0;
+      const unsigned long long l2_pol = l2_policy_evict_first();
+      // `prev` = length of the row this sub-slot held before (lmax on first use in the tile): cells [prev, lmax) still
+      // hold pad, so only [len, prev) has to be refilled
+      auto build64 = [&](int j, int64_t* rb, int prev) -> int {   // cells [0, lmax) of row j: tokens below len, pad beyond
         const int rN = __shfl_sync(kFull, N, j), rcnt = __shfl_sync(kFull, cnt, j);
         const int reo = __shfl_sync(kFull, eo, j), rno = __shfl_sync(kFull, no, j);
         const int len = __shfl_sync(kFull, my_len, j), rfull = __shfl_sync(kFull, full_T, j);
@@ -418,9 +425,11 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
           }
           if (lane < 3) put(bb + 4 * rcnt + lane, (unsigned)tail_tok);
         }
-        for (int p = len + lane; p < lmax; p += 32) rb[p] = padv;
+        for (int p = len + lane; p < prev; p += 32) rb[p] = padv;
+        return len;
       };
       int sl = 0;
+      int pA0 = lmax, pB0 = lmax, pA1 = lmax, pB1 = lmax;
 #pragma unroll 1
       for (; j_first + 1 < nv; j_first += 2) {
         const int j = j_first;
@@ -429,20 +438,22 @@ zinc_tpm_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
           if (TMA == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
         }
         __syncwarp();
-        build64(j, rb);
-        build64(j + 1, rb + lmax);
+        const int lenA = build64(j, rb, sl ? pA1 : pA0);
+        const int lenB = build64(j + 1, rb + lmax, sl ? pB1 : pB0);
+        if (sl) { pA1 = lenA; pB1 = lenB; } else { pA0 = lenA; pB0 = lenB; }
         fence_proxy_async_smem();
         __syncwarp();
         wait_base();
         if (base + pub <= o.x_capacity) {
           const long long cell = base + (long long)(32 * w + j) * lmax;
           if (lane == 0) {
-            bulk_store_s2g(o.X + cell, rb, (unsigned)(2 * lmax) * 8u);
+            if (l2_hint) bulk_store_s2g_hint(o.X + cell, rb, (unsigned)(2 * lmax) * 8u, l2_pol);
+            else bulk_store_s2g(o.X + cell, rb, (unsigned)(2 * lmax) * 8u);
             bulk_commit();
           }
-          warp_mask_run2(__shfl_sync(kFull, my_len, j), __shfl_sync(kFull, my_len, j + 1), lmax, o.attn + cell);
+          warp_mask_run2(lenA, lenB, lmax, o.attn + cell, s_m16);
         }
-        sl ^= 1;
+        if (TMA == 2) sl ^= 1;
       }
       if (lane == 0) bulk_wait_read<0>();                  // the slots alias the row buffers / next tile's pair bitmaps
       __syncwarp();
@@ -479,13 +490,18 @@ int tpm_prefetch_dist() {
 
 // Shared-memory plan for tiles of T molecules; false if it does not fit.
 template <typename StageT>
-bool tpm_layout(int T, int max_nodes, int max_entries, int smem_optin, TpmLayout* out, int tma_slots = 0) {
+bool tpm_layout(int T, int max_nodes, int max_entries, int smem_optin, TpmLayout* out, int tma_slots = 0,
+                int group_nodes = 0, int group_entries = 0) {
   TpmLayout L;
   L.T = T;
   L.nmax = max_nodes < 1 ? 1 : max_nodes;
   L.bm_words = (L.nmax * (L.nmax + 1) / 2 + 31) / 32;
   L.col_cap = 32 * max_entries;
   L.x_cap = 32 * L.nmax;
+  // a warp stages the 32 molecules of one aligned group: the caller's per-group bounds, when given, are tighter than
+  // 32 x the per-molecule bounds (ZINC-shaped data: 1.8k instead of 2.5k columns - one more resident CTA per SM)
+  if (group_entries > 0 && group_entries < L.col_cap) L.col_cap = (group_entries + 7) & ~7;
+  if (group_nodes > 0 && group_nodes < L.x_cap) L.x_cap = (group_nodes + 15) & ~15;
   L.row_cap = (2 * L.nmax + 4 * max_entries + 8 + 7) & ~7;      // untruncated row + slack, keeps buffers 16-byte aligned
   int o = 0;
   L.o_col = o; o += ((L.col_cap + 16) * 2 + 15) & ~15;          // slack: the aligned first / last 16-byte group may spill over
@@ -522,15 +538,16 @@ int tpm_launch(const GtokGraphBatch* batch, const GtokZincVocab* vocab, const Tp
   GTOK_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   TpmLayout lay;
   bool ok = false;
-  // bulk-store flush: measured faster on the compact 16-bit layout (0.526 -> 0.498 ms per 1M molecules), slower on the
-  // int32 layout where the slot costs a resident CTA (6 -> 5 per SM: 0.648 -> 0.701 ms); GTOK_ZINC_TMA=0/1/2 overrides
+  // bulk-store flush, one slot per warp (measured on 1M ZINC-shaped molecules, same box: register flush 0.705 ms,
+  // one slot 0.594 ms, two slots 0.649 ms - the second slot costs resident CTAs); GTOK_ZINC_TMA=0/1/2 overrides
   static const int tma_env = [] { const char* e = getenv("GTOK_ZINC_TMA"); return e ? atoi(e) : -1; }();
-  int tma = PADDED ? (tma_env < 0 ? (x8 ? 1 : 0) : (tma_env > 2 ? 2 : tma_env)) : 0;
+  int tma = PADDED ? (tma_env < 0 ? 1 : (tma_env > 2 ? 2 : tma_env)) : 0;
   if (T_fixed > 0) {
-    ok = tma && tpm_layout<StageT>(T_fixed, batch->max_nodes, batch->max_entries, optin, &lay, tma);
+    const int gn = batch->max_nodes_per_32, ge = batch->max_entries_per_32;
+    ok = tma && tpm_layout<StageT>(T_fixed, batch->max_nodes, batch->max_entries, optin, &lay, tma, gn, ge);
     if (!ok) {
-      tma = 0;
-      ok = tpm_layout<StageT>(T_fixed, batch->max_nodes, batch->max_entries, optin, &lay);
+      tma = 0;                                           // (register flush: more resident CTAs only lengthen the look-back
+      ok = tpm_layout<StageT>(T_fixed, batch->max_nodes, batch->max_entries, optin, &lay);   //  chain - measured slower)
     }
   } else {
     static const int t_env = [] { const char* e = getenv("GTOK_ZINC_TILE"); return e ? atoi(e) : 0; }();
@@ -561,8 +578,9 @@ int tpm_launch(const GtokGraphBatch* batch, const GtokZincVocab* vocab, const Tp
   const int grid = persistent_grid(k, lay.T, (size_t)lay.smem, tiles);
   const int vec_ok = x8 ? 1 : ((reinterpret_cast<uintptr_t>(batch->src) | reinterpret_cast<uintptr_t>(batch->dst) |
                                    reinterpret_cast<uintptr_t>(batch->edge_attr) | reinterpret_cast<uintptr_t>(batch->x)) & 15) == 0;
+  static const int hint_env = [] { const char* e = getenv("GTOK_ZINC_L2HINT"); return e ? atoi(e) : 1; }();
   k<<<grid, lay.T, lay.smem, st>>>(*batch, *vocab, lay, o, reinterpret_cast<unsigned int*>(ws),
-                                   reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + 16), vec_ok,
+                                   reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + 16), vec_ok | (hint_env ? 2 : 0),
                                    tpm_prefetch_dist(), col16, x8);
   GTOK_CUDA_TRY(cudaGetLastError());
   *handled = true;
@@ -700,6 +718,7 @@ extern "C" int gtok_zinc_collate_packed(const GtokPackedMolBatch* pk, const Gtok
   GtokGraphBatch b{};
   b.num_graphs = pk->num_graphs; b.node_off = pk->node_off; b.edge_off = pk->edge_off;
   b.max_nodes = pk->max_nodes; b.max_entries = pk->max_entries;
+  b.max_nodes_per_32 = pk->max_nodes_per_32; b.max_entries_per_32 = pk->max_entries_per_32;
   TpmOut o{};
   o.len_out = len_out; o.lmax_out = lmax_out; o.xoff_out = xoff_out; o.X = X; o.attn = attn;
   o.x_capacity = x_capacity; o.pad = pad_id;

@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgtok.so")
+LIB_PATH = os.environ.get("GTOK_LIB_PATH") or os.path.join(_HERE, "libgtok.so")   # (override: A/B builds of the same ABI)
 
 GTOK_OK, GTOK_EINVAL, GTOK_ECUDA, GTOK_EUNSUPPORTED, GTOK_EWORKSPACE = 0, -1, -2, -3, -4
 TASK_CYCLE_CHECK, TASK_SHORTEST_PATH = 0, 1
@@ -29,12 +29,13 @@ class GtokError(RuntimeError):
 class GraphBatchC(C.Structure):
     _fields_ = [("num_graphs", i64), ("node_off", vp), ("edge_off", vp), ("src", vp), ("dst", vp),
                 ("x", vp), ("edge_attr", vp), ("query_u", vp), ("query_v", vp),
-                ("max_nodes", i32), ("max_entries", i32)]
+                ("max_nodes", i32), ("max_entries", i32), ("max_nodes_per_32", i32), ("max_entries_per_32", i32)]
 
 
 class PackedMolBatchC(C.Structure):
     _fields_ = [("num_graphs", i64), ("node_off", vp), ("edge_off", vp), ("col16", vp), ("x8", vp),
-                ("max_nodes", i32), ("max_entries", i32), ("unique_columns", i32), ("reserved_", i32)]
+                ("max_nodes", i32), ("max_entries", i32), ("unique_columns", i32), ("max_nodes_per_32", i32),
+                ("max_entries_per_32", i32), ("reserved_", i32)]
 
 
 class IbttRulesC(C.Structure):
@@ -57,7 +58,8 @@ class CsrBatchC(C.Structure):
 
 class SentCfgC(C.Structure):
     _fields_ = [("idx_offset", i32), ("node_idx_offset", i32), ("edge_idx_offset", i32), ("max_length", i32),
-                ("labeled", i32), ("edge_label_shift", i32), ("remap_zinc", i32), ("append_query", i32)]
+                ("labeled", i32), ("edge_label_shift", i32), ("remap_zinc", i32), ("append_query", i32),
+                ("restart_policy", i32), ("bracket_order", i32)]
 
 
 class ErSpecC(C.Structure):
@@ -105,6 +107,10 @@ PROTOTYPES = {
     "gtok_pad_mask_batched": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, vp]),
     "gtok_csr_adjacency": (C.c_int, [C.POINTER(GraphBatchC), i32, i64, vp, vp, vp]),
     "gtok_csr_fill": (C.c_int, [C.POINTER(GraphBatchC), i32, i64, vp, vp, i64, vp, vp, vp, vp, vp]),
+    "gtok_compact_rows": (C.c_int, [vp, i64, vp, vp, i64, vp, vp]),
+    "gtok_segment_counts": (C.c_int, [vp, i64, vp, i64, vp, vp, vp]),
+    "gtok_gather_segments": (C.c_int, [vp, vp, i64, vp, vp, i64, vp, vp]),
+    "gtok_balance_order": (C.c_int, [vp, vp, i64, i32, vp, vp]),
     "gtok_find_token": (C.c_int, [vp, vp, vp, i64, i64, vp, i64, vp, vp]),
     "gtok_graph_labels": (C.c_int, [C.POINTER(CsrBatchC), vp, vp, vp, vp]),
     "gtok_er_sizes": (C.c_int, [C.POINTER(ErSpecC), i64, vp, vp, vp, vp, vp]),

@@ -104,7 +104,11 @@ class GraphBatch:
                           opt(self.query_v, g0, g1), opt(self.y, g0, g1))
 
     def select(self, idx: torch.Tensor) -> "GraphBatch":
-        """Gather the graphs idx[0], idx[1], ... into a new batch (any order, repeats allowed)."""
+        """Gather the graphs idx[0], idx[1], ... into a new batch (any order, repeats allowed).  CUDA batches go through
+        the library kernels (engine.gather_graphs); host batches (tests, dataset construction) use tensor ops."""
+        if self.node_off.is_cuda:
+            from . import engine
+            return engine.gather_graphs(self, idx.to(self.node_off.device))
         idx = idx.to(self.node_off.device, torch.int64)
         n = (self.node_off[idx + 1] - self.node_off[idx])
         e = (self.edge_off[idx + 1] - self.edge_off[idx])

@@ -66,6 +66,17 @@ def _batch_c(b: GraphBatch, max_nodes: Optional[int], max_entries: Optional[int]
                             _ptr(b.edge_attr), _ptr(b.query_u), _ptr(b.query_v), max(1, max_nodes), max(1, max_entries))
 
 
+def group_bounds(off: torch.Tensor, group: int = 32) -> int:
+    """max over aligned groups of `group` consecutive graphs of their item total (off = node_off / edge_off):
+    the staging bound GtokGraphBatch.max_nodes_per_32 / max_entries_per_32 of the thread-per-molecule kernels."""
+    G = off.numel() - 1
+    if G <= 0:
+        return 0
+    idx = torch.arange(0, G + group, group, device=off.device).clamp_(max=G)
+    b = off[idx]
+    return int((b[1:] - b[:-1]).max())
+
+
 def node_token_table(vocab: Dict[str, int], size: int, device) -> torch.Tensor:
     """node_tok[k] = vocab.get(str(k), vocab['<pad>']) - the lookup the reference does
     per token with a dict (data_loader.py:482)."""
@@ -407,6 +418,8 @@ def zinc_collate_epoch(batch: GraphBatch, vocab: Dict[str, int], max_len: int, b
     G, B = batch.num_graphs, int(batch_size)
     nb = (G + B - 1) // B
     bc = _batch_c(batch, max_nodes, max_entries)
+    if max_nodes is None and max_entries is None:
+        bc.max_nodes_per_32, bc.max_entries_per_32 = group_bounds(batch.node_off), group_bounds(batch.edge_off)
     zv, tbl = zinc_vocab_c(vocab, max_len if item_max_len is None else item_max_len, max_len, bc.max_nodes, dev)
     lengths = torch.empty(G, dtype=torch.int32, device=dev)
     lmax = torch.empty(nb, dtype=torch.int32, device=dev)
@@ -483,8 +496,13 @@ def _finish_csr(batch: GraphBatch, rowptr, col_local, eattr, adj64, adj_words, b
         # one thread walks one graph: give the 32 lanes of a warp graphs of similar work, but only reorder
         # inside windows of consecutive graphs - a global sort scatters a warp's reads and rows over the whole
         # buffers and was measured 10-30 % SLOWER than natural order
-        w = torch.arange(G, device=dev) // int(balance_window)
-        order = torch.argsort(w * (1 << 40) + n * 4096 + nnz_g, stable=True).to(torch.int32)
+        if rowptr.is_cuda:
+            order = torch.empty(G, dtype=torch.int32, device=dev)
+            check(lib.gtok_balance_order(_ptr(batch.node_off), _ptr(rowptr.to(torch.int32)), G, min(int(balance_window), 4096),
+                                         _ptr(order), _stream()))
+        else:                                             # host tensors (CPU tests of the sort-based reference build)
+            w = torch.arange(G, device=dev) // int(balance_window)
+            order = torch.argsort(w * (1 << 40) + n * (1 << 20) + nnz_g.clamp(max=(1 << 20) - 1), stable=True).to(torch.int32)
     return CsrBatch(batch.node_off, rowptr.to(torch.int32), col_local, eattr, batch.x, batch.query_u, batch.query_v,
                     int(n.max()) if G else 1, int(nnz_g.max()) if G else 0, max_label, adj64, adj_words, order)
 
@@ -585,6 +603,64 @@ class SentConfig:
     edge_label_shift: int = 0
     remap_zinc: bool = False
     append_query: bool = False
+    restart: str = "open_first"          # oracle.sent_oracle.SentSpec.restart: "open_first" | "unvisited"
+    bracket_order: str = "visit_asc"     # SentSpec.bracket_order: "visit_asc" | "visit_desc"
+
+    RESTART = {"open_first": 0, "unvisited": 1}
+    BRACKET = {"visit_asc": 0, "visit_desc": 1}
+
+
+def compact_rows(tok: torch.Tensor, lengths: torch.Tensor):
+    """Strided rows [G, stride] + lengths -> (ragged int64 stream, offsets int64[G+1]) with library kernels (K0 scan +
+    gtok_compact_rows) - what boolean-mask indexing would do with torch ops."""
+    _require_cuda(tok, lengths)
+    G, stride = int(tok.shape[0]), int(tok.shape[1])
+    off = scan_offsets(lengths)
+    total = int(off[-1]) if G else 0
+    out = torch.empty(total, dtype=torch.int64, device=tok.device)
+    check(lib.gtok_compact_rows(_ptr(tok), stride, _ptr(lengths), _ptr(off), G, _ptr(out), _stream()))
+    return out, off
+
+
+def gather_graphs(batch: GraphBatch, idx: torch.Tensor) -> GraphBatch:
+    """The graphs idx[0], idx[1], ... of a CUDA batch as a new batch (any order, repeats allowed): gtok_segment_counts
+    -> K0 scan -> gtok_gather_segments per array.  Raises IndexError on an index outside the batch."""
+    _require_cuda(batch.src, idx)
+    dev = batch.device
+    idx = idx.to(torch.int64).contiguous()
+    M, G = int(idx.numel()), batch.num_graphs
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def offsets(off):
+        cnt = torch.empty(M, dtype=torch.int32, device=dev)
+        check(lib.gtok_segment_counts(_ptr(off), G, _ptr(idx), M, _ptr(cnt), _ptr(status), _stream()))
+        return scan_offsets(cnt)
+    node_off, edge_off = offsets(batch.node_off), offsets(batch.edge_off)
+    if int(status):
+        raise IndexError("gather_graphs: index outside the batch")
+    one = torch.ones(M + 1, dtype=torch.int64, device=dev).cumsum(0) - 1          # offsets of one item per graph
+
+    def gather(arr, src_off, dst_off):
+        if arr is None:
+            return None
+        out = torch.empty(int(dst_off[-1]) if M else 0, dtype=torch.int32, device=dev)
+        check(lib.gtok_gather_segments(_ptr(arr), _ptr(src_off), G, _ptr(idx), _ptr(dst_off), M, _ptr(out), _stream()))
+        return out
+    per_graph = lambda a: gather(a, one_src, one)
+    one_src = torch.ones(G + 1, dtype=torch.int64, device=dev).cumsum(0) - 1
+    y = None
+    if batch.y is not None:
+        y = batch.y.to(dev)[idx]                          # labels never enter a kernel (plain indexing of G values)
+    return GraphBatch(node_off, edge_off, gather(batch.src, batch.edge_off, edge_off), gather(batch.dst, batch.edge_off, edge_off),
+                      gather(batch.x, batch.node_off, node_off), gather(batch.edge_attr, batch.edge_off, edge_off),
+                      per_graph(batch.query_u), per_graph(batch.query_v), y)
+
+
+def _sent_switch(table: Dict[str, int], value: str) -> int:
+    if value not in table:
+        raise ValueError(f"the CUDA SENT kernels implement {sorted(table)} (got {value!r}); the other settings of "
+                         "oracle.sent_oracle.SentSpec are oracle-only")
+    return table[value]
 
 
 def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: int = 0,
@@ -606,7 +682,8 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
     lengths = torch.empty(G, dtype=torch.int32, device=dev)
     cc = _csr_c(csr)
     sc = _lib.SentCfgC(cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset, cfg.max_length, int(cfg.labeled),
-                       cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query))
+                       cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query), _sent_switch(cfg.RESTART, cfg.restart),
+                       _sent_switch(cfg.BRACKET, cfg.bracket_order))
     ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))
     n_total = int(csr.rowptr.numel()) - 1
     if use_workspace is None:

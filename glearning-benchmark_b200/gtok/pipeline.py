@@ -236,6 +236,10 @@ class ZincIbttPipeline(_PipelineBase):
         e = host_batch.num_entries()
         self.max_nodes = max(int(n.max()) if G else 1, max_nodes or 0)
         self.max_entries = max(int(e.max()) if G else 1, max_entries or 0)
+        # per-warp staging bounds (aligned groups of 32 molecules) - only when this batch is all the pipeline will see
+        stream_of_shards = any(v is not None for v in (max_nodes, max_entries, node_capacity, entry_capacity))
+        self.group_nodes = 0 if stream_of_shards else engine.group_bounds(host_batch.node_off)
+        self.group_entries = 0 if stream_of_shards else engine.group_bounds(host_batch.edge_off)
         n_total = max(int(host_batch.node_off[-1]), node_capacity or 0)
         e_total = max(int(host_batch.edge_off[-1]), entry_capacity or 0)
         row_bound = min(max_len, 2 * self.max_nodes + 4 * self.max_entries + 4)
@@ -262,7 +266,7 @@ class ZincIbttPipeline(_PipelineBase):
         d = self.dev_in
         return _lib.GraphBatchC(self.G, _ptr(d["node_off"]), _ptr(d["edge_off"]), _ptr(d["src"]), _ptr(d["dst"]),
                                 _ptr(d["x"]), _ptr(d["edge_attr"]), None, None, max(1, self.max_nodes),
-                                max(1, self.max_entries))
+                                max(1, self.max_entries), self.group_nodes, self.group_entries)
 
     def launch(self) -> None:
         """The hot path on whatever dev_in points at: 4 kernels (fused tokenizer) or 6, no sync."""
@@ -272,7 +276,8 @@ class ZincIbttPipeline(_PipelineBase):
             col16, x8, max_id, unique, edge_off = self._packed_dev
             d = self.dev_in
             pk = _lib.PackedMolBatchC(self.G, _ptr(d["node_off"]), _ptr(edge_off), _ptr(col16), _ptr(x8),
-                                      max(1, self.max_nodes, max_id + 1), max(1, self.max_entries), int(unique), 0)
+                                      max(1, self.max_nodes, max_id + 1), max(1, self.max_entries), int(unique),
+                                      self.group_nodes, 0 if unique else self.group_entries, 0)
             self._timed("zinc_collate_packed", lambda: check(lib.gtok_zinc_collate_packed(
                 C.byref(pk), C.byref(self.zv), self.B, self.pad_id, _ptr(self.lengths), _ptr(self.lmax), _ptr(self.xoff),
                 _ptr(self.X), _ptr(self.attn), min(self.X.numel(), self.attn.numel()), _ptr(self.ws), self.ws_bytes, st)))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GTOK_VERSION 100 /* 0.1.0 */
+#define GTOK_VERSION 101 /* 0.1.1 */
 
 #if defined(__GNUC__)
 #define GTOK_API __attribute__((visibility("default")))
@@ -64,6 +64,9 @@ typedef struct GtokGraphBatch {
   const int32_t* query_v;    /* [G] or NULL */
   int32_t max_nodes;         /* upper bound on nodes per graph   (0 = unknown) */
   int32_t max_entries;       /* upper bound on entries per graph (0 = unknown) */
+  int32_t max_nodes_per_32;  /* optional tighter staging bounds for the thread-per-molecule ZINC kernels: upper bound on */
+  int32_t max_entries_per_32;/* the nodes / entries of any aligned group of 32 consecutive graphs [32k, 32k+32) (one warp's
+                                staging run); 0 = unknown (32 * max_nodes / 32 * max_entries is assumed) */
 } GtokGraphBatch;
 
 /* graph-token rule set (docs/synthetic_data.md:46-68, docs/models.md:22) with the
@@ -136,7 +139,15 @@ typedef struct GtokSentCfg {
   int32_t edge_label_shift;  /* edge label token = edge_idx_offset + attr + shift */
   int32_t remap_zinc;        /* apply remap_zinc_tokens (train_agtt.py:171-244) */
   int32_t append_query;      /* append [idx_offset+N, idx_offset+u, idx_offset+v] (:257-267) */
+  /* Decisions the reference leaves open (AutoGraph's source is not in its checkout; oracle/sent_oracle.py SentSpec
+   * holds the full list, tools/pin_autograph.py finds the setting that reproduces the real tokenizer).  0 = this
+   * repo's normative choice. */
+  int32_t restart_policy;    /* GTOK_SENT_RESTART_*: where a new segment starts when the walk is stuck */
+  int32_t bracket_order;     /* GTOK_SENT_BRACKET_*: order of the neighbourhood set between LADJ and RADJ */
 } GtokSentCfg;
+enum { GTOK_SENT_RESTART_OPEN_FIRST = 0, /* visited nodes that still have an unvisited neighbour, else unvisited nodes */
+       GTOK_SENT_RESTART_UNVISITED = 1   /* any unvisited node */ };
+enum { GTOK_SENT_BRACKET_VISIT_ASC = 0, GTOK_SENT_BRACKET_VISIT_DESC = 1 };
 
 /* Where the walk's random words come from (oracle/sent_oracle.py "pick"). */
 typedef struct GtokChoice {
@@ -285,6 +296,8 @@ typedef struct GtokPackedMolBatch {
                                 a canonical PyG edge_index - both directions, sorted by (src, dst), symmetric
                                 edge_attr - when only its src < dst half is kept; gtok/batch.py verifies that before
                                 it drops the other half).  The kernel then skips the dedupe.  0: any column list */
+  int32_t max_nodes_per_32;  /* as in GtokGraphBatch (0 = unknown) */
+  int32_t max_entries_per_32;
   int32_t reserved_;
 } GtokPackedMolBatch;
 GTOK_API int gtok_zinc_collate_packed(const GtokPackedMolBatch* batch, const GtokZincVocab* vocab, int64_t batch_size,
@@ -343,6 +356,25 @@ GTOK_API int gtok_batch_extents(const int32_t* row_len, const int64_t* batch_idx
 GTOK_API int gtok_pad_mask_batched(const int64_t* tok, const int64_t* row_start, const int32_t* row_len,
                           const int64_t* batch_idx, int64_t G, int64_t B, const int32_t* lmax,
                           const int64_t* xoff, int64_t pad_id, int64_t* X, uint8_t* attn, void* stream);
+
+/* Plumbing kernels (no torch op computes anything on the product path):
+ *      gtok_compact_rows: strided rows [num_rows, stride] + row_len -> ragged stream, row r at out[off[r] ..]
+ *      (off = gtok_scan_offsets(row_len)); the AGTT shim serves Graph2TrailTokenizer.__call__ results from it
+ *      (trainer/train_agtt.py:250).
+ *      gtok_segment_counts / gtok_gather_segments: gather the graphs idx[0..num_idx) of a batch (any order, repeats
+ *      allowed) into a new batch - TokenDataset over a shuffled / subset view of a PyG dataset (ds._indices).
+ *      cnt_out[i] = off[idx[i]+1] - off[idx[i]] (status |= 1 on an index outside [0, num_graphs)); the caller scans
+ *      cnt_out into dst_off and gathers every int32 array with gtok_gather_segments.
+ *      gtok_balance_order: order_out = graphs sorted by (nodes, CSR entries) inside windows of `window` (2..4096)
+ *      consecutive graphs (GtokCsrBatch.order: the 32 lanes of a warp then walk graphs of similar work). */
+GTOK_API int gtok_compact_rows(const int64_t* tok, int64_t stride, const int32_t* row_len, const int64_t* off,
+                               int64_t num_rows, int64_t* out, void* stream);
+GTOK_API int gtok_segment_counts(const int64_t* off, int64_t num_graphs, const int64_t* idx, int64_t num_idx,
+                                 int32_t* cnt_out, int32_t* status, void* stream);
+GTOK_API int gtok_gather_segments(const int32_t* src, const int64_t* src_off, int64_t num_graphs, const int64_t* idx,
+                                  const int64_t* dst_off, int64_t num_idx, int32_t* dst, void* stream);
+GTOK_API int gtok_balance_order(const int64_t* node_off, const int32_t* rowptr, int64_t num_graphs, int32_t window,
+                                int32_t* order_out, void* stream);
 
 /* K6   the steps around the path: consumer-side query positions, task labels, and an
  *      on-device Erdos-Renyi generator for fully device-side benchmarks.

@@ -96,6 +96,49 @@ class SentConfig:
     edge_label_shift: int = 0
 
 
+@dataclass(frozen=True)
+class SentSpec:
+    """The decisions the reference leaves open (AutoGraph's source is not in the checkout): every field is a switch,
+    the defaults are this repo's normative choice.  tools/pin_autograph.py runs the real tokenizer when it can be
+    imported, searches this space for the one setting that reproduces ALL its outputs (fit_spec) and writes
+    tests/golden/sent_autograph.json; GtokSentCfg carries the same switches for the kernels (`restart`,
+    `bracket_order`, `edge_label_shift`; the others are oracle-only until a pin says they are needed).
+
+    restart          where a new segment starts when the walk is stuck
+                       "open_first"      visited nodes that still have an unvisited neighbour, else unvisited nodes
+                       "unvisited"       any unvisited node
+                       "frontier_first"  unvisited nodes with a visited neighbour, else any unvisited node
+    bracket_order    order of the neighbourhood set: "visit_asc" | "visit_desc" | "node_asc"
+    bracket_prev     the trail predecessor is listed in the bracket as well
+    node_label_first node-type token BEFORE the node index token (labeled mode)
+    edge_label_after edge-type token AFTER the node index it leads to
+    revisit_closes   docs/models/embed_gtt.md:17-19,64 reading ("<sos> 0 1 2 3 0"): no brackets at all - the trail
+                     follows ANY uncovered edge and re-emits the index of a visited node it returns to
+    """
+    restart: str = "open_first"
+    bracket_order: str = "visit_asc"
+    bracket_prev: bool = False
+    node_label_first: bool = False
+    edge_label_after: bool = False
+    revisit_closes: bool = False
+
+
+DEFAULT_SPEC = SentSpec()
+
+
+class NeedChoice(Exception):
+    """Raised by ScriptedWords when the script is exhausted: `count` options at this decision."""
+
+    def __init__(self, count: int):
+        super().__init__(count)
+        self.count = count
+
+
+def word_for(k: int, c: int) -> int:
+    """Smallest 32-bit word r with (r * c) >> 32 == k: the explicit-choice-stream encoding of 'option k of c'."""
+    return ((k << 32) + c - 1) // c
+
+
 class PhiloxWords:
     """word d of graph ``gid`` under ``seed``."""
 
@@ -151,46 +194,79 @@ def canonical_csr(num_nodes: int, src: Sequence[int], dst: Sequence[int],
 
 def sent_tokenize(num_nodes: int, rowptr: np.ndarray, col: np.ndarray, cfg: SentConfig,
                   word: Callable[[], int], x: Optional[Sequence[int]] = None,
-                  eattr: Optional[Sequence[int]] = None) -> np.ndarray:
-    """One graph -> int64 token sequence, per the SPEC in the module docstring."""
-    def pick(c: int) -> int:
-        return (word() * c) >> 32
+                  eattr: Optional[Sequence[int]] = None, spec: SentSpec = DEFAULT_SPEC) -> np.ndarray:
+    """One graph -> int64 token sequence, per the SPEC in the module docstring (spec = the open decisions)."""
+    out: List[int] = []
+    _sent_emit(out, num_nodes, rowptr, col, cfg, lambda c: (word() * c) >> 32, x, eattr, spec)
+    return np.asarray(out[: cfg.max_length], dtype=np.int64)
 
-    out: List[int] = [SOS]
+
+def _sent_emit(out: List[int], num_nodes: int, rowptr, col, cfg: SentConfig, pick: Callable[[int], int],
+               x, eattr, spec: SentSpec) -> None:
+    """Appends the untruncated sequence to `out` (the caller can read what was emitted so far when `pick` raises)."""
+    out.append(SOS)
     n = int(num_nodes)
-    if n > 0:
+    nbrs = lambda v: range(int(rowptr[v]), int(rowptr[v + 1]))
+    elab = lambda e: cfg.edge_idx_offset + int(eattr[e]) + cfg.edge_label_shift
+    if n > 0 and spec.revisit_closes:
+        _sent_revisit(n, rowptr, col, cfg, pick, x, eattr, spec, out)
+    elif n > 0:
         vis = [-1] * n
         nvis = 0
         cur = pick(n)
         prev = -1
+        pend = None                                   # edge label owed after the next node token (edge_label_after)
         while True:
-            lo, hi = int(rowptr[cur]), int(rowptr[cur + 1])
             if vis[cur] < 0:
                 vis[cur] = nvis
                 nvis += 1
-                out.append(cfg.idx_offset + vis[cur])
-                if cfg.labeled:
+                if cfg.labeled and spec.node_label_first:
                     out.append(cfg.node_idx_offset + int(x[cur]))
-                B = sorted((vis[int(col[e])], e) for e in range(lo, hi)
-                           if vis[int(col[e])] >= 0 and int(col[e]) != prev and int(col[e]) != cur)
+                out.append(cfg.idx_offset + vis[cur])
+                if cfg.labeled and not spec.node_label_first:
+                    out.append(cfg.node_idx_offset + int(x[cur]))
+                if pend is not None:
+                    out.append(pend)
+                    pend = None
+                B = [(vis[int(col[e])], int(col[e]), e) for e in nbrs(cur)
+                     if vis[int(col[e])] >= 0 and int(col[e]) != cur and (spec.bracket_prev or int(col[e]) != prev)]
+                if spec.bracket_order == "visit_asc":
+                    B.sort()
+                elif spec.bracket_order == "visit_desc":
+                    B.sort(reverse=True)
+                elif spec.bracket_order != "node_asc":
+                    raise ValueError(spec.bracket_order)
                 if B:
                     out.append(LADJ)
-                    for k, e in B:
-                        if cfg.labeled:
-                            out.append(cfg.edge_idx_offset + int(eattr[e]) + cfg.edge_label_shift)
+                    for k, _, e in B:
+                        if cfg.labeled and not spec.edge_label_after:
+                            out.append(elab(e))
                         out.append(cfg.idx_offset + k)
+                        if cfg.labeled and spec.edge_label_after:
+                            out.append(elab(e))
                     out.append(RADJ)
             else:
                 out.append(cfg.idx_offset + vis[cur])
-            C = [e for e in range(lo, hi) if vis[int(col[e])] < 0]
+            C = [e for e in nbrs(cur) if vis[int(col[e])] < 0]
             if C:
                 e = C[pick(len(C))]
                 if cfg.labeled:
-                    out.append(cfg.edge_idx_offset + int(eattr[e]) + cfg.edge_label_shift)
+                    if spec.edge_label_after:
+                        pend = elab(e)
+                    else:
+                        out.append(elab(e))
                 prev, cur = cur, int(col[e])
                 continue
-            R = [v for v in range(n) if vis[v] >= 0 and
-                 any(vis[int(col[e])] < 0 for e in range(int(rowptr[v]), int(rowptr[v + 1])))]
+            has_unvis = lambda v: any(vis[int(col[e])] < 0 for e in nbrs(v))
+            has_vis = lambda v: any(vis[int(col[e])] >= 0 for e in nbrs(v))
+            if spec.restart == "open_first":
+                R = [v for v in range(n) if vis[v] >= 0 and has_unvis(v)]
+            elif spec.restart == "frontier_first":
+                R = [v for v in range(n) if vis[v] < 0 and has_vis(v)]
+            elif spec.restart == "unvisited":
+                R = []
+            else:
+                raise ValueError(spec.restart)
             if not R:
                 R = [v for v in range(n) if vis[v] < 0]
             if not R:
@@ -199,7 +275,117 @@ def sent_tokenize(num_nodes: int, rowptr: np.ndarray, col: np.ndarray, cfg: Sent
             cur = R[pick(len(R))]
             prev = -1
     out.append(EOS)
-    return np.asarray(out[: cfg.max_length], dtype=np.int64)
+
+
+def _sent_revisit(n, rowptr, col, cfg, pick, x, eattr, spec, out) -> None:
+    """SentSpec.revisit_closes: segments of a plain random trail decomposition - every step follows a uniformly chosen
+    uncovered incident edge (to a visited node as well, whose index is re-emitted); stuck -> RESET at a visited node
+    with an uncovered edge, else at an unvisited node."""
+    vis = [-1] * n
+    nvis = 0
+    covered = set()
+    key = lambda v, e: (min(v, int(col[e])), max(v, int(col[e])))
+    unc = lambda v: [e for e in range(int(rowptr[v]), int(rowptr[v + 1])) if key(v, e) not in covered]
+    cur = pick(n)
+    while True:
+        first = vis[cur] < 0
+        if first:
+            vis[cur] = nvis
+            nvis += 1
+        if cfg.labeled and first and spec.node_label_first:
+            out.append(cfg.node_idx_offset + int(x[cur]))
+        out.append(cfg.idx_offset + vis[cur])
+        if cfg.labeled and first and not spec.node_label_first:
+            out.append(cfg.node_idx_offset + int(x[cur]))
+        C = unc(cur)
+        if C:
+            e = C[pick(len(C))]
+            covered.add(key(cur, e))
+            if cfg.labeled:
+                out.append(cfg.edge_idx_offset + int(eattr[e]) + cfg.edge_label_shift)
+            cur = int(col[e])
+            continue
+        R = [v for v in range(n) if vis[v] >= 0 and unc(v)]
+        if not R:
+            R = [v for v in range(n) if vis[v] < 0]
+        if not R:
+            return
+        out.append(RESET)
+        cur = R[pick(len(R))]
+
+
+def fit_choice_stream(num_nodes: int, rowptr, col, cfg: SentConfig, target: Sequence[int], x=None, eattr=None,
+                      spec: SentSpec = DEFAULT_SPEC, max_runs: int = 100_000) -> Optional[List[int]]:
+    """Is `target` a sequence this specification can produce?  Depth-first search over the decisions (start node,
+    k-th unvisited neighbour, restart node): a partial script of options is extended one decision at a time and
+    abandoned as soon as the tokens it forces leave the target.  -> the explicit choice stream (32-bit words, GtokChoice
+    format) that replays `target` through sent_tokenize / the CUDA kernels, or None if no stream exists.  Needs nothing
+    from the implementation that produced `target` but its output - which is what makes an AutoGraph pin possible
+    without touching its random number generator (tools/pin_autograph.py)."""
+    target = [int(t) for t in target]
+    truncated = len(target) >= cfg.max_length
+    runs = 0
+
+    def run(script: List[int]):
+        out: List[int] = []
+        counts: List[int] = []
+        it = iter(script)
+
+        def pick(c: int) -> int:
+            k = next(it, None)
+            if k is None:
+                raise NeedChoice(c)
+            counts.append(c)
+            return k
+        try:
+            _sent_emit(out, num_nodes, rowptr, col, cfg, pick, x, eattr, spec)
+            return out, None, counts
+        except NeedChoice as nc:
+            return out, nc.count, counts
+
+    stack: List[List[int]] = [[]]
+    while stack:
+        script = stack.pop()
+        runs += 1
+        if runs > max_runs:
+            raise RuntimeError("fit_choice_stream: search budget exhausted")
+        out, need, counts = run(script)
+        m = min(len(out), len(target))
+        if out[:m] != target[:m]:
+            continue
+        if need is None:
+            if out[: cfg.max_length] != target:
+                continue
+        elif not (truncated and len(out) >= len(target)):     # (a truncated target is settled once it is covered:
+            if len(out) > len(target):                          #  words past the script read as 0, any option will do)
+                continue
+            stack.extend(script + [k] for k in range(need - 1, -1, -1))
+            continue
+        return [word_for(k, c) for k, c in zip(script, counts)]
+    return None
+
+
+def fit_spec(samples: Sequence[dict], cfg_of: Callable[[dict], SentConfig], candidates: Optional[Sequence[SentSpec]] = None):
+    """samples: dicts with n, rowptr, col, tokens (+ x, eattr).  -> [(spec, streams)] for every candidate specification
+    under which EVERY sample has a choice stream (streams[i] replays samples[i])."""
+    if candidates is None:
+        candidates = [SentSpec(r, b, p, nf, ea, rv)
+                      for rv in (False, True) for r in ("open_first", "unvisited", "frontier_first")
+                      for b in ("visit_asc", "visit_desc", "node_asc") for p in (False, True)
+                      for nf in (False, True) for ea in (False, True)
+                      if not (rv and (r != "open_first" or b != "visit_asc" or p or ea))]
+    good = []
+    for spec in candidates:
+        streams = []
+        for smp in samples:
+            st = fit_choice_stream(smp["n"], smp["rowptr"], smp["col"], cfg_of(smp), smp["tokens"], smp.get("x"),
+                                   smp.get("eattr"), spec)
+            if st is None:
+                break
+            streams.append(st)
+        else:
+            good.append((spec, streams))
+    return good
 
 
 def sent_decode(tokens: Sequence[int], cfg: SentConfig):

@@ -23,13 +23,13 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_struct_sizes():
     from gtok import _lib
-    assert _lib.version() == 100
+    assert _lib.version() == 101
     # layout guards: these sizes are what nvcc sees for the structs in gtok.h (x86-64 SysV)
-    assert ctypes.sizeof(_lib.GraphBatchC) == 80
+    assert ctypes.sizeof(_lib.GraphBatchC) == 88
     assert ctypes.sizeof(_lib.IbttRulesC) == 56
     assert ctypes.sizeof(_lib.ZincVocabC) == 120
     assert ctypes.sizeof(_lib.CsrBatchC) == 96
-    assert ctypes.sizeof(_lib.SentCfgC) == 32
+    assert ctypes.sizeof(_lib.SentCfgC) == 40
     assert ctypes.sizeof(_lib.ChoiceC) == 32
     assert ctypes.sizeof(_lib.ErSpecC) == 72 and _lib.ErSpecC.seed.offset == 56
 
@@ -56,7 +56,7 @@ def test_no_cpu_fallback():
 def test_header_is_plain_c():
     """include/gtok.h is the drop-in boundary: it must compile as C (no C++-only constructs, no torch types)."""
     import subprocess
-    src = "#include \"gtok.h\"\nint main(void) { return GTOK_VERSION == 100 ? 0 : 1; }\n"
+    src = "#include \"gtok.h\"\nint main(void) { return GTOK_VERSION == 101 ? 0 : 1; }\n"
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
                        input=src, text=True, capture_output=True)
     assert r.returncode == 0, r.stderr
@@ -78,5 +78,5 @@ def test_bench_reference_arm_contract():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "graphs/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0

@@ -112,3 +112,71 @@ def test_engine_build_csr_matches_oracle_on_cpu():
     c2 = engine.build_csr(z)
     assert int(c2.rowptr[-1]) == z.src.numel()            # already canonical: both directions, unique
     assert torch.equal(c2.col, z.dst) and torch.equal(c2.eattr, z.edge_attr)
+
+
+# ---- the open decisions as switches + the fit search behind tools/pin_autograph.py ------------------------------------
+def _samples(spec, labeled, count, seed, nmax=14):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(count):
+        n = int(rng.integers(1, nmax))
+        src, dst, attr, x = _random_graph(rng, n, float(rng.uniform(0.1, 0.5)), labeled)
+        rp, col, ea = S.canonical_csr(n, src, dst, attr)
+        cfg = S.SentConfig(6, 6 + 20, 6 + 20 + 9, 10_000, labeled)
+        t = S.sent_tokenize(n, rp, col, cfg, S.PhiloxWords(seed, i), x=x, eattr=ea, spec=spec)
+        out.append({"n": n, "rowptr": rp, "col": col, "x": x, "eattr": ea, "tokens": t.tolist(), "cfg": cfg})
+    return out
+
+
+@pytest.mark.parametrize("spec", [S.SentSpec(), S.SentSpec(restart="unvisited", bracket_order="visit_desc"),
+                                  S.SentSpec(restart="frontier_first", bracket_order="node_asc", bracket_prev=True,
+                                             node_label_first=True, edge_label_after=True),
+                                  S.SentSpec(revisit_closes=True)])
+@pytest.mark.parametrize("labeled", [False, True])
+def test_fit_choice_stream_recovers_a_replayable_stream(spec, labeled):
+    """Whatever produced a sequence, if the specification CAN produce it the search finds an explicit choice stream
+    that replays it word for word (the pin mechanism: no access to the producer's RNG needed)."""
+    for smp in _samples(spec, labeled, 25, seed=3, nmax=10 if spec.revisit_closes else 14):
+        st = S.fit_choice_stream(smp["n"], smp["rowptr"], smp["col"], smp["cfg"], smp["tokens"], smp["x"], smp["eattr"], spec)
+        assert st is not None
+        again = S.sent_tokenize(smp["n"], smp["rowptr"], smp["col"], smp["cfg"], S.StreamWords(st), smp["x"], smp["eattr"], spec)
+        assert again.tolist() == smp["tokens"]
+    # a sequence the specification cannot produce has no stream
+    smp = _samples(spec, labeled, 1, seed=9, nmax=7)[0]
+    bad = list(smp["tokens"])
+    bad[1] += 1                                            # first node token is always index 0
+    assert S.fit_choice_stream(smp["n"], smp["rowptr"], smp["col"], smp["cfg"], bad, smp["x"], smp["eattr"], spec) is None
+
+
+def test_fit_choice_stream_truncated_target():
+    spec = S.SentSpec()
+    rng = np.random.default_rng(5)
+    src, dst, _, _ = _random_graph(rng, 12, 0.4, False)
+    rp, col, _ = S.canonical_csr(12, src, dst)
+    cfg = S.SentConfig(max_length=17)
+    t = S.sent_tokenize(12, rp, col, cfg, S.PhiloxWords(1, 0), spec=spec)
+    assert len(t) == 17
+    st = S.fit_choice_stream(12, rp, col, cfg, t, spec=spec)
+    assert S.sent_tokenize(12, rp, col, cfg, S.StreamWords(st), spec=spec).tolist() == t.tolist()
+
+
+def test_fit_spec_identifies_the_producing_specification():
+    """Given only outputs, the candidate search keeps the specification that produced them and rejects the default
+    when the producer differs from it (what tools/pin_autograph.py does with AutoGraph's outputs)."""
+    truth = S.SentSpec(restart="frontier_first", bracket_order="visit_desc", edge_label_after=True)
+    smp = _samples(truth, True, 30, seed=11)
+    good = S.fit_spec(smp, lambda s_: s_["cfg"])
+    specs = [g[0] for g in good]
+    assert truth in specs and S.SentSpec() not in specs
+    for spec, streams in good:
+        for s_, st in zip(smp, streams):
+            assert S.sent_tokenize(s_["n"], s_["rowptr"], s_["col"], s_["cfg"], S.StreamWords(st), s_["x"], s_["eattr"],
+                                   spec).tolist() == s_["tokens"]
+
+
+def test_revisit_mode_matches_the_reference_doc_illustration():
+    """docs/models/embed_gtt.md:17-19,64 draws the 4-cycle as '<sos> 0 1 2 3 0': under revisit_closes the walk returns
+    to the start node and re-emits its index (the default specification carries that edge in a bracket instead)."""
+    rp, col, _ = S.canonical_csr(4, [0, 1, 2, 0], [1, 2, 3, 3])
+    t = S.sent_tokenize(4, rp, col, S.SentConfig(), S.PhiloxWords(0, 0), spec=S.SentSpec(revisit_closes=True)).tolist()
+    assert t == [S.SOS, 6, 7, 8, 9, 6, S.EOS]

@@ -37,6 +37,9 @@ vocab = {t: i for i, t in enumerate(["<bos>", "<eos>", "<pad>", "<unk>", "<q>", 
                                     [str(k) for k in range(37)] + ["X", "unknown"])}
 mn, me = int(gb.num_nodes().max()), int(gb.num_entries().max())
 bc = engine._batch_c(gb, mn, me)
+if os.environ.get("GTOK_GROUP_BOUNDS", "1") != "0":
+    bc.max_nodes_per_32, bc.max_entries_per_32 = engine.group_bounds(gb.node_off), engine.group_bounds(gb.edge_off)
+    print("group bounds", bc.max_nodes_per_32, bc.max_entries_per_32)
 zv, tbl = engine.zinc_vocab_c(vocab, 1024, 1024, mn, dev)
 n_total, e_total = gb.x.numel(), gb.src.numel()
 cap = 2 * n_total + 4 * e_total + 4 * G + 2
@@ -82,7 +85,8 @@ print(f"zinc_collate (fused tokenize+pad/mask, B={B}): {ms:.4f} ms  {G / ms / 1e
 from gtok.batch import PackedGraphBatch
 pkb = PackedGraphBatch.from_batch(gb.to("cpu"), fuse_columns=True)
 col16, x8 = pkb.col16.to(dev), pkb.x.to(dev)
-pk = _lib.PackedMolBatchC(G, _ptr(gb.node_off), _ptr(gb.edge_off), _ptr(col16), _ptr(x8), max(mn, pkb.max_id + 1), me)
+pk = _lib.PackedMolBatchC(G, _ptr(gb.node_off), _ptr(gb.edge_off), _ptr(col16), _ptr(x8), max(mn, pkb.max_id + 1), me, 0,
+                          bc.max_nodes_per_32, bc.max_entries_per_32, 0)
 
 
 def fused_packed():
