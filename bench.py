@@ -379,6 +379,65 @@ def run_extras(dev, G, peak):
     return out
 
 
+def run_sharded_sent(dev, rank, world, total, peak):
+    """BASELINE configs[3]: labeled SENT + fused remap + collate_fn over `total` ZINC-shaped graphs sharded by index
+    across the ranks (STRONG scaling: total fixed).  No collective on the data path; Philox words keyed by the GLOBAL
+    graph id, so the trails do not depend on the rank count.  Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from gtok import engine, synth
+    G = total // world
+    CH, STRIDE = 1_250_000, 384                     # graphs per launch (bounds the [G, stride] trail buffer: 3.8 GB)
+    chunks = []
+    for c0 in range(0, G, CH):
+        n = min(CH, G - c0)
+        gb = synth.zinc_shaped(n, seed=1000 * rank + c0 // CH, device=dev)
+        chunks.append((c0, n, engine.build_csr(gb)))
+        del gb
+    nmax = max(c.max_nodes for _, _, c in chunks)
+    cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 9, max_length=STRIDE,
+                            labeled=True, remap_zinc=True)
+    m = min(CH, G)
+    buf = torch.empty((m, STRIDE), dtype=torch.int64, device=dev)
+    row_start = torch.arange(m, device=dev, dtype=torch.int64) * STRIDE
+    Xc, Ac = torch.empty(m * 200, dtype=torch.int64, device=dev), torch.empty(m * 200, dtype=torch.bool, device=dev)
+
+    def epoch(seed):
+        toks = 0
+        for c0, n, csr in chunks:
+            _, ln = engine.tokenize_sent(csr, cfg, seed=seed, graph_id_base=rank * G + c0, out=buf[:n], stride=STRIDE)
+            engine.pad_mask_epoch(buf.view(-1), row_start[:n], ln, 5, BATCH, X=Xc, attn=Ac)
+            toks = toks + ln.sum()
+        return toks
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    epoch(0)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 3
+    a.record()
+    for s_ in range(steps):
+        toks = epoch(1 + s_)
+    b.record()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b) / steps, float(toks)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, tokens = float(tm[0]), float(t[1])
+    else:
+        ms, tokens = float(t[0]), float(t[1])
+    del buf, Xc, Ac, chunks
+    return {"workload": f"AGTT SENT (labeled + fused remap_zinc_tokens) + collate_fn of every batch of {BATCH}: {G * world} "
+                        f"ZINC-shaped graphs sharded by index over {world} GPU(s) (BASELINE configs[3])",
+            "n_gpus": world, "graphs_per_gpu": G, "ms_per_epoch": ms, "graphs_per_s": G * world / ms * 1e3,
+            "tokens_per_s": tokens / ms * 1e3, "scaling": "strong"}
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -417,6 +476,8 @@ def run_gpu(args):
     from gtok.pipeline import ZincIbttPipeline
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (gtok has no CPU fallback)"
+    from gtok import numa
+    placement = numa.bind_to_gpu_node(local) if not args.no_numa_bind else numa.topology(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -532,6 +593,9 @@ def run_gpu(args):
     extras = None
     if world == 1 and not args.no_extras:
         extras = run_extras(dev, args.graphs, peak_gbs())
+    if not args.no_extras:
+        sh = run_sharded_sent(dev, rank, world, args.sharded_sent_graphs, peak_gbs())
+        extras = dict(extras or {}, sent_zinc_10M_sharded=sh)
     names = list(pre)
     t = torch.tensor([ms, e2e_ms] + [pre[n][0] for n in names], dtype=torch.float64, device=dev)
     if world > 1:
@@ -609,6 +673,7 @@ def run_gpu(args):
             "step_roofline": {"algo_bytes": step_algo, "GBps": step_algo / step_s / 1e9, "frac": step_algo / step_s / 1e9 / peak,
                               "note": "fused-minimum bytes (graph reads + 9*B*Lmax writes) / whole-step time"},
             "clocks": sampler.summary(),
+            "host_placement": {k: placement.get(k) for k in ("gpu_numa_node", "numa_nodes", "node_cpulist", "bound")},
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
@@ -647,8 +712,11 @@ def main():
     ap.add_argument("--cpu-graphs-per-core", type=int, default=40000,
                     help="CPU arm sample: graphs per host core per step (default: ~25 core-seconds of reference work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="keep the launcher's CPU affinity (default: bind each rank to its GPU's NUMA node)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pieces the int64 PyG tensors travel in (copy / narrow overlap)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (graph-token IBTT, SENT)")
+    ap.add_argument("--sharded-sent-graphs", type=int, default=10_000_000,
+                    help="total graphs of the strong-scaling SENT extra (BASELINE configs[3]), split over the ranks")
     ap.add_argument("--zinc-fused", type=int, default=-1, help="-1 auto, 0 three-kernel path, 1 fused single pass")
     ap.add_argument("--zinc-mode", default="auto", choices=["auto", "collate", "ragged"],
                     help="collate: molecules -> padded batches in one kernel; ragged: tokenizer + K4 collate kernels")

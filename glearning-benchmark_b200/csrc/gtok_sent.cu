@@ -19,6 +19,8 @@
 // Random words: Philox-4x32-10 keyed by the seed, counter = (global graph id,
 // decision >> 2), or an explicit per-graph choice stream (deterministic replay).
 // Algorithmic bytes / graph: 4(N+1) + 4 nnz (CSR) [+4N + 4 nnz labels] + 8 L.
+#include <stdlib.h>
+
 #include "gtok_sent_common.cuh"
 
 namespace gtok {
@@ -493,6 +495,8 @@ static int sent_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const Gtok
 
 int sent_small_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
                         int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
+int sent_walk_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
+                       int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
 int sent_mid_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
                       int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
 int sent_big_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
@@ -535,9 +539,16 @@ extern "C" int gtok_sent_tokenize_ws(const GtokCsrBatch* csr, const GtokSentCfg*
   GTOK_REQUIRE((reinterpret_cast<uintptr_t>(tok_out) & 15) == 0, GTOK_EINVAL, "sent: tok_out must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   {
-    // graphs of at most 64 nodes: one thread per graph on 64-bit adjacency masks (gtok_sent_small.cu)
+    // graphs of at most 64 nodes, 64-bit adjacency masks: thread-per-graph walk, then warp-wide emission with a lane
+    // per event (gtok_sent_walk.cu); GTOK_SENT_SMALL=1 selects the one-phase kernel (gtok_sent_small.cu)
     bool handled = false;
-    int rc = sent_small_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);
+    static const int small_env = [] { const char* e = getenv("GTOK_SENT_SMALL"); return e ? atoi(e) : 2; }();
+    int rc = GTOK_OK;
+    if (small_env != 1) {
+      rc = sent_walk_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);
+      if (rc != GTOK_OK || handled) return rc;
+    }
+    rc = sent_small_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);
     if (rc != GTOK_OK || handled) return rc;
     // 65..256 nodes: the same scheme on 2 or 4 mask words (gtok_sent_mid.cu)
     rc = sent_mid_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);

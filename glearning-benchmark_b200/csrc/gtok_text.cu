@@ -194,3 +194,105 @@ extern "C" int gtok_text_edges(const uint8_t* text, const int64_t* text_off, int
   GTOK_CUDA_TRY(cudaGetLastError());
   return GTOK_OK;
 }
+
+// ---- ids -> text bytes (the other direction): ZINCTokenizationDataset items carry their text because the unchanged
+// trainer reads it to collect its vocabulary (trainer/train_ibtt.py:231-233, :364-369).  Rendering 220k molecules token
+// by token in Python is hot loop #3 of the reference path; here every token of the ragged id stream writes its word (+ one
+// blank) into one byte buffer, the host cuts an item's text out of it with one slice.
+//   gtok_detok_lengths  chars[i] = word_len[tok[i]] + 1   (then K0 scan -> char_off)
+//   gtok_detok_render   text[char_off[i] ..] = word(tok[i]) + ' '
+//   gtok_first_occurrence  first[id] = smallest i with tok[i] == id (UINT64_MAX: never) - the first-seen order of the
+//                          dynamic vocabulary tokens (extend_vocab_with_dynamic_tokens, zinc_vocab.py:154-179)
+namespace gtok {
+
+constexpr int kDetokThreads = 256;
+
+__global__ void __launch_bounds__(kDetokThreads)
+detok_lengths_kernel(const int64_t* __restrict__ tok, int64_t n, const int32_t* __restrict__ word_off, int32_t num_words,
+                     int32_t* __restrict__ chars) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long t = __ldcs(tok + i);
+    chars[i] = (t >= 0 && t < num_words) ? (__ldg(word_off + t + 1) - __ldg(word_off + t) + 1) : 2;   // unknown id: "? "
+  }
+}
+
+__global__ void __launch_bounds__(kDetokThreads)
+detok_render_kernel(const int64_t* __restrict__ tok, int64_t n, const uint8_t* __restrict__ words,
+                    const int32_t* __restrict__ word_off, int32_t num_words, const int64_t* __restrict__ char_off,
+                    uint8_t* __restrict__ text) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long t = __ldcs(tok + i);
+    uint8_t* __restrict__ dst = text + __ldg(char_off + i);
+    if (t >= 0 && t < num_words) {
+      const int a = __ldg(word_off + t), b = __ldg(word_off + t + 1);
+      for (int j = a; j < b; ++j) dst[j - a] = __ldg(words + j);
+      dst[b - a] = ' ';
+    } else {
+      dst[0] = '?';
+      dst[1] = ' ';
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kDetokThreads)
+first_occurrence_kernel(const int64_t* __restrict__ tok, int64_t n, int32_t num_ids, unsigned long long* __restrict__ first) {
+  extern __shared__ unsigned long long s_first[];
+  for (int i = threadIdx.x; i < num_ids; i += blockDim.x) s_first[i] = ~0ull;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long t = __ldcs(tok + i);
+    if (t >= 0 && t < num_ids && s_first[t] > (unsigned long long)i) atomicMin(&s_first[t], (unsigned long long)i);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < num_ids; i += blockDim.x)
+    if (s_first[i] != ~0ull) atomicMin(first + i, s_first[i]);
+}
+
+}  // namespace gtok
+
+extern "C" int gtok_detok_lengths(const int64_t* tok, int64_t num_tokens, const int32_t* word_off, int32_t num_words,
+                                  int32_t* chars_out, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(num_tokens >= 0 && num_words >= 0, GTOK_EINVAL, "detok_lengths: negative size");
+  if (num_tokens == 0) return GTOK_OK;
+  GTOK_REQUIRE(tok && word_off && chars_out, GTOK_EINVAL, "detok_lengths: null pointer");
+  const int grid = persistent_grid(detok_lengths_kernel, kDetokThreads, 0, (num_tokens + kDetokThreads - 1) / kDetokThreads);
+  detok_lengths_kernel<<<grid, kDetokThreads, 0, (cudaStream_t)stream>>>(tok, num_tokens, word_off, num_words, chars_out);
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}
+
+extern "C" int gtok_detok_render(const int64_t* tok, int64_t num_tokens, const uint8_t* words, const int32_t* word_off,
+                                 int32_t num_words, const int64_t* char_off, uint8_t* text_out, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(num_tokens >= 0 && num_words >= 0, GTOK_EINVAL, "detok_render: negative size");
+  if (num_tokens == 0) return GTOK_OK;
+  GTOK_REQUIRE(tok && words && word_off && char_off && text_out, GTOK_EINVAL, "detok_render: null pointer");
+  const int grid = persistent_grid(detok_render_kernel, kDetokThreads, 0, (num_tokens + kDetokThreads - 1) / kDetokThreads);
+  detok_render_kernel<<<grid, kDetokThreads, 0, (cudaStream_t)stream>>>(tok, num_tokens, words, word_off, num_words, char_off,
+                                                                        text_out);
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}
+
+extern "C" int gtok_first_occurrence(const int64_t* tok, int64_t num_tokens, int32_t num_ids, uint64_t* first_out, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(num_tokens >= 0 && num_ids >= 0, GTOK_EINVAL, "first_occurrence: negative size");
+  GTOK_REQUIRE(num_ids <= 4096, GTOK_EUNSUPPORTED, "first_occurrence: at most 4096 distinct ids (got %d)", num_ids);
+  if (num_ids == 0) return GTOK_OK;
+  GTOK_REQUIRE(first_out != nullptr, GTOK_EINVAL, "first_occurrence: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  GTOK_CUDA_TRY(cudaMemsetAsync(first_out, 0xff, (size_t)num_ids * 8, st));
+  if (num_tokens == 0) return GTOK_OK;
+  GTOK_REQUIRE(tok != nullptr, GTOK_EINVAL, "first_occurrence: null tokens");
+  int64_t blocks = (num_tokens + kDetokThreads * 8 - 1) / (kDetokThreads * 8);
+  const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 4;
+  if (blocks > cap) blocks = cap;
+  first_occurrence_kernel<<<(unsigned)blocks, kDetokThreads, (size_t)num_ids * 8, st>>>(
+      tok, num_tokens, num_ids, reinterpret_cast<unsigned long long*>(first_out));
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}

@@ -54,6 +54,32 @@ gather_segments_kernel(const int32_t* __restrict__ src, const int64_t* __restric
   }
 }
 
+// rows + per-row tails -> new ragged stream: row r = (tok[off[r] .. off[r]+len[r]) ++ tail[r, :tail_len[r]])[:max_len].
+// new_len is computed by append_lengths_kernel, scanned by the caller into new_off.
+__global__ void __launch_bounds__(kUtilThreads)
+append_lengths_kernel(const int32_t* __restrict__ len, const int32_t* __restrict__ tail_len, int64_t rows, int max_len,
+                      int32_t* __restrict__ new_len) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) {
+    const int l = __ldg(len + r) + __ldg(tail_len + r);
+    new_len[r] = l < max_len ? l : max_len;
+  }
+}
+__global__ void __launch_bounds__(kUtilThreads)
+append_rows_kernel(const int64_t* __restrict__ tok, const int64_t* __restrict__ off, const int32_t* __restrict__ len,
+                   const int64_t* __restrict__ tail, int tail_stride, const int64_t* __restrict__ new_off, int64_t rows,
+                   int64_t* __restrict__ out) {
+  const int lane = lane_id();
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = w0; r < rows; r += nw) {
+    const int l = __ldg(len + r);
+    const int64_t d0 = __ldg(new_off + r);
+    const int nl = (int)(__ldg(new_off + r + 1) - d0);
+    const int64_t* __restrict__ src = tok + __ldg(off + r);
+    for (int p = lane; p < nl; p += kWarp) out[d0 + p] = p < l ? __ldg(src + p) : __ldg(tail + r * tail_stride + (p - l));
+  }
+}
+
 // one CTA per window of W <= 4096 consecutive graphs: bitonic sort of (key << 32 | local index) in shared memory
 constexpr int kBalanceThreads = 512;
 __global__ void __launch_bounds__(kBalanceThreads)
@@ -146,6 +172,30 @@ extern "C" int gtok_balance_order(const int64_t* node_off, const int32_t* rowptr
   const int64_t blocks = (num_graphs + window - 1) / window;
   balance_order_kernel<<<(unsigned)blocks, kBalanceThreads, (size_t)pow2 * 8, (cudaStream_t)stream>>>(node_off, rowptr, num_graphs,
                                                                                                      window, pow2, order_out);
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}
+
+extern "C" int gtok_ragged_append_lengths(const int32_t* row_len, const int32_t* tail_len, int64_t num_rows, int32_t max_len,
+                                          int32_t* new_len, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(num_rows >= 0 && max_len >= 0, GTOK_EINVAL, "ragged_append_lengths: negative size");
+  if (num_rows == 0) return GTOK_OK;
+  GTOK_REQUIRE(row_len && tail_len && new_len, GTOK_EINVAL, "ragged_append_lengths: null pointer");
+  append_lengths_kernel<<<(unsigned)((num_rows + kUtilThreads - 1) / kUtilThreads), kUtilThreads, 0, (cudaStream_t)stream>>>(
+      row_len, tail_len, num_rows, max_len, new_len);
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}
+
+extern "C" int gtok_ragged_append(const int64_t* tok, const int64_t* off, const int32_t* row_len, const int64_t* tail,
+                                  int32_t tail_stride, const int64_t* new_off, int64_t num_rows, int64_t* out, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(num_rows >= 0 && tail_stride >= 0, GTOK_EINVAL, "ragged_append: negative size");
+  if (num_rows == 0) return GTOK_OK;
+  GTOK_REQUIRE(off && row_len && new_off && out, GTOK_EINVAL, "ragged_append: null pointer");
+  append_rows_kernel<<<util_grid(num_rows), kUtilThreads, 0, (cudaStream_t)stream>>>(tok, off, row_len, tail, tail_stride, new_off,
+                                                                                     num_rows, out);
   GTOK_CUDA_TRY(cudaGetLastError());
   return GTOK_OK;
 }

@@ -22,6 +22,8 @@ from collections import Counter
 from glob import glob
 from typing import Any, Dict, List, Optional, Tuple
 
+import weakref
+
 import torch
 from torch.utils.data import Dataset
 
@@ -376,7 +378,9 @@ def graph_of_text(text: str):
 
 
 # --------------------------------------------------------------------------- TokenDataset / collate
-_REGISTRY: Dict[int, "TokenDataset"] = {}      # host storage ptr -> dataset (lets collate find the device rows)
+# host storage ptr -> dataset (lets collate find the device rows).  Weak: a dataset (pinned copy + resident device rows)
+# lives exactly as long as the trainer holds it, and a recycled pointer can never resolve to a dead dataset.
+_REGISTRY: "weakref.WeakValueDictionary[int, TokenDataset]" = weakref.WeakValueDictionary()
 
 
 class TokenDataset(Dataset):
@@ -391,8 +395,6 @@ class TokenDataset(Dataset):
         from gtok.batch import GraphBatch
         if not torch.cuda.is_available():
             raise RuntimeError("TokenDataset needs a CUDA device: the gtok engine has no CPU fallback")
-        if not strip_label:
-            raise ValueError("strip_label=False is not supported by the CUDA tokenizers (the reference never uses it)")
         self.vocab, self.max_len = vocab, max_len
         self.device = torch.device(device or "cuda")
         kept, labels = [], []
@@ -430,6 +432,19 @@ class TokenDataset(Dataset):
                 gb = GraphBatch.from_lists([p[0] for p in parsed], [p[1] for p in parsed],
                                            queries=[p[3] for p in parsed] if task == "shortest_path" else None).to(self.device)
             self.ragged = engine.tokenize_ibtt(gb, vocab, task, max_len)
+        if not strip_label and kept:
+            # reference :478-482 without the strip: the tokens after <p> (label, <eos>) stay in the row.  The kernels emit
+            # the stripped rows; the tails - two or three ids per text - are looked up here and re-attached on the device
+            pad = vocab["<pad>"]
+            tails = []
+            for ex in kept:
+                t = ex["text"]
+                i = t.find("<p>")
+                tails.append([vocab.get(w, pad) for w in t[i + 3:].split()] if i >= 0 else [])
+            K = max(1, max(len(t) for t in tails))
+            tail = torch.tensor([t + [pad] * (K - len(t)) for t in tails], dtype=torch.int64, device=self.device)
+            tlen = torch.tensor([len(t) for t in tails], dtype=torch.int32, device=self.device)
+            self.ragged = engine.ragged_append(self.ragged, tail, tlen, max_len)
         host = torch.empty(self.ragged.tokens.numel(), dtype=torch.int64).pin_memory()
         host.copy_(self.ragged.tokens)
         lens = self.ragged.lengths.cpu().tolist()

@@ -2,10 +2,12 @@
 
 ``ZINCTokenizationDataset`` keeps the reference constructor and item contract
 (``ds[i] -> {'text','label','graph_id'}``, reference :63-70, :197-227).  The item's
-text is rendered on the host only because the unchanged trainer reads it to build
-its vocabulary (trainer/train_ibtt.py:364-369); the token ids themselves come from
-the K2 CUDA kernels when ``TokenDataset`` (data_loader.py) sees the hidden
-``_zinc`` handle each item carries - the text is never parsed back.
+text exists only because the unchanged trainer reads it to build its vocabulary
+(trainer/train_ibtt.py:364-369): all texts are rendered at once on the GPU (K2 ids ->
+gtok_detok_render) and an item is one slice of that buffer; ``dynamic_tokens()`` gives
+the same token set without any text.  The token ids themselves come from the K2 CUDA
+kernels when ``TokenDataset`` (data_loader.py) sees the hidden ``_zinc`` handle each
+item carries - the text is never parsed back.
 """
 from __future__ import annotations
 
@@ -77,14 +79,85 @@ class ZINCTokenizationDataset(Dataset):
         toks += ["<q>", "regression", "<p>", _label_token(label), "<eos>"]
         return " ".join(toks)
 
+    # ---- all texts at once: tokenized and rendered on the GPU, items cut out of one byte buffer --------
+    _RENDER_WORDS = ["<bos>", "<eos>", "<pad>", "<unk>", "<q>", "<p>", "<atom>", "<bond>"] + list(ATOM_TYPE_LIST) + \
+        list(BOND_TYPE_LIST) + ["regression"]                        # the fixed vocabulary's ids 0..21 (zinc_vocab.py:35-78)
+
+    def _bulk(self):
+        """Every molecule's stripped token row (`<bos> ... <q> regression <p>`) from the K2 kernel under a private
+        rendering vocabulary, turned into text bytes on the device; label tokens formatted in one vectorised pass.
+        What `[ds[i] for i in range(len(ds))]` (trainer/train_ibtt.py:231-233) costs in the reference - one .item() per
+        atom and bond - becomes three kernels and one slice per item."""
+        st = getattr(self, "_bulk_state", None)
+        if st is not None:
+            return st
+        import numpy as np
+        from gtok import engine
+        gb = self.graph_batch
+        G = gb.num_graphs
+        top = 0
+        if gb.src.numel():
+            top = max(int(gb.src.max()), int(gb.dst.max())) + 1
+        words = self._RENDER_WORDS + [str(k) for k in range(max(top, 1))] + ["X", "unknown"]
+        rv = {w_: i for i, w_ in enumerate(words)}
+        big = 1 << 24
+        rag = engine.tokenize_zinc(gb.to("cuda"), rv, big, item_max_len=big)
+        buf, row_off = engine.render_texts(rag, words)
+        y = gb.y.reshape(-1).to(torch.float32).to(torch.float64).numpy() if gb.y is not None else np.zeros(G)
+        lab = np.char.mod("val_%.2f", y)
+        lab = np.char.replace(np.char.replace(lab, ".", "_"), "-", "neg")              # reference :192
+        st = {"buf": buf, "row_off": row_off, "ntok": rag.lengths.cpu().tolist(), "lab": lab.tolist(), "y": y.tolist(),
+              "rag": rag, "words": words}
+        self._bulk_state = st
+        return st
+
+    def dynamic_tokens(self, known=()):
+        """The tokens of this dataset's texts that are not in the fixed vocabulary (node-index strings, 'X', 'unknown',
+        the val_* labels), in order of first appearance - what the trainer's loop over every token of every text collects
+        (trainer/train_ibtt.py:364-369; there into a set, whose order is arbitrary - SURVEY C5 - here deterministic).
+        Computed from the device-resident ids (gtok_first_occurrence), labels from the formatted label column."""
+        import numpy as np
+        from gtok import engine
+        st = self._bulk()
+        rag, words = st["rag"], st["words"]
+        nfix = len(self._RENDER_WORDS)
+        first = engine.first_occurrence(rag.tokens, len(words)).cpu().numpy()
+        off = rag.offsets.cpu().numpy()
+        ev = []
+        for i in range(nfix, len(words)):
+            if first[i] >= 0:
+                ev.append((int(np.searchsorted(off, first[i], side="right") - 1), 0, int(first[i]), words[i]))
+        lab = np.asarray(st["lab"])
+        if lab.size:
+            _, idx = np.unique(lab, return_index=True)
+            ev += [(int(i), 1, 0, str(lab[i])) for i in idx]
+        seen = set(known)
+        out = []
+        for _, _, _, tok in sorted(ev):
+            if tok not in seen:
+                seen.add(tok)
+                out.append(tok)
+        return out
+
     def __getitem__(self, idx):
-        data = self.zinc_dataset[idx]
-        label = data.y.item()
-        toks = self.tokenize_molecule(data, label).split()
-        if len(toks) > self.max_len:                                  # reference :216-221
-            toks = toks[:self.max_len - 1] + ['<eos>']
-        return {'text': " ".join(toks), 'label': label, 'graph_id': f"zinc_{self.split}_{idx}",
-                '_zinc': (self, int(idx))}
+        if idx < 0:
+            idx += len(self)
+        if torch.cuda.is_available():
+            st = self._bulk()
+            a, b = st["row_off"][idx], st["row_off"][idx + 1]
+            text = st["buf"][a:b - 1].decode("ascii") + " " + st["lab"][idx] + " <eos>"
+            label = st["y"][idx]
+            if st["ntok"][idx] + 2 > self.max_len:                        # reference :216-221 (rare: max_len below the row)
+                toks = text.split()
+                text = " ".join(toks[:self.max_len - 1] + ['<eos>'])
+        else:                                                            # no device: the per-item host rendering (text only -
+            data = self.zinc_dataset[idx]                                # TokenDataset still needs CUDA for the ids)
+            label = data.y.item()
+            toks = self.tokenize_molecule(data, label).split()
+            if len(toks) > self.max_len:
+                toks = toks[:self.max_len - 1] + ['<eos>']
+            text = " ".join(toks)
+        return {'text': text, 'label': label, 'graph_id': f"zinc_{self.split}_{idx}", '_zinc': (self, int(idx))}
 
 
 def collate_zinc_batch(batch, pad_id):

@@ -83,6 +83,9 @@ PROTOTYPES = {
     "gtok_pyg_narrow": (C.c_int, [vp, i64, vp, vp, vp]),
     "gtok_text_scan": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp, vp]),
     "gtok_text_edges": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]),
+    "gtok_detok_lengths": (C.c_int, [vp, i64, vp, i32, vp, vp]),
+    "gtok_detok_render": (C.c_int, [vp, i64, vp, vp, i32, vp, vp, vp]),
+    "gtok_first_occurrence": (C.c_int, [vp, i64, i32, vp, vp]),
     "gtok_vocab_histogram": (C.c_int, [C.POINTER(GraphBatchC), i32, i32, vp, vp, vp]),
     "gtok_ibtt_lengths": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(IbttRulesC), vp, vp]),
     "gtok_scan_workspace_bytes": (C.c_size_t, [i64]),
@@ -110,7 +113,13 @@ PROTOTYPES = {
     "gtok_compact_rows": (C.c_int, [vp, i64, vp, vp, i64, vp, vp]),
     "gtok_segment_counts": (C.c_int, [vp, i64, vp, i64, vp, vp, vp]),
     "gtok_gather_segments": (C.c_int, [vp, vp, i64, vp, vp, i64, vp, vp]),
+    "gtok_ragged_append_lengths": (C.c_int, [vp, vp, i64, i32, vp, vp]),
+    "gtok_ragged_append": (C.c_int, [vp, vp, vp, vp, i32, vp, i64, vp, vp]),
     "gtok_balance_order": (C.c_int, [vp, vp, i64, i32, vp, vp]),
+    "gtok_csrl_count": (C.c_int, [C.POINTER(GraphBatchC), i64, vp, vp]),
+    "gtok_csrl_table_bytes": (C.c_size_t, [i32]),
+    "gtok_csrl_sort": (C.c_int, [C.POINTER(GraphBatchC), i64, vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    "gtok_csrl_emit": (C.c_int, [C.POINTER(GraphBatchC), i64, vp, vp, vp, i64, vp, vp, vp, vp]),
     "gtok_find_token": (C.c_int, [vp, vp, vp, i64, i64, vp, i64, vp, vp]),
     "gtok_graph_labels": (C.c_int, [C.POINTER(CsrBatchC), vp, vp, vp, vp]),
     "gtok_er_sizes": (C.c_int, [C.POINTER(ErSpecC), i64, vp, vp, vp, vp, vp]),

@@ -531,21 +531,53 @@ def _build_csr_native(batch: GraphBatch, balance_window: int) -> CsrBatch:
     return _finish_csr(batch, rowptr, col, eattr, adj64, W, balance_window)
 
 
+def _build_csr_large(batch: GraphBatch, balance_window: int) -> CsrBatch:
+    """K7 for any graph size (csrc/gtok_csr_large.cu): degree upper bounds -> K0 scan -> scatter of (neighbour, column)
+    keys -> per-row sort + first-key-per-neighbour -> K0 scan -> col / eattr.  No adjacency bit rows (graphs > 256 nodes)."""
+    dev = batch.device
+    G = batch.num_graphs
+    Ntot = int(batch.node_off[-1]) if G else 0
+    max_nodes = int(batch.num_nodes().max()) if G else 1
+    bc = _batch_c(batch, max(1, max_nodes), 1)
+    deg_ub = torch.empty(Ntot, dtype=torch.int32, device=dev)
+    check(lib.gtok_csrl_count(C.byref(bc), Ntot, _ptr(deg_ub), _stream()))
+    rowptr_ub = scan_offsets(deg_ub)
+    total_ub = int(rowptr_ub[-1]) if Ntot else 0
+    entries = torch.empty(max(1, total_ub), dtype=torch.int64, device=dev)
+    cursor = torch.empty(max(1, Ntot), dtype=torch.int32, device=dev)
+    degree = torch.empty(Ntot, dtype=torch.int32, device=dev)
+    tbytes = lib.gtok_csrl_table_bytes(max(1, max_nodes))
+    table = torch.empty(tbytes, dtype=torch.uint8, device=dev)
+    check(lib.gtok_csrl_sort(C.byref(bc), Ntot, _ptr(rowptr_ub), _ptr(cursor), _ptr(entries), _ptr(degree), _ptr(table), tbytes,
+                             _stream()))
+    rowptr64 = scan_offsets(degree)
+    nnz = int(rowptr64[-1]) if Ntot else 0
+    if nnz >= 2 ** 31:
+        raise ValueError("CSR with >= 2^31 entries: shard the dataset")
+    rowptr = torch.empty(Ntot + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    eattr = torch.empty(nnz, dtype=torch.int32, device=dev) if batch.edge_attr is not None else None
+    check(lib.gtok_csrl_emit(C.byref(bc), Ntot, _ptr(rowptr_ub), _ptr(entries), _ptr(rowptr64), nnz, _ptr(rowptr), _ptr(col),
+                             _ptr(eattr), _stream()))
+    return _finish_csr(batch, rowptr, col, eattr, None, 1, balance_window)
+
+
 def build_csr(batch: GraphBatch, balance_window: int = 0, native: Optional[bool] = None) -> CsrBatch:
     """edge_index (any orientation, duplicates allowed) -> canonical undirected CSR (+ adjacency bit rows up to 256
     nodes per graph).  One-off ingest per dataset (what to_undirected/coalesce does inside AutoGraph per call).  The
     label of {u,v} is the edge_attr of its FIRST directed entry in caller order (oracle: canonical_csr).
-    Graphs of at most 256 nodes: library kernels (K7, `native`); larger graphs: a sort-based build with torch ops
-    (plumbing, not the hot path).  native=False forces the torch build (tests compare the two)."""
+    Library kernels on the device (K7: adjacency bit rows up to 256 nodes per graph, csrc/gtok_csr.cu; per-row sort of
+    (neighbour, column) keys beyond, csrc/gtok_csr_large.cu).  native=False is the sort-based reference build with
+    torch ops that the tests compare against (and what host tensors get)."""
     dev = batch.device
     G = batch.num_graphs
     max_nodes_ = int(batch.num_nodes().max()) if G else 1
     if native is None:
-        native = max_nodes_ <= 256 and batch.node_off.is_cuda        # (host tensors: the torch build, used by CPU tests)
+        native = batch.node_off.is_cuda                              # (host tensors: the torch build, used by CPU tests)
     if native:
         _require_cuda(batch.node_off, batch.src)
         if max_nodes_ > 256:
-            raise ValueError("the native CSR build covers graphs of at most 256 nodes")
+            return _build_csr_large(batch, balance_window)
         return _build_csr_native(batch, balance_window)
     E = batch.src.numel()
     n = batch.num_nodes()
@@ -618,8 +650,56 @@ def compact_rows(tok: torch.Tensor, lengths: torch.Tensor):
     off = scan_offsets(lengths)
     total = int(off[-1]) if G else 0
     out = torch.empty(total, dtype=torch.int64, device=tok.device)
-    check(lib.gtok_compact_rows(_ptr(tok), stride, _ptr(lengths), _ptr(off), G, _ptr(out), _stream()))
+    if total:
+        check(lib.gtok_compact_rows(_ptr(tok), stride, _ptr(lengths), _ptr(off), G, _ptr(out), _stream()))
     return out, off
+
+
+def render_texts(rag: "Ragged", words: Sequence[str]):
+    """Ragged ids -> texts, rendered on the GPU (gtok_detok_lengths -> K0 scan -> gtok_detok_render): one ASCII byte
+    buffer holding word(tok) + ' ' for every token, and the char offset of every ROW boundary.
+    -> (bytes, row_char_off list[G+1]); text of row g = buf[off[g]:off[g+1]-1]."""
+    _require_cuda(rag.tokens)
+    dev = rag.tokens.device
+    n = int(rag.tokens.numel())
+    enc = [w.encode("ascii") for w in words]
+    woff = torch.zeros(len(enc) + 1, dtype=torch.int32)
+    woff[1:] = torch.tensor([len(b) for b in enc], dtype=torch.int32).cumsum(0)
+    wbytes = torch.frombuffer(bytearray(b"".join(enc) or b" "), dtype=torch.uint8).to(dev)
+    woff_d = woff.to(dev)
+    chars = torch.empty(n, dtype=torch.int32, device=dev)
+    check(lib.gtok_detok_lengths(_ptr(rag.tokens), n, _ptr(woff_d), len(enc), _ptr(chars), _stream()))
+    coff = scan_offsets(chars)
+    total = int(coff[-1]) if n else 0
+    text = torch.empty(max(1, total), dtype=torch.uint8, device=dev)
+    check(lib.gtok_detok_render(_ptr(rag.tokens), n, _ptr(wbytes), _ptr(woff_d), len(enc), _ptr(coff), _ptr(text), _stream()))
+    row_off = coff[rag.offsets.clamp(max=n)].cpu().tolist()
+    return text[:total].cpu().numpy().tobytes(), row_off
+
+
+def first_occurrence(tokens: torch.Tensor, num_ids: int) -> torch.Tensor:
+    """first[id] = smallest index i with tokens[i] == id, -1 when the id never occurs (int64[num_ids], device)."""
+    _require_cuda(tokens)
+    first = torch.empty(num_ids, dtype=torch.int64, device=tokens.device)
+    check(lib.gtok_first_occurrence(_ptr(tokens), int(tokens.numel()), int(num_ids), _ptr(first), _stream()))
+    return first                                            # UINT64_MAX reads as -1
+
+
+def ragged_append(rag: "Ragged", tail: torch.Tensor, tail_len: torch.Tensor, max_len: int) -> "Ragged":
+    """row r = (row r ++ tail[r, :tail_len[r]])[:max_len] - TokenDataset(strip_label=False): the ids of the tokens after
+    <p> (label, <eos>) re-attached to the stripped rows the tokenizers produce."""
+    _require_cuda(rag.tokens, tail, tail_len)
+    G = rag.num_rows
+    dev = rag.tokens.device
+    new_len = torch.empty(G, dtype=torch.int32, device=dev)
+    check(lib.gtok_ragged_append_lengths(_ptr(rag.lengths), _ptr(tail_len), G, int(max_len), _ptr(new_len), _stream()))
+    new_off = scan_offsets(new_len)
+    total = int(new_off[-1]) if G else 0
+    out = torch.empty(total, dtype=torch.int64, device=dev)
+    if total:
+        check(lib.gtok_ragged_append(_ptr(rag.tokens), _ptr(rag.offsets), _ptr(rag.lengths), _ptr(tail), int(tail.shape[1]),
+                                     _ptr(new_off), G, _ptr(out), _stream()))
+    return Ragged(out, new_off, new_len)
 
 
 def gather_graphs(batch: GraphBatch, idx: torch.Tensor) -> GraphBatch:

@@ -207,6 +207,19 @@ GTOK_API int gtok_text_edges(const uint8_t* text, const int64_t* text_off, int64
                              const int32_t* task, const int64_t* edge_off, int32_t* src, int32_t* dst, int32_t* status,
                              void* stream);
 
+/* Render  ids -> text bytes, the inverse of the text ingest: ZINCTokenizationDataset items carry their TEXT because the
+ *      unchanged trainer reads it to collect its vocabulary (trainer/train_ibtt.py:231-233, :364-369;
+ *      zinc_dataset_indexbase.py:143-227 renders it per molecule with .item() loops).  words = the vocabulary's strings
+ *      back to back (ASCII), word_off int32[num_words+1].  gtok_detok_lengths: chars_out[i] = len(word(tok[i])) + 1; the
+ *      caller scans them into char_off (gtok_scan_offsets); gtok_detok_render writes word(tok[i]) + ' ' at
+ *      text_out + char_off[i].  gtok_first_occurrence: first_out[id] = smallest i with tok[i] == id (UINT64_MAX = never),
+ *      num_ids <= 4096 - the first-seen order of the dynamic vocabulary tokens (zinc_vocab.py:154-179). */
+GTOK_API int gtok_detok_lengths(const int64_t* tok, int64_t num_tokens, const int32_t* word_off, int32_t num_words,
+                                int32_t* chars_out, void* stream);
+GTOK_API int gtok_detok_render(const int64_t* tok, int64_t num_tokens, const uint8_t* words, const int32_t* word_off,
+                               int32_t num_words, const int64_t* char_off, uint8_t* text_out, void* stream);
+GTOK_API int gtok_first_occurrence(const int64_t* tok, int64_t num_tokens, int32_t num_ids, uint64_t* first_out, void* stream);
+
 /* K5   token statistics for build_vocab_from_texts (data_loader.py:451-463) computed from the graphs instead
  *      of from their serialized texts: for every node index k < num_bins, counts[k] = occurrences of the
  *      string str(k) over all graph-token texts (edge endpoints + node list + query nodes) and first[k] =
@@ -318,6 +331,22 @@ GTOK_API int gtok_csr_fill(const GtokGraphBatch* batch, int32_t adj_words, int64
                            const int64_t* rowptr64, int64_t nnz, int32_t* rowptr_out, int32_t* col_out,
                            int32_t* eattr_out, uint64_t* first_col_ws, void* stream);
 
+/* K7 (any size)  the same canonical CSR for graphs beyond 256 nodes (up to the 32767 the SENT kernels accept), library
+ *      kernels only: gtok_csrl_count writes degree upper bounds (repeated columns counted) -> the caller scans them
+ *      into rowptr_ub int64[total_nodes+1]; gtok_csrl_sort scatters key = neighbour << 32 | column index into both
+ *      endpoint rows of entries[rowptr_ub[total_nodes]], sorts every row and keeps the first key per neighbour (warp
+ *      bitonic network <= 32 entries, CTA shared-memory bitonic <= 4096, neighbour-indexed table beyond: table_ws of
+ *      gtok_csrl_table_bytes(max_nodes) bytes) and writes the unique degrees -> the caller scans them into rowptr64;
+ *      gtok_csrl_emit writes rowptr_out int32[total_nodes+1], col_out[nnz] and eattr_out[nnz] (label = edge_attr of the
+ *      pair's first column in caller order).  cursor_ws: total_nodes int32.  batch->max_nodes must be set. */
+GTOK_API int gtok_csrl_count(const GtokGraphBatch* batch, int64_t total_nodes, int32_t* degree_ub, void* stream);
+GTOK_API size_t gtok_csrl_table_bytes(int32_t max_nodes);
+GTOK_API int gtok_csrl_sort(const GtokGraphBatch* batch, int64_t total_nodes, const int64_t* rowptr_ub, int32_t* cursor_ws,
+                            uint64_t* entries, int32_t* degree_out, void* table_ws, size_t table_bytes, void* stream);
+GTOK_API int gtok_csrl_emit(const GtokGraphBatch* batch, int64_t total_nodes, const int64_t* rowptr_ub, const uint64_t* entries,
+                            const int64_t* rowptr64, int64_t nnz, int32_t* rowptr_out, int32_t* col_out, int32_t* eattr_out,
+                            void* stream);
+
 /* K3   Graph2TrailTokenizer.__call__ (external AutoGraph; spec in
  *      oracle/sent_oracle.py) + remap_zinc_tokens + query append
  *      (train_agtt.py:171-273).  Row g is written at tok_out[g*stride ..], its
@@ -373,6 +402,13 @@ GTOK_API int gtok_segment_counts(const int64_t* off, int64_t num_graphs, const i
                                  int32_t* cnt_out, int32_t* status, void* stream);
 GTOK_API int gtok_gather_segments(const int32_t* src, const int64_t* src_off, int64_t num_graphs, const int64_t* idx,
                                   const int64_t* dst_off, int64_t num_idx, int32_t* dst, void* stream);
+/*      gtok_ragged_append_lengths / gtok_ragged_append: TokenDataset(strip_label=False) (data_loader.py:478-482 without
+ *      the strip): row r = (tok[off[r] .. +row_len[r]) ++ tail[r, :tail_len[r]])[:max_len]; the tails are the ids of the
+ *      few tokens after <p> (label, <eos>).  new_len -> gtok_scan_offsets -> new_off -> out. */
+GTOK_API int gtok_ragged_append_lengths(const int32_t* row_len, const int32_t* tail_len, int64_t num_rows, int32_t max_len,
+                                        int32_t* new_len, void* stream);
+GTOK_API int gtok_ragged_append(const int64_t* tok, const int64_t* off, const int32_t* row_len, const int64_t* tail,
+                                int32_t tail_stride, const int64_t* new_off, int64_t num_rows, int64_t* out, void* stream);
 GTOK_API int gtok_balance_order(const int64_t* node_off, const int32_t* rowptr, int64_t num_graphs, int32_t window,
                                 int32_t* order_out, void* stream);
 

@@ -230,3 +230,133 @@ def test_epoch_loaders_query_positions():
             assert int(qp[b]) == (int(nz[0]) if len(nz) else -1)
             found += len(nz) > 0
     assert found > 0
+
+
+@pytest.mark.parametrize("max_len", [600, 97, 64])
+def test_token_dataset_keeps_label_tokens_when_asked(golden_zinc, max_len):
+    """TokenDataset(strip_label=False) (reference data_loader.py:478-482 without the strip): the whole text, label and <eos>
+    included, cut at max_len - graph-token texts and ZINC texts (truncated items keep their own tail)."""
+    import graph_data_loader as g
+    for task in ("cycle_check", "shortest_path"):
+        _, texts, ex = gt_examples(task, 200)
+        vocab, _ = g.build_vocab_from_texts(texts, max_tokens=600)
+        ds = g.TokenDataset(ex, vocab, max_len, strip_label=False)
+        kept = [e for e in ex if e["label"] is not None]
+        assert len(ds) == len(kept)
+        for s, e in zip(ds.seqs, kept):
+            assert s.tolist() == O.encode_text(e["text"], vocab, max_len, strip_label=False)
+    zds = g.ZINCTokenizationDataset(split="train", max_vocab=2000, max_len=max_len, zinc_dataset=_fake_zinc(golden_zinc["mols"]))
+    ex = [zds[i] for i in range(len(zds))]
+    vocab = golden_zinc["L1024"]["vocab"]
+    ds = g.TokenDataset(ex, vocab, max_len, strip_label=False)
+    for s, e in zip(ds.seqs, ex):
+        assert s.tolist() == O.encode_text(e["text"], vocab, max_len, strip_label=False)
+    X, A, Y = g.collate([ds[i] for i in range(16)], vocab["<pad>"])
+    Xw, Aw, _ = O.collate([s.numpy() for s in ds.seqs[:16]], [0] * 16, vocab["<pad>"])
+    assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw)
+
+
+def test_token_dataset_registry_does_not_keep_datasets_alive():
+    import gc
+    import weakref
+    import graph_data_loader as g
+    from graph_data_loader import data_loader as dl
+    _, texts, ex = gt_examples("cycle_check", 50)
+    vocab, _ = g.build_vocab_from_texts(texts, max_tokens=600)
+    ds = g.TokenDataset(ex, vocab, 600)
+    key = ds._host.data_ptr()
+    assert dl._REGISTRY[key] is ds
+    ref = weakref.ref(ds)
+    del ds
+    gc.collect()
+    assert ref() is None and key not in dl._REGISTRY
+
+
+def test_sent_shim_epoch_rule_and_worker_guard(golden_zinc):
+    """an early re-read of an item is served from the current epoch's trails; a re-read after half of the dataset has been
+    served starts a new epoch; new_epoch() forces one; DataLoader workers are refused with a clear message."""
+    import graph_data_loader as g
+    from autograph.datamodules.data.tokenizer import Graph2TrailTokenizer
+    zds = g.ZINCDatasetForAutoGraph(split="train", zinc_dataset=_fake_zinc(golden_zinc["mols"][:64]))
+    tok = Graph2TrailTokenizer(dataset_names=[], max_length=512, truncation_length=512, labeled_graph=True, undirected=True)
+    tok.set_num_nodes(40)
+    tok.set_num_node_and_edge_types(9, 4)
+    a0 = tok(zds[0]).tolist()
+    assert tok(zds[0]).tolist() == a0                        # peek: same epoch, same trail
+    first = [tok(zds[i]).tolist() for i in range(40)]        # more than half served
+    assert first[0] == a0
+    b0 = tok(zds[0]).tolist()                                # served before and > half done: new epoch, fresh trails
+    again = [tok(zds[i]).tolist() for i in range(1, 40)]
+    assert any(x != y for x, y in zip(first[1:], again)) or b0 != a0
+    tok.new_epoch()
+    c = [tok(zds[i]).tolist() for i in range(40)]
+    assert any(x != y for x, y in zip([b0] + again, c))
+    import torch.utils.data as tud
+    real = tud.get_worker_info
+    tud.get_worker_info = lambda: object()
+    try:
+        with pytest.raises(RuntimeError, match="num_workers: 0"):
+            tok(zds[0])
+    finally:
+        tud.get_worker_info = real
+
+
+@pytest.mark.parametrize("max_len", [1024, 120, 64])
+def test_zinc_items_rendered_on_the_gpu_match_host_rendering(golden_zinc, max_len):
+    """every item's text comes from one GPU-rendered byte buffer and equals the per-item host rendering (the
+    restatement of tokenize_molecule + __getitem__ truncation, pinned to the reference's own texts in the golden file);
+    dynamic_tokens() reproduces the first-seen dynamic vocabulary of the golden vocab without reading any text."""
+    import graph_data_loader as g
+    mols = _fake_zinc(golden_zinc["mols"])
+    zds = g.ZINCTokenizationDataset(split="train", max_vocab=2000, max_len=max_len, zinc_dataset=mols)
+    ex = [zds[i] for i in range(len(zds))]
+    gold = golden_zinc.get(f"L{max_len}")
+    if gold is not None:
+        assert [e["text"] for e in ex[:3]] == gold["first_texts"]
+    for i, e in enumerate(ex):
+        d = mols[i]
+        lab = d.y.item()
+        toks = zds.tokenize_molecule(d, lab).split()
+        if len(toks) > max_len:
+            toks = toks[:max_len - 1] + ["<eos>"]
+        assert e["text"] == " ".join(toks) and e["label"] == lab, i
+    if max_len == 1024:
+        fixed, _ = g.build_fixed_zinc_vocab()
+        vocab = g.extend_vocab_with_dynamic_tokens(fixed, zds.dynamic_tokens())
+        assert vocab == gold["vocab"]
+        # and it is what the trainer's own loop collects (train_ibtt.py:364-369), in first-seen order
+        dyn = []
+        for e in ex:
+            for t in e["text"].split():
+                if t not in fixed and t not in dyn:
+                    dyn.append(t)
+        assert zds.dynamic_tokens() == dyn
+
+
+def test_zinc_bulk_text_rendering_speed():
+    """[ds[i] for i in range(len(ds))] over 100k molecules: well under a second per 100k once the buffer exists."""
+    import time
+    import graph_data_loader as g
+    from gtok import synth
+    gb = synth.zinc_shaped(100_000, seed=5)
+
+    class _DS:
+        _indices = None
+
+    class _D:
+        pass
+    ds = _DS()
+    ds._data = _D()
+    ds._data.x = gb.x.to(torch.int64).reshape(-1, 1)
+    ds._data.edge_index = torch.stack([gb.src.to(torch.int64), gb.dst.to(torch.int64)])
+    ds._data.edge_attr = gb.edge_attr.to(torch.int64)
+    ds._data.y = gb.y
+    ds.slices = {"x": gb.node_off, "edge_index": gb.edge_off}
+    ds.__class__.__len__ = lambda self: 100_000
+    zds = g.ZINCTokenizationDataset(split="train", max_len=1024, zinc_dataset=ds)
+    t0 = time.perf_counter()
+    ex = [zds[i] for i in range(len(zds))]
+    dt = time.perf_counter() - t0
+    assert len(ex) == 100_000 and ex[7]["text"].startswith("<bos> <atom> ") and ex[7]["text"].endswith(" <eos>")
+    assert dt < 5.0, dt                                    # (reference: ~18 s per 100k molecules on one core, BASELINE.md)
+    print(f"100k ZINC items in {dt:.2f} s")

@@ -646,6 +646,45 @@ def test_sent_validity_and_distribution_large(dev):
     assert abs(resets_gpu - resets_cpu) < 6 * np.sqrt(resets_gpu + resets_cpu + 1)
 
 
+def test_sent_free_running_token_frequencies_chi_square(dev):
+    """north_star: "trail-length and token-frequency distribution check for the free-running stochastic mode".  The same
+    300 graphs are sampled 40 times by the CUDA kernels (seeds 1..40) and 40 times by the oracle (seeds 1001..1040):
+    the two token-id histograms must be draws of one distribution (chi-square test of homogeneity), and so must the two
+    trail-length samples (two-sample Kolmogorov-Smirnov).  Thresholds at p ~ 1e-4: a wrong neighbour-selection or
+    restart distribution (e.g. always picking the lowest neighbour) fails both by orders of magnitude."""
+    from scipy import stats
+    from gtok import engine, synth
+    recs = synth.er_config1_numpy(300, seed=9, task="cycle_check")
+    gb, csr = _sent_inputs(recs, dev)
+    cfg = engine.SentConfig(idx_offset=6, max_length=2000)
+    ocfg = S.SentConfig(idx_offset=6, max_length=2000)
+    nbins = 6 + 50
+    h_gpu, h_cpu = np.zeros(nbins), np.zeros(nbins)
+    len_gpu, len_cpu = [], []
+    csrs = [S.canonical_csr(r["n"], [e[0] for e in r["edges"]], [e[1] for e in r["edges"]]) for r in recs]
+    for rep in range(40):
+        tok, ln = engine.tokenize_sent(csr, cfg, seed=1 + rep)
+        keep = torch.arange(tok.shape[1], device=dev)[None, :] < ln[:, None]
+        h_gpu += np.bincount(tok[keep].cpu().numpy(), minlength=nbins)[:nbins]
+        len_gpu += ln.cpu().tolist()
+        for g, r in enumerate(recs):
+            o = S.sent_tokenize(r["n"], csrs[g][0], csrs[g][1], ocfg, S.PhiloxWords(1001 + rep, g))
+            h_cpu += np.bincount(o, minlength=nbins)[:nbins]
+            len_cpu.append(len(o))
+    use = (h_gpu + h_cpu) >= 20                                # (SOS / EOS counts are deterministic and equal: harmless)
+    chi2, p, dof, _ = stats.chi2_contingency(np.stack([h_gpu[use], h_cpu[use]]))
+    assert p > 1e-4, (chi2, dof, p)
+    ks = stats.ks_2samp(len_gpu, len_cpu)
+    assert ks.pvalue > 1e-4, ks
+    # the test has teeth: a biased walk (always the first unvisited neighbour, oracle with a constant-zero stream) is rejected
+    h_bad = np.zeros(nbins)
+    for rep in range(40):
+        for g, r in enumerate(recs):
+            h_bad += np.bincount(S.sent_tokenize(r["n"], csrs[g][0], csrs[g][1], ocfg, S.StreamWords([])), minlength=nbins)[:nbins]
+    useb = (h_gpu + h_bad) >= 20
+    assert stats.chi2_contingency(np.stack([h_gpu[useb], h_bad[useb]]))[1] < 1e-6
+
+
 def test_sent_sharding_invariance(dev):
     """Rank shards see the same rows as the single-GPU run (seeds keyed by GLOBAL graph id)."""
     from gtok import engine, synth
@@ -1147,3 +1186,57 @@ def test_native_csr_build_equals_sort_based_build(dev, nmax):
                 assert ea[lo:hi].tolist() == wea.tolist()
             n0 += m["n"]
     assert engine.build_csr(GraphBatch.from_lists([], []).to(dev)).num_graphs == 0
+
+
+@pytest.mark.parametrize("shape", ["sparse_300", "mixed_1000", "star_9000", "dense_700", "tiny_and_huge"])
+def test_large_csr_build_equals_sort_based_build(dev, shape):
+    """K7 beyond 256 nodes (csrc/gtok_csr_large.cu): rows sorted in registers (<= 32 entries), in shared memory (<= 4096)
+    and through the neighbour table (longer) - all three against the sort-based torch build; repeats in both directions,
+    self loops, conflicting labels, isolated nodes."""
+    from gtok import engine
+    from gtok.batch import GraphBatch
+    rng = np.random.default_rng(len(shape))
+    mols = []
+
+    def add(n, m, hub=None):
+        s_ = rng.integers(0, n, m)
+        d_ = rng.integers(0, n, m)
+        if hub is not None:
+            s_[: m // 2] = hub                                 # a hub row far beyond 4096 entries (with repeats)
+        if m > 4:
+            s_[1], d_[1] = d_[0], s_[0]
+            s_[3], d_[3] = s_[2], d_[2]
+        mols.append({"n": n, "src": s_.tolist(), "dst": d_.tolist(), "x": rng.integers(0, 12, n).tolist(),
+                     "attr": rng.integers(1, 9, m).tolist()})
+    if shape == "sparse_300":
+        for _ in range(40):
+            n = int(rng.integers(257, 301))
+            add(n, int(rng.integers(0, 3 * n)))
+    elif shape == "mixed_1000":
+        for _ in range(12):
+            n = int(rng.integers(300, 1001))
+            add(n, int(rng.integers(n, 12 * n)))
+    elif shape == "star_9000":
+        add(9000, 30000, hub=7)
+        add(300, 100)
+    elif shape == "dense_700":
+        add(700, 120000)                                       # rows of ~340 entries before dedupe: shared-memory sort
+        add(700, 700 * 20, hub=3)                              # hub row of 7000 entries: table path
+    else:
+        add(1, 0); add(2, 1); add(5000, 4000); add(3, 9); add(260, 0)
+    for labeled in (True, False):
+        gb = GraphBatch.from_lists([m["n"] for m in mols], [list(zip(m["src"], m["dst"])) for m in mols],
+                                   x_lists=[m["x"] for m in mols] if labeled else None,
+                                   attr_lists=[m["attr"] for m in mols] if labeled else None).to(dev)
+        a = engine.build_csr(gb, native=True)
+        b = engine.build_csr(gb, native=False)
+        assert a.adj64 is None and b.adj64 is None
+        for f in ("rowptr", "col"):
+            assert torch.equal(getattr(a, f), getattr(b, f)), (shape, labeled, f)
+        assert (a.eattr is None) == (not labeled) and (a.eattr is None or torch.equal(a.eattr, b.eattr))
+        assert (a.max_nodes, a.max_nnz, a.max_label) == (b.max_nodes, b.max_nnz, b.max_label)
+    m = mols[0]
+    wrp, wcol, wea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"])
+    gb = GraphBatch.from_lists([m["n"]], [list(zip(m["src"], m["dst"]))], x_lists=[m["x"]], attr_lists=[m["attr"]]).to(dev)
+    a = engine.build_csr(gb)
+    assert a.rowptr.cpu().tolist() == wrp.tolist() and a.col.cpu().tolist() == wcol.tolist() and a.eattr.cpu().tolist() == wea.tolist()
