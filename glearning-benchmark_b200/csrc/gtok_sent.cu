@@ -496,7 +496,9 @@ static int sent_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const Gtok
 int sent_small_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
                         int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
 int sent_walk_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
-                       int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
+                       int64_t* out, int64_t stride, int64_t total_nodes, void* ws, size_t ws_bytes, cudaStream_t st,
+                       bool* handled);
+size_t sent_log_bytes(int64_t total_nodes);
 int sent_mid_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
                       int64_t* out, int64_t stride, cudaStream_t st, bool* handled);
 int sent_big_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int32_t* len_out,
@@ -506,7 +508,9 @@ int sent_big_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokC
 }  // namespace gtok
 
 extern "C" size_t gtok_sent_workspace_bytes(int64_t total_nodes, int32_t max_nodes) {
-  return (max_nodes > 256 && total_nodes > 0) ? (size_t)total_nodes * 8 : 0;
+  if (total_nodes <= 0) return 0;
+  if (max_nodes <= 64) return gtok::sent_log_bytes(total_nodes);        // the walk's item log (gtok_sent_walk.cu)
+  return max_nodes > 256 ? (size_t)total_nodes * 8 : 0;
 }
 
 extern "C" int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cfg, const GtokChoice* choice,
@@ -539,13 +543,13 @@ extern "C" int gtok_sent_tokenize_ws(const GtokCsrBatch* csr, const GtokSentCfg*
   GTOK_REQUIRE((reinterpret_cast<uintptr_t>(tok_out) & 15) == 0, GTOK_EINVAL, "sent: tok_out must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   {
-    // graphs of at most 64 nodes, 64-bit adjacency masks: thread-per-graph walk, then warp-wide emission with a lane
-    // per event (gtok_sent_walk.cu); GTOK_SENT_SMALL=1 selects the one-phase kernel (gtok_sent_small.cu)
+    // graphs of at most 64 nodes, 64-bit adjacency masks, workspace given: thread-per-graph walk kernel + warp-per-row
+    // emission kernel (gtok_sent_walk.cu); otherwise, or with GTOK_SENT_SMALL=1, the one-kernel path (gtok_sent_small.cu)
     bool handled = false;
     static const int small_env = [] { const char* e = getenv("GTOK_SENT_SMALL"); return e ? atoi(e) : 2; }();
     int rc = GTOK_OK;
     if (small_env != 1) {
-      rc = sent_walk_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);
+      rc = sent_walk_dispatch(csr, cfg, choice, len_out, tok_out, stride, total_nodes, ws, ws_bytes, st, &handled);
       if (rc != GTOK_OK || handled) return rc;
     }
     rc = sent_small_dispatch(csr, cfg, choice, len_out, tok_out, stride, st, &handled);

@@ -105,6 +105,10 @@ PROTOTYPES = {
     "gtok_sent_workspace_bytes": (C.c_size_t, [i64, i32]),
     "gtok_sent_tokenize_ws": (C.c_int, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), C.POINTER(ChoiceC), vp, vp, i64, i64, vp,
                                         C.c_size_t, vp]),
+    "gtok_sent_log_bytes": (C.c_size_t, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), i64]),
+    "gtok_sent_walk": (C.c_int, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), C.POINTER(ChoiceC), i64, vp, C.c_size_t, vp, vp]),
+    "gtok_sent_emit_collate": (C.c_int, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), i64, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp,
+                                         vp]),
     "gtok_pad_mask": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp]),
     "gtok_batch_extents": (C.c_int, [vp, vp, i64, i64, vp, vp, vp]),
     "gtok_pad_mask_batched": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, vp]),

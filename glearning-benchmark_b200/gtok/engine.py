@@ -767,7 +767,8 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
     ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))
     n_total = int(csr.rowptr.numel()) - 1
     if use_workspace is None:
-        use_workspace = csr.max_nodes * (4 * (2 if cfg.labeled else 1) + 0.375) > 12288
+        # <= 64 nodes: the workspace is the walk kernel's item log (walk + emission kernels, csrc/gtok_sent_walk.cu)
+        use_workspace = csr.max_nodes <= 64 or csr.max_nodes * (4 * (2 if cfg.labeled else 1) + 0.375) > 12288
     nbytes = lib.gtok_sent_workspace_bytes(n_total, max(1, csr.max_nodes)) if use_workspace else 0
     if nbytes:
         if csr.scratch is None or csr.scratch.numel() < nbytes:
@@ -777,6 +778,59 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
     else:
         check(lib.gtok_sent_tokenize(C.byref(cc), C.byref(sc), C.byref(ch), _ptr(lengths), _ptr(out), int(stride), _stream()))
     return out, lengths
+
+
+def _sent_c(cfg: SentConfig, seed: int, graph_id_base: int, choice_words, choice_off):
+    sc = _lib.SentCfgC(cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset, cfg.max_length, int(cfg.labeled),
+                       cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query), _sent_switch(cfg.RESTART, cfg.restart),
+                       _sent_switch(cfg.BRACKET, cfg.bracket_order))
+    ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))
+    return sc, ch
+
+
+def sent_collate_supported(csr: CsrBatch, cfg: SentConfig) -> bool:
+    """True when the walk / emission kernels take this configuration (graphs up to 64 nodes with adjacency bit rows,
+    tokens below 65536): sent_collate_epoch then writes the padded batches without the strided int64 rows."""
+    sc, _ = _sent_c(cfg, 0, 0, None, None)
+    cc = _csr_c(csr)
+    return lib.gtok_sent_log_bytes(C.byref(cc), C.byref(sc), int(csr.rowptr.numel()) - 1) > 0
+
+
+def sent_collate_epoch(csr: CsrBatch, cfg: SentConfig, pad_id: int, batch_size: int, seed: int = 0, graph_id_base: int = 0,
+                       batch_idx: Optional[torch.Tensor] = None, choice_words: Optional[torch.Tensor] = None,
+                       choice_off: Optional[torch.Tensor] = None, X: Optional[torch.Tensor] = None,
+                       attn: Optional[torch.Tensor] = None):
+    """K3+K4 fused: Graph2TrailTokenizer.__call__ + remap / query append + collate_fn of every batch of an epoch
+    (train_agtt.py:246-302).  The walk kernel leaves an item log + row lengths, K4b's extents / scan give the batch
+    geometry, the emission kernel expands every row straight into its padded batch.  -> (PaddedEpoch, lengths int32[G]);
+    identical to tokenize_sent + pad_mask_epoch."""
+    _require_cuda(csr.node_off, csr.rowptr, batch_idx)
+    dev = csr.node_off.device
+    G = csr.num_graphs
+    sc, ch = _sent_c(cfg, seed, graph_id_base, choice_words, choice_off)
+    cc = _csr_c(csr)
+    n_total = int(csr.rowptr.numel()) - 1
+    nbytes = lib.gtok_sent_log_bytes(C.byref(cc), C.byref(sc), n_total)
+    if not nbytes:
+        raise ValueError("sent_collate_epoch: configuration not supported by the walk kernels (see sent_collate_supported)")
+    if csr.scratch is None or csr.scratch.numel() < nbytes:
+        csr.scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)          # kept with the CSR: every epoch reuses it
+    lengths = torch.empty(G, dtype=torch.int32, device=dev)
+    check(lib.gtok_sent_walk(C.byref(cc), C.byref(sc), C.byref(ch), n_total, _ptr(csr.scratch), nbytes, _ptr(lengths), _stream()))
+    R = int(batch_idx.numel() if batch_idx is not None else G)
+    B = int(batch_size)
+    nb = (R + B - 1) // B
+    lmax = torch.empty(nb, dtype=torch.int32, device=dev)
+    cells = torch.empty(nb, dtype=torch.int32, device=dev)
+    check(lib.gtok_batch_extents(_ptr(lengths), _ptr(batch_idx), R, B, _ptr(lmax), _ptr(cells), _stream()))
+    xoff = scan_offsets(cells)
+    if X is None or attn is None:
+        total = int(xoff[-1]) if nb else 0
+        X = torch.empty(total, dtype=torch.int64, device=dev)
+        attn = torch.empty(total, dtype=torch.bool, device=dev)
+    check(lib.gtok_sent_emit_collate(C.byref(cc), C.byref(sc), n_total, _ptr(csr.scratch), _ptr(lengths), _ptr(batch_idx), R, B,
+                                     _ptr(lmax), _ptr(xoff), int(pad_id), _ptr(X), _ptr(attn), _stream()))
+    return PaddedEpoch(X, attn, xoff, lmax, B, R), lengths
 
 
 # ---------------------------------------------------------------------------

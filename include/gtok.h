@@ -359,10 +359,30 @@ GTOK_API int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cfg,
  *      gtok_sent_tokenize).  The workspace carries no state between calls.  Measured on B200 (32M nodes per call,
  *      mean degree 8): the shared-memory kernel is faster up to ~2048 nodes per graph (14.6 vs 15.8 ms), the
  *      workspace kernel beyond (18.2 vs 28.7 ms at 4096 nodes) - gtok/engine.py picks by that rule. */
+/*      Graphs of at most 64 nodes: the workspace (12 bytes per node of the batch) is the walk's ITEM LOG - the walk kernel
+ *      (thread per graph) records one 8-byte item per first visit and the emission kernel (warp per row) expands the
+ *      items into tokens with full-sector stores; without it the one-kernel path runs (1.23 -> ... ms per 1M ER graphs). */
 GTOK_API size_t gtok_sent_workspace_bytes(int64_t total_nodes, int32_t max_nodes);
 GTOK_API int gtok_sent_tokenize_ws(const GtokCsrBatch* csr, const GtokSentCfg* cfg, const GtokChoice* choice,
                                    int32_t* len_out, int64_t* tok_out, int64_t stride, int64_t total_nodes, void* ws,
                                    size_t ws_bytes, void* stream);
+
+/* K3+K4 fused  TokenizedGraphDataset.__getitem__ + collate_fn of a whole epoch (train_agtt.py:246-302) for graphs of at
+ *      most 64 nodes, without the int64 rows at stride max_length in between:
+ *        gtok_sent_log_bytes   bytes of item log the configuration needs (0 = not supported by these kernels: use
+ *                              gtok_sent_tokenize + gtok_pad_mask_batched);
+ *        gtok_sent_walk        the walk: item log + row lengths len_out int32[G] (query included);
+ *        gtok_batch_extents(len_out, batch_idx, ...) + gtok_scan_offsets give lmax / xoff as for K4b;
+ *        gtok_sent_emit_collate  row r of the epoch (graph batch_idx[r], or r) is expanded from the log straight into
+ *                              X / attn + xoff[r / B] + (r % B) * lmax[r / B], padded with pad_id (K4b's layout).
+ *      Output identical to gtok_sent_tokenize followed by gtok_pad_mask_batched. */
+GTOK_API size_t gtok_sent_log_bytes(const GtokCsrBatch* csr, const GtokSentCfg* cfg, int64_t total_nodes);
+GTOK_API int gtok_sent_walk(const GtokCsrBatch* csr, const GtokSentCfg* cfg, const GtokChoice* choice, int64_t total_nodes,
+                            void* log, size_t log_bytes, int32_t* len_out, void* stream);
+GTOK_API int gtok_sent_emit_collate(const GtokCsrBatch* csr, const GtokSentCfg* cfg, int64_t total_nodes, const void* log,
+                                    const int32_t* row_len, const int64_t* batch_idx, int64_t num_rows, int64_t B,
+                                    const int32_t* lmax, const int64_t* xoff, int64_t pad_id, int64_t* X, uint8_t* attn,
+                                    void* stream);
 
 /* K4   collate / collate_fn (data_loader.py:488-497, train_agtt.py:276-302):
  *      X[b, :len] = row, X[b, len:] = pad_id, attn[b, :len] = 1.  Row b is

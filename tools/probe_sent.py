@@ -43,9 +43,9 @@ if WHICH in ("both", "er"):
     gb = synth.er_graph_token(G, seed=0, device=dev)
     run("sent ER unlabeled (window %d)" % BW, gb, engine.SentConfig(idx_offset=6, max_length=600), 600, False, BW)
     del gb
-if WHICH in ("both", "zinc"):
+if WHICH in ("both", "zinc", "zincb"):
     zb = synth.zinc_shaped(G, seed=0, device=dev)
     nmax = int(zb.num_nodes().max())
     cfgz = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 9, max_length=384, labeled=True,
                              remap_zinc=True)
-    run("sent ZINC labeled+remap", zb, cfgz, 384, True, 0)
+    run("sent ZINC labeled+remap", zb, cfgz, 384, True, BW if WHICH == "zincb" else 0)
