@@ -304,8 +304,28 @@ def run_extras(dev, G, peak):
         ms_c = timeit(lambda: engine.pad_mask_epoch(buf.view(-1), row_start, ln, 5, BATCH, X=X, attn=A), 5, 2)
         out[name]["collate_ms"] = ms_c
         out[name]["collate_frac"] = (8 * tot + 9 * cells) / ms_c / 1e6 / peak
-        out[name]["epoch_ms"] = ms + ms_c
-        out[name]["epoch_graphs_per_s"] = G / (ms + ms_c) * 1e3
+        out[name]["epoch_two_step_ms"] = ms + ms_c
+        # the same epoch without the strided int64 rows: walk kernel -> item log -> emission straight into the padded batches
+        # (gtok_sent_walk + gtok_sent_emit_collate); byte-identical to the two-step result, asserted here
+        if engine.sent_collate_supported(csr, cfg):
+            X1, A1 = torch.empty_like(X), torch.empty_like(A)
+            ep1, ln1 = engine.sent_collate_epoch(csr, cfg, 5, BATCH, seed=0, X=X1, attn=A1)
+            if not (torch.equal(ln1, ln) and torch.equal(ep1.xoff, ep.xoff) and torch.equal(X1, X) and torch.equal(A1, A)):
+                raise RuntimeError(f"{name}: fused SENT + collate_fn differs from tokenize_sent + pad_mask_epoch")
+            cap = int(X.numel() * 1.25) + 1024                       # other seeds: other trail lengths
+            X1, A1 = torch.empty(cap, dtype=torch.int64, device=dev), torch.empty(cap, dtype=torch.bool, device=dev)
+
+            def go_fused():
+                step[0] += 1
+                engine.sent_collate_epoch(csr, cfg, 5, BATCH, seed=step[0], X=X1, attn=A1)
+            ms_f = timeit(go_fused, 5, 2)
+            out[name]["epoch_ms"] = ms_f
+            out[name]["epoch_frac"] = (csr.sent_input_bytes(labeled) + 9 * cells + 4 * G) / ms_f / 1e6 / peak
+            out[name]["epoch_identical_to_two_step"] = True
+            del X1, A1
+        else:
+            out[name]["epoch_ms"] = ms + ms_c
+        out[name]["epoch_graphs_per_s"] = G / out[name]["epoch_ms"] * 1e3
         del buf, X, A, ep
 
     sent("sent_graph_token", gb, engine.SentConfig(idx_offset=6, max_length=600), 600, False, 2048)
@@ -402,11 +422,16 @@ def run_sharded_sent(dev, rank, world, total, peak):
     row_start = torch.arange(m, device=dev, dtype=torch.int64) * STRIDE
     Xc, Ac = torch.empty(m * 200, dtype=torch.int64, device=dev), torch.empty(m * 200, dtype=torch.bool, device=dev)
 
+    fused = all(engine.sent_collate_supported(c, cfg) for _, _, c in chunks)
+
     def epoch(seed):
         toks = 0
         for c0, n, csr in chunks:
-            _, ln = engine.tokenize_sent(csr, cfg, seed=seed, graph_id_base=rank * G + c0, out=buf[:n], stride=STRIDE)
-            engine.pad_mask_epoch(buf.view(-1), row_start[:n], ln, 5, BATCH, X=Xc, attn=Ac)
+            if fused:       # walk -> item log -> emission straight into the padded batches (no strided int64 rows)
+                _, ln = engine.sent_collate_epoch(csr, cfg, 5, BATCH, seed=seed, graph_id_base=rank * G + c0, X=Xc, attn=Ac)
+            else:
+                _, ln = engine.tokenize_sent(csr, cfg, seed=seed, graph_id_base=rank * G + c0, out=buf[:n], stride=STRIDE)
+                engine.pad_mask_epoch(buf.view(-1), row_start[:n], ln, 5, BATCH, X=Xc, attn=Ac)
             toks = toks + ln.sum()
         return toks
 
@@ -434,7 +459,8 @@ def run_sharded_sent(dev, rank, world, total, peak):
     del buf, Xc, Ac, chunks
     return {"workload": f"AGTT SENT (labeled + fused remap_zinc_tokens) + collate_fn of every batch of {BATCH}: {G * world} "
                         f"ZINC-shaped graphs sharded by index over {world} GPU(s) (BASELINE configs[3])",
-            "n_gpus": world, "graphs_per_gpu": G, "ms_per_epoch": ms, "graphs_per_s": G * world / ms * 1e3,
+            "n_gpus": world, "graphs_per_gpu": G, "fused_walk_emit_collate": bool(fused), "ms_per_epoch": ms,
+            "graphs_per_s": G * world / ms * 1e3,
             "tokens_per_s": tokens / ms * 1e3, "scaling": "strong"}
 
 

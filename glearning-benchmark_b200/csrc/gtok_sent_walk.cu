@@ -23,6 +23,7 @@
 // Random words, decisions and token order are exactly those of the oracle; tests compare all kernels with it.
 #include "gtok_sent_common.cuh"
 
+
 namespace gtok {
 
 namespace {
@@ -162,7 +163,7 @@ __device__ __forceinline__ void walk_body(const GtokCsrBatch& c, const GtokSentC
 }
 
 template <bool LABELED>
-__global__ void __launch_bounds__(kSmallThreads)
+__global__ void __launch_bounds__(kSmallThreads, 10)   // 48 registers: 40 warps per SM (56+ registers: 0.72 -> 0.84 ms)
 sent_walk_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch, const int nmax,
                  uint2* __restrict__ log_lo, unsigned* __restrict__ log_hi, int32_t* __restrict__ len_out) {
   extern __shared__ __align__(16) unsigned char w_smem[];
@@ -190,7 +191,7 @@ sent_walk_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice c
 // Emission.  COLLATE = false: row r of the batch goes to out + r * stride (r = graph index).  COLLATE = true: rows are
 // grouped B at a time in batch_idx order; row r (graph batch_idx[r]) goes to X / attn + xoff[r / B] + (r % B) * lmax[r / B],
 // padded to lmax[r / B] (gtok_pad_mask_batched's layout).
-template <bool LABELED, typename TokT, bool COLLATE>
+template <bool LABELED, typename TokT, bool COLLATE, bool REMAP>
 __global__ void __launch_bounds__(kEmitThreads)
 sent_emit_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __restrict__ log_lo,
                  const unsigned* __restrict__ log_hi, const int32_t* __restrict__ len, int64_t* __restrict__ out,
@@ -206,18 +207,19 @@ sent_emit_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __res
   TokT* rowb = reinterpret_cast<TokT*>(e_smem) + (size_t)w * row_cap;
   unsigned char* ordb = s_ord[w];
   const unsigned long long* __restrict__ adj64 = reinterpret_cast<const unsigned long long*>(c.adj64);
-  const bool remap = cfg.remap_zinc != 0;
   const bool bracket_desc = cfg.bracket_order == GTOK_SENT_BRACKET_VISIT_DESC;
   const int idx_off = cfg.idx_offset, node_off = cfg.node_idx_offset, edge_off = cfg.edge_idx_offset;
   const int elab_off = edge_off + cfg.edge_label_shift;
   const int q3 = cfg.append_query ? 3 : 0;
-  if (remap) {
+  if (REMAP) {
     for (int t = threadIdx.x; t < kRemapN; t += blockDim.x) s_remap[t] = (unsigned short)remap_zinc_tok(t, idx_off, node_off, edge_off);
     __syncthreads();
   }
   const int64_t wid0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = wid0; r < num_rows; r += nw) {
+    // (requesting the next row's extents and items one row ahead was tried: 0.42 -> 0.57 ms, the extra live registers cost
+    // more occupancy than the shorter dependent chain wins)
     const int64_t g = (COLLATE && batch_idx) ? __ldg(batch_idx + r) : r;
     const int64_t n0 = __ldg(c.node_off + g);
     const int N = (int)(__ldg(c.node_off + g + 1) - n0);
@@ -241,6 +243,13 @@ sent_emit_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __res
       if (lane < nk) ordb[k] = (unsigned char)u;
       __syncwarp();
       if (lane < nk) {
+        unsigned long long a_u = 0;
+        int rp_u = 0, xl = 0;
+        if (LABELED) {
+          a_u = __ldg(adj64 + n0 + u);
+          rp_u = __ldg(c.rowptr + n0 + u);
+          xl = __ldg(c.x + n0 + u);
+        }
         const int pr = (it.y >> 8) & 0xff;
         int p = (int)(it.y >> 16);
         int pv = -1;                                                   // trail predecessor (node id), -1 = none
@@ -248,16 +257,10 @@ sent_emit_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __res
         else if (!(pr & kPreReset) && k > 0) pv = ordb[k - 1];
         if (pr & kPreReset) rowb[p++] = (TokT)RESET;
         if (pr & kPreHead) rowb[p++] = (TokT)(idx_off + (pr & 63));
-        unsigned long long a_u = 0;
-        int rp_u = 0;
         unsigned vlo = it.x;
-        if (LABELED) {
-          a_u = __ldg(adj64 + n0 + u);
-          rp_u = __ldg(c.rowptr + n0 + u);
-          if (pv >= 0) rowb[p++] = (TokT)(elab_off + __ldg(c.eattr + rp_u + __popcll(a_u & ((1ull << pv) - 1ull))));
-        }
+        if (LABELED && pv >= 0) rowb[p++] = (TokT)(elab_off + __ldg(c.eattr + rp_u + __popcll(a_u & ((1ull << pv) - 1ull))));
         rowb[p++] = (TokT)(idx_off + k);
-        if (LABELED) rowb[p++] = (TokT)(node_off + __ldg(c.x + n0 + u));
+        if (LABELED) rowb[p++] = (TokT)(node_off + xl);
         if (vlo | vhi) {
           rowb[p++] = (TokT)LADJ;
           auto member = [&](int kv) {
@@ -283,19 +286,28 @@ sent_emit_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __res
     if (end_pos >= 0) rowb[end_pos] = (TokT)EOS;     // (clipped by the stream below when it lies at or beyond max_length)
     __syncwarp();
     // ---- stream the row: 64 tokens per store instruction ----------------------------------------------------------------
-    auto tokv = [&](int q) -> int64_t {
-      int t = (int)rowb[q];
-      if (remap) t = t < kRemapN ? (int)s_remap[t] : remap_zinc_tok(t, idx_off, node_off, edge_off);
+    auto rm = [&](int t) -> int64_t {
+      if (REMAP) t = (sizeof(TokT) == 1 || t < kRemapN) ? (int)s_remap[t] : remap_zinc_tok(t, idx_off, node_off, edge_off);
       return (int64_t)t;
     };
+    auto tokv = [&](int q) -> int64_t { return rm((int)rowb[q]); };
     int64_t qt = 0;
     if (q3 && lane < 3) qt = idx_off + (lane == 0 ? N : (lane == 1 ? __ldg(c.query_u + g) : __ldg(c.query_v + g)));
     if (!COLLATE) {
       int64_t* __restrict__ row = out + g * stride;  // rows are 16-byte aligned (even stride, aligned base)
-      for (int q = 2 * lane; q < L0; q += 64) {
-        if (q + 1 < L0) st_stream_i64x2(row + q, tokv(q), tokv(q + 1));
-        else st_stream_i64(row + q, tokv(q));
+      const int npair = L0 >> 1;
+      for (int j = lane; j < npair; j += 32) {       // the row buffer is read two tokens at a time
+        int t0, t1;
+        if (sizeof(TokT) == 1) {
+          const unsigned pr2 = reinterpret_cast<const unsigned short*>(rowb)[j];
+          t0 = pr2 & 0xff; t1 = pr2 >> 8;
+        } else {
+          const unsigned pr2 = reinterpret_cast<const unsigned*>(rowb)[j];
+          t0 = pr2 & 0xffff; t1 = pr2 >> 16;
+        }
+        st_stream_i64x2(row + 2 * j, rm(t0), rm(t1));
       }
+      if ((L0 & 1) && lane == 0) st_stream_i64(row + L0 - 1, tokv(L0 - 1));
       if (q3 && lane < 3) row[L0 + lane] = qt;
     } else {
       const int64_t kbatch = r / B;
@@ -367,8 +379,13 @@ static int sent_emit_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const
                             cudaStream_t st) {
   void (*k)(GtokCsrBatch, GtokSentCfg, const uint2*, const unsigned*, const int32_t*, int64_t*, int64_t, const int64_t*,
             int64_t, int64_t, const int32_t*, const int64_t*, int64_t, uint8_t*, int);
-  if (cfg->labeled) k = p.tok8 ? sent_emit_kernel<true, uint8_t, COLLATE> : sent_emit_kernel<true, uint16_t, COLLATE>;
-  else k = p.tok8 ? sent_emit_kernel<false, uint8_t, COLLATE> : sent_emit_kernel<false, uint16_t, COLLATE>;
+  if (cfg->remap_zinc) {
+    if (cfg->labeled) k = p.tok8 ? sent_emit_kernel<true, uint8_t, COLLATE, true> : sent_emit_kernel<true, uint16_t, COLLATE, true>;
+    else k = p.tok8 ? sent_emit_kernel<false, uint8_t, COLLATE, true> : sent_emit_kernel<false, uint16_t, COLLATE, true>;
+  } else {
+    if (cfg->labeled) k = p.tok8 ? sent_emit_kernel<true, uint8_t, COLLATE, false> : sent_emit_kernel<true, uint16_t, COLLATE, false>;
+    else k = p.tok8 ? sent_emit_kernel<false, uint8_t, COLLATE, false> : sent_emit_kernel<false, uint16_t, COLLATE, false>;
+  }
   const size_t smem = (size_t)kEmitWarps * p.row_cap * (p.tok8 ? 1 : 2);
   GTOK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = persistent_grid(k, kEmitThreads, smem, (num_rows + kEmitWarps - 1) / kEmitWarps);

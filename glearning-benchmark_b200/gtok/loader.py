@@ -120,8 +120,10 @@ class AgttEpochLoader(_EpochLoaderBase):
         self.csr, self.config, self.seed, self.graph_id_base = csr, config, int(seed), int(graph_id_base)
         need = config.max_length + (3 if config.append_query else 0)
         self.stride = need + (need & 1)
-        self._buf = torch.empty((self.G, self.stride), dtype=torch.int64, device=self.device)
-        self._row_start = torch.arange(self.G, device=self.device, dtype=torch.int64) * self.stride
+        self._fused = engine.sent_collate_supported(csr, config)
+        if not self._fused:  # strided int64 rows + K4 (graphs above 64 nodes, tokens beyond 16 bits)
+            self._buf = torch.empty((self.G, self.stride), dtype=torch.int64, device=self.device)
+            self._row_start = torch.arange(self.G, device=self.device, dtype=torch.int64) * self.stride
 
     def __iter__(self):
         order = self._order()
@@ -129,9 +131,13 @@ class AgttEpochLoader(_EpochLoaderBase):
         self.epoch += 1
         if order is not None and order.numel() == 0:
             return iter(())
-        _, ln = engine.tokenize_sent(self.csr, self.config, seed=seed, graph_id_base=self.graph_id_base, out=self._buf,
-                                     stride=self.stride)
-        ep = engine.pad_mask_epoch(self._buf.view(-1), self._row_start, ln, self.PAD, self.B, batch_idx=order)
+        if self._fused:      # walk -> item log -> emission straight into the padded batches (csrc/gtok_sent_walk.cu)
+            ep, _ = engine.sent_collate_epoch(self.csr, self.config, self.PAD, self.B, seed=seed, graph_id_base=self.graph_id_base,
+                                              batch_idx=order)
+        else:
+            _, ln = engine.tokenize_sent(self.csr, self.config, seed=seed, graph_id_base=self.graph_id_base, out=self._buf,
+                                         stride=self.stride)
+            ep = engine.pad_mask_epoch(self._buf.view(-1), self._row_start, ln, self.PAD, self.B, batch_idx=order)
         q_pos = None
         if self.with_q_pos:
             first = torch.arange(0, ep.num_rows, self.B, device=self.device)
