@@ -31,13 +31,12 @@ class Graph2TrailTokenizer:
                  device=None, **kwargs):
         if not undirected:
             raise NotImplementedError("gtok's SENT kernel covers undirected graphs (the only mode the reference uses)")
-        if not append_eos:
-            raise NotImplementedError("append_eos=False is not supported")
         self.dataset_names = list(dataset_names or [])
         self.max_length = max_length
         self.truncation_length = truncation_length if truncation_length is not None else max_length
         self.labeled_graph = labeled_graph
         self.undirected = undirected
+        self.append_eos = bool(append_eos)
         self.idx_offset = len(self.special_toks) + len(self.dataset_names)
         self.max_num_nodes: Optional[int] = None
         self.num_node_types = self.num_edge_types = 0
@@ -85,7 +84,7 @@ class Graph2TrailTokenizer:
         return engine.SentConfig(idx_offset=self.idx_offset, node_idx_offset=self.node_idx_offset or 0,
                                  edge_idx_offset=self.edge_idx_offset or 0, max_length=self._limit(),
                                  labeled=self.labeled_graph, edge_label_shift=self.edge_label_shift,
-                                 restart=self.restart, bracket_order=self.bracket_order)
+                                 append_eos=self.append_eos, restart=self.restart, bracket_order=self.bracket_order)
 
     def tokenize_batch(self, graph_batch, seed: Optional[int] = None, graph_id_base: int = 0, csr=None):
         """Native entry point: GraphBatch (CUDA) -> (tokens int64[G, stride], lengths int32[G])."""

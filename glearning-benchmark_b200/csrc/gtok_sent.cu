@@ -441,8 +441,10 @@ __global__ void sent_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const G
         }
       }
     }
-    if (lane == 0) put(len, EOS);
-    len += 1;
+    if (!cfg.no_eos) {
+      if (lane == 0) put(len, EOS);
+      len += 1;
+    }
     const int L = len < Lcap ? len : Lcap;
     __syncwarp();
 

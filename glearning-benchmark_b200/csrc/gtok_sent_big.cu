@@ -398,8 +398,10 @@ sent_big_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
         prev = -1;
       }
     }
-    if (lane == 0) put(len, EOS);
-    len += 1;
+    if (!cfg.no_eos) {
+      if (lane == 0) put(len, EOS);
+      len += 1;
+    }
     const int L = len < Lcap ? len : Lcap;
     int Ltot = L;
     if (cfg.append_query) {

@@ -311,7 +311,7 @@ sent_mid_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch
       if (__all_sync(kFull, done)) break;
     }
     if (valid) {
-      emit(EOS);
+      if (!cfg.no_eos) emit(EOS);
       const int L0 = pos < Lcap ? pos : Lcap;
       // the ring holds the last kMidRing tokens; everything older has been flushed
       for (int p = flushed; p + 1 < L0; p += 2) st_stream_i64x2(row + p, tok(p), tok(p + 1));

@@ -305,7 +305,7 @@ sent_small_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
       if (__all_sync(kFull, done)) break;
     }
     if (valid) {
-      emit(EOS);
+      if (!cfg.no_eos) emit(EOS);
       const int L0 = pos < Lcap ? pos : Lcap;
       // drain: whole pairs, then the unpaired last token
       for (int p = flushed; p + 1 < L0; p += 2) st_stream_i64x2(row + p, tok(p), tok(p + 1));

@@ -157,7 +157,7 @@ __device__ __forceinline__ void walk_body(const GtokCsrBatch& c, const GtokSentC
   }
   if (valid) {
     if (nvis < N) log_lo[my_n0 + nvis] = make_uint2(0u, (unsigned)kOrdEnd);      // early stop: end of the item list
-    const int Lfull = pos + 1;                      // + EOS
+    const int Lfull = pos + (cfg.no_eos ? 0 : 1);   // + EOS
     len_out[g] = (Lfull < Lcap ? Lfull : Lcap) + (cfg.append_query ? 3 : 0);
   }
 }
@@ -283,7 +283,7 @@ sent_emit_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __res
       }
       __syncwarp();
     }
-    if (end_pos >= 0) rowb[end_pos] = (TokT)EOS;     // (clipped by the stream below when it lies at or beyond max_length)
+    if (end_pos >= 0) rowb[end_pos] = (TokT)EOS;     // (clipped by the stream below: at or beyond the row length it is never read)
     __syncwarp();
     // ---- stream the row: 64 tokens per store instruction ----------------------------------------------------------------
     auto rm = [&](int t) -> int64_t {

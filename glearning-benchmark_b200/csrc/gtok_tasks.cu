@@ -195,7 +195,7 @@ __device__ __forceinline__ ErHeader er_header(const GtokErSpec& s, unsigned long
   h.qu = (int)mulhi_u32(w3, (unsigned)h.n);
   h.qv = h.n > 1 ? (h.qu + 1 + (int)mulhi_u32(w4, (unsigned)(h.n - 1))) % h.n : h.qu;
   h.m = 0;
-  if (s.kind == GTOK_GEN_BA) h.m = min(1 + (int)mulhi_u32(w2, (unsigned)s.num_blocks), h.n - 1);   // attachments per new node
+  if (s.kind == GTOK_GEN_BA || s.kind == GTOK_GEN_SFN) h.m = min(1 + (int)mulhi_u32(w2, (unsigned)s.num_blocks), h.n - 1);   // attachments per new node
   return h;
 }
 
@@ -224,8 +224,8 @@ er_kernel(GtokErSpec s, int64_t G, int32_t* __restrict__ nn_out, int32_t* __rest
     const unsigned long long gid = (unsigned long long)(s.graph_id_base + g);
     const ErHeader h = er_header(s, gid);
     const long long P = (long long)h.n * (h.n - 1) / 2;
-    const long long blocks = s.kind == GTOK_GEN_BA ? 0 : (P + 3) >> 2;     // ba: closed-form count, filled by ba_fill_kernel
-    long long base = FILL ? __ldg(edge_off + g) : (s.kind == GTOK_GEN_BA ? (long long)h.m * (h.n - h.m) : 0);
+    const long long blocks = h.m ? 0 : (P + 3) >> 2;     // ba: closed-form count, filled by ba_fill_kernel
+    long long base = FILL ? __ldg(edge_off + g) : (h.m ? (long long)h.m * (h.n - h.m) : 0);
     for (long long b0 = 0; b0 < blocks; b0 += kWarp) {
       const long long blk = b0 + lane;
       unsigned bits = 0;
@@ -304,24 +304,51 @@ ba_fill_kernel(GtokErSpec s, int64_t G, const int64_t* __restrict__ edge_off, in
     for (int i = 1; i <= m; ++i) add_edge(0, i);                 // star on nodes 0..m
     unsigned e2 = 2u * (unsigned)m;                              // sum of degrees
     unsigned d = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0, have = 0xffffffffu;
+    auto next_word = [&]() -> unsigned {
+      const unsigned wi = 8u + d, blk = wi >> 2;
+      ++d;
+      if (blk != have) { philox10((unsigned)gid, (unsigned)(gid >> 32), blk, 1u, k0, k1, b0, b1, b2, b3); have = blk; }
+      return (wi & 2u) ? ((wi & 1u) ? b3 : b2) : ((wi & 1u) ? b1 : b0);
+    };
     for (int source = m + 1; source < n; ++source) {
       unsigned long long tm = 0ull;
       int cnt = 0;
       while (cnt < m) {
-        const unsigned wi = 8u + d, blk = wi >> 2;
-        ++d;
-        if (blk != have) { philox10((unsigned)gid, (unsigned)(gid >> 32), blk, 1u, k0, k1, b0, b1, b2, b3); have = blk; }
-        const unsigned word = (wi & 2u) ? ((wi & 1u) ? b3 : b2) : ((wi & 1u) ? b1 : b0);
+        const unsigned word = next_word();
         const unsigned r = __umulhi(word, e2);
         int x = 0;
         unsigned acc = deg[0][t];
         while (acc <= r) { ++x; acc += deg[x][t]; }
         if (!((tm >> x) & 1ull)) { tm |= 1ull << x; ++cnt; }
       }
-      while (tm) {
-        const int x = __ffsll((long long)tm) - 1;
+      if (s.kind == GTOK_GEN_SFN) {                               // Holme-Kim: triad steps between the preferential ones
+        int target = __ffsll((long long)tm) - 1;
         tm &= tm - 1;
-        add_edge(x, source);
+        add_edge(target, source);
+        for (int count = 1; count < m; ++count) {
+          const unsigned a = next_word();
+          bool done = false;
+          if ((a >> 16) < s.out_ratio_q16) {
+            const unsigned long long cand = rows[target][t] & ~rows[source][t] & ~(1ull << source);
+            if (cand) {
+              const unsigned b = next_word();
+              add_edge(select64(cand, (int)__umulhi(b, (unsigned)__popcll(cand))), source);
+              done = true;
+            }
+          }
+          if (!done) {
+            tm &= ~rows[source][t];
+            target = __ffsll((long long)tm) - 1;
+            tm &= tm - 1;
+            add_edge(target, source);
+          }
+        }
+      } else {
+        while (tm) {
+          const int x = __ffsll((long long)tm) - 1;
+          tm &= tm - 1;
+          add_edge(x, source);
+        }
       }
       e2 += 2u * (unsigned)m;
     }
@@ -353,11 +380,12 @@ static int er_check(const GtokErSpec* s, int64_t G, const char* who) {
     GTOK_REQUIRE(s->n_lo[b] >= 1 && s->n_lo[b] < s->n_hi[b] && s->n_hi[b] <= 32768, GTOK_EINVAL,
                  "%s: bucket %d needs 1 <= n_lo < n_hi <= 32768 (got [%d, %d))", who, b, s->n_lo[b], s->n_hi[b]);
   GTOK_REQUIRE(s->thr_lo <= s->thr_hi, GTOK_EINVAL, "%s: thr_lo > thr_hi", who);
-  GTOK_REQUIRE(s->kind >= GTOK_GEN_ER && s->kind <= GTOK_GEN_BA, GTOK_EINVAL, "%s: unknown generator kind %d", who, s->kind);
-  if (s->kind == GTOK_GEN_BA) {
-    GTOK_REQUIRE(s->num_blocks >= 1 && s->num_blocks <= 8, GTOK_EINVAL, "%s: ba needs 1..8 attachments per node (num_blocks)", who);
+  GTOK_REQUIRE(s->kind >= GTOK_GEN_ER && s->kind <= GTOK_GEN_SFN, GTOK_EINVAL, "%s: unknown generator kind %d", who, s->kind);
+  if (s->kind == GTOK_GEN_BA || s->kind == GTOK_GEN_SFN) {
+    GTOK_REQUIRE(s->num_blocks >= 1 && s->num_blocks <= 8, GTOK_EINVAL, "%s: ba / sfn need 1..8 attachments per node (num_blocks)", who);
+    GTOK_REQUIRE(s->out_ratio_q16 <= 65536u, GTOK_EINVAL, "%s: sfn triad probability above 1", who);
     for (int b = 0; b < s->num_buckets; ++b)
-      GTOK_REQUIRE(s->n_hi[b] <= 65, GTOK_EINVAL, "%s: ba graphs are limited to 64 nodes (bucket %d ends at %d)", who, b, s->n_hi[b]);
+      GTOK_REQUIRE(s->n_hi[b] <= 65, GTOK_EINVAL, "%s: ba / sfn graphs are limited to 64 nodes (bucket %d ends at %d)", who, b, s->n_hi[b]);
   }
   GTOK_REQUIRE(s->kind != GTOK_GEN_SBM || (s->num_blocks >= 1 && s->num_blocks <= 16 && s->out_ratio_q16 <= 65536u), GTOK_EINVAL,
                "%s: sbm needs 1..16 blocks and out_ratio_q16 <= 65536", who);
@@ -433,7 +461,7 @@ extern "C" int gtok_er_edges(const GtokErSpec* spec, int64_t num_graphs, const i
   if (int rc = er_check(spec, num_graphs, "er_edges")) return rc;
   if (num_graphs == 0) return GTOK_OK;
   GTOK_REQUIRE(edge_off != nullptr, GTOK_EINVAL, "er_edges: null edge_off");          // src / dst may be null without edges
-  if (spec->kind == GTOK_GEN_BA) {
+  if (spec->kind == GTOK_GEN_BA || spec->kind == GTOK_GEN_SFN) {
     const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 4;
     const int64_t blocks = (num_graphs + kBaThreads - 1) / kBaThreads;
     ba_fill_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kBaThreads, 0, (cudaStream_t)stream>>>(*spec, num_graphs, edge_off,

@@ -459,14 +459,56 @@ class TokenDataset(Dataset):
         return self.seqs[idx], self.labels[idx]
 
 
+class _DeferredBatch:
+    """What collate() hands back from INSIDE a DataLoader worker (configs/ibtt_graph_token.yaml:27 and ibtt_zinc.yaml:23 set
+    num_workers: 2): a worker must not touch CUDA, so it ships only the row handles (which dataset, where each row starts,
+    how long it is) and the batch is padded by K4 in the trainer's process at its first `.to(device)`
+    (trainer/train_ibtt.py:144,164).  No token is copied or padded on the host."""
+
+    def __init__(self, base: int, starts: torch.Tensor, lens: torch.Tensor, pad_id: int):
+        self.base, self.starts, self.lens, self.pad_id = int(base), starts, lens, int(pad_id)
+        self._out = None
+
+    def materialize(self):
+        if self._out is None:
+            from gtok import engine
+            ds = _REGISTRY.get(self.base)
+            if ds is None:
+                raise RuntimeError("deferred batch: its TokenDataset is gone (the dataset must outlive its DataLoader)")
+            dev = ds.device
+            self._out = engine.pad_mask(ds.ragged.tokens, self.starts.to(dev), self.lens.to(dev), self.pad_id,
+                                        lmax=int(self.lens.max()))
+        return self._out
+
+
+class _DeferredTensor:
+    """One member (0 = X, 1 = attn) of a _DeferredBatch; `.to(device)` returns the CUDA tensor."""
+
+    def __init__(self, batch: _DeferredBatch, which: int):
+        self.batch, self.which = batch, which
+
+    def to(self, *args, **kwargs):
+        return self.batch.materialize()[self.which].to(*args, **kwargs)
+
+    def cuda(self, *args, **kwargs):
+        return self.batch.materialize()[self.which]
+
+
 def collate(batch, pad_id: int):
     """X[b,:L_b] = row, X[b,L_b:] = pad_id, attn[b,:L_b] = True, Y long - computed by K4 on the
-    GPU and returned as CUDA tensors (the trainer's .to(device) becomes a no-op).  Reference :488-497."""
+    GPU and returned as CUDA tensors (the trainer's .to(device) becomes a no-op).  Reference :488-497.
+    Inside a DataLoader worker (num_workers > 0) the rows' handles are returned instead and K4 runs at the trainer's
+    `.to(device)` (_DeferredBatch)."""
     from gtok import engine
-    if torch.utils.data.get_worker_info() is not None:
-        raise RuntimeError("gtok collate runs on the GPU and cannot be used inside a forked DataLoader worker; "
-                           "set num_workers=0")
     xs, ys = zip(*batch)
+    if torch.utils.data.get_worker_info() is not None:
+        base = xs[0].untyped_storage().data_ptr() if not xs[0].is_cuda else None
+        if base is None or base not in _REGISTRY or any(x.untyped_storage().data_ptr() != base for x in xs):
+            raise RuntimeError("gtok collate inside a DataLoader worker needs rows of ONE gtok TokenDataset (their padding is "
+                               "deferred to the trainer's process); foreign rows need num_workers=0")
+        db = _DeferredBatch(base, torch.tensor([x.storage_offset() for x in xs], dtype=torch.int64),
+                            torch.tensor([x.numel() for x in xs], dtype=torch.int32), pad_id)
+        return _DeferredTensor(db, 0), _DeferredTensor(db, 1), torch.tensor([int(y) for y in ys], dtype=torch.long)
     ds = None
     base = xs[0].untyped_storage().data_ptr() if not xs[0].is_cuda else None
     if base is not None and base in _REGISTRY and all(x.untyped_storage().data_ptr() == base for x in xs):

@@ -59,7 +59,7 @@ class CsrBatchC(C.Structure):
 class SentCfgC(C.Structure):
     _fields_ = [("idx_offset", i32), ("node_idx_offset", i32), ("edge_idx_offset", i32), ("max_length", i32),
                 ("labeled", i32), ("edge_label_shift", i32), ("remap_zinc", i32), ("append_query", i32),
-                ("restart_policy", i32), ("bracket_order", i32)]
+                ("restart_policy", i32), ("bracket_order", i32), ("no_eos", i32), ("reserved0", i32)]
 
 
 class ErSpecC(C.Structure):

@@ -635,6 +635,7 @@ class SentConfig:
     edge_label_shift: int = 0
     remap_zinc: bool = False
     append_query: bool = False
+    append_eos: bool = True              # Graph2TrailTokenizer(append_eos=...)
     restart: str = "open_first"          # oracle.sent_oracle.SentSpec.restart: "open_first" | "unvisited"
     bracket_order: str = "visit_asc"     # SentSpec.bracket_order: "visit_asc" | "visit_desc"
 
@@ -763,7 +764,7 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
     cc = _csr_c(csr)
     sc = _lib.SentCfgC(cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset, cfg.max_length, int(cfg.labeled),
                        cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query), _sent_switch(cfg.RESTART, cfg.restart),
-                       _sent_switch(cfg.BRACKET, cfg.bracket_order))
+                       _sent_switch(cfg.BRACKET, cfg.bracket_order), int(not cfg.append_eos), 0)
     ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))
     n_total = int(csr.rowptr.numel()) - 1
     if use_workspace is None:
@@ -783,7 +784,7 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
 def _sent_c(cfg: SentConfig, seed: int, graph_id_base: int, choice_words, choice_off):
     sc = _lib.SentCfgC(cfg.idx_offset, cfg.node_idx_offset, cfg.edge_idx_offset, cfg.max_length, int(cfg.labeled),
                        cfg.edge_label_shift, int(cfg.remap_zinc), int(cfg.append_query), _sent_switch(cfg.RESTART, cfg.restart),
-                       _sent_switch(cfg.BRACKET, cfg.bracket_order))
+                       _sent_switch(cfg.BRACKET, cfg.bracket_order), int(not cfg.append_eos), 0)
     ch = _lib.ChoiceC(int(seed) & (2 ** 64 - 1), int(graph_id_base), _ptr(choice_words), _ptr(choice_off))
     return sc, ch
 
@@ -869,7 +870,7 @@ def graph_labels(csr: CsrBatch, edge_off: Optional[torch.Tensor] = None, cycle: 
 ER_BUCKETS = ((10, 20), (20, 40), (40, 50))        # docs/synthetic_data.md:130-138
 
 
-GEN_KINDS = {"er": 0, "sbm": 1, "complete": 2, "star": 3, "path": 4, "ba": 5}      # include/gtok.h GTOK_GEN_*
+GEN_KINDS = {"er": 0, "sbm": 1, "complete": 2, "star": 3, "path": 4, "ba": 5, "sfn": 6}      # include/gtok.h GTOK_GEN_*
 
 
 def er_spec(seed: int, graph_id_base: int = 0, buckets=ER_BUCKETS, p_min: float = 0.1, p_max: float = 0.2,
@@ -877,7 +878,7 @@ def er_spec(seed: int, graph_id_base: int = 0, buckets=ER_BUCKETS, p_min: float 
     if not 1 <= len(buckets) <= 4:
         raise ValueError("1..4 size buckets expected")
     if kind not in GEN_KINDS:
-        raise ValueError(f"unknown generator {kind!r} (have {sorted(GEN_KINDS)}; sfn is not provided)")
+        raise ValueError(f"unknown generator {kind!r} (have {sorted(GEN_KINDS)})")
     thr = lambda p: max(0, min(0xFFFFFFFF, int(math.floor(float(p) * 4294967296.0))))
     s = _lib.ErSpecC()
     s.num_buckets = len(buckets)
@@ -894,7 +895,8 @@ def generate_er(num_graphs: int, seed: int = 0, graph_id_base: int = 0, buckets=
     """Graph-token-shaped graphs generated ON the device (docs/synthetic_data.md:93-94,130-138 distribution; stream =
     oracle/tasks_oracle.py er_graph): every undirected edge once, u < v ascending, plus a query pair per graph.
     kind: "er" (default), "sbm" (num_blocks contiguous blocks, p inside / p * out_ratio across), "complete", "star",
-    "path", "ba" (Barabasi-Albert, m ~ U{1..num_blocks} attachments per new node, graphs of at most 64 nodes).  Keyed by the global graph id, so shards of a larger job generate their own slice."""
+    "path", "ba" (Barabasi-Albert, m ~ U{1..num_blocks} attachments per new node, graphs of at most 64 nodes), "sfn" (Holme-Kim
+    scale-free graphs: ba + triad steps with probability out_ratio - the test algorithm of configs/ibtt_graph_token.yaml:5).  Keyed by the global graph id, so shards of a larger job generate their own slice."""
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("gtok has no CPU path: a CUDA device is required")

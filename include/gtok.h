@@ -144,6 +144,8 @@ typedef struct GtokSentCfg {
    * repo's normative choice. */
   int32_t restart_policy;    /* GTOK_SENT_RESTART_*: where a new segment starts when the walk is stuck */
   int32_t bracket_order;     /* GTOK_SENT_BRACKET_*: order of the neighbourhood set between LADJ and RADJ */
+  int32_t no_eos;            /* 1 = Graph2TrailTokenizer(append_eos=False): the sequence ends without EOS */
+  int32_t reserved0;         /* (keeps the struct a multiple of 8 bytes) */
 } GtokSentCfg;
 enum { GTOK_SENT_RESTART_OPEN_FIRST = 0, /* visited nodes that still have an unvisited neighbour, else unvisited nodes */
        GTOK_SENT_RESTART_UNVISITED = 1   /* any unvisited node */ };
@@ -463,15 +465,18 @@ GTOK_API int gtok_graph_labels(const GtokCsrBatch* csr, const int64_t* edge_off,
 enum { GTOK_GEN_ER = 0,        /* every pair with probability p */
        GTOK_GEN_SBM = 1,       /* stochastic block model: p inside a block, p_out across */
        GTOK_GEN_COMPLETE = 2, GTOK_GEN_STAR = 3 /* centre 0 */, GTOK_GEN_PATH = 4 /* i - (i+1) */,
-       GTOK_GEN_BA = 5         /* Barabasi-Albert preferential attachment, m ~ U{1..num_blocks} new edges per node, N <= 64 */ };
+       GTOK_GEN_BA = 5,        /* Barabasi-Albert preferential attachment, m ~ U{1..num_blocks} new edges per node, N <= 64 */
+       GTOK_GEN_SFN = 6        /* Holme-Kim scale-free graphs (docs "sfn"): BA + triad steps with probability
+                                  out_ratio_q16 / 65536, N <= 64 */ };
 typedef struct GtokErSpec {
   int32_t num_buckets;       /* 1..4 size buckets, one drawn uniformly per graph */
   int32_t n_lo[4], n_hi[4];  /* N uniform in [n_lo, n_hi), 1 <= n_lo < n_hi <= 32768 */
   uint32_t thr_lo, thr_hi;   /* edge probability p ~ U(thr_lo, thr_hi) / 2^32 */
   int32_t kind;              /* GTOK_GEN_*: which of the docs' generator families (docs/synthetic_data.md:93-94) */
   int32_t num_blocks;        /* GTOK_GEN_SBM: 1..16 contiguous blocks, block(i) = i * num_blocks / N;
-                                GTOK_GEN_BA: largest attachment count m (1..8) */
-  uint32_t out_ratio_q16;    /* GTOK_GEN_SBM: p_out = p * out_ratio_q16 / 65536 between different blocks */
+                                GTOK_GEN_BA / GTOK_GEN_SFN: largest attachment count m (1..8) */
+  uint32_t out_ratio_q16;    /* GTOK_GEN_SBM: p_out = p * out_ratio_q16 / 65536 between different blocks;
+                                GTOK_GEN_SFN: probability of a triad step, in 1/65536 */
   uint64_t seed;
   int64_t graph_id_base;
 } GtokErSpec;

@@ -94,6 +94,7 @@ class SentConfig:
     max_length: int = 600
     labeled: bool = False
     edge_label_shift: int = 0
+    append_eos: bool = True        # Graph2TrailTokenizer(append_eos=...) (train_agtt.py:514-530 leaves the default)
 
 
 @dataclass(frozen=True)
@@ -274,7 +275,8 @@ def _sent_emit(out: List[int], num_nodes: int, rowptr, col, cfg: SentConfig, pic
             out.append(RESET)
             cur = R[pick(len(R))]
             prev = -1
-    out.append(EOS)
+    if cfg.append_eos:
+        out.append(EOS)
 
 
 def _sent_revisit(n, rowptr, col, cfg, pick, x, eattr, spec, out) -> None:

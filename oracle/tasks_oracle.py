@@ -114,6 +114,60 @@ def prob_threshold(p: float) -> int:
     return max(0, min(_MASK, int(np.floor(float(p) * 4294967296.0))))
 
 
+def _sfn_edges(w, n: int, m: int, tri_q16: int):
+    """Holme-Kim scale-free graphs with tunable clustering (docs/synthetic_data.md:15 "sfn"; networkx.powerlaw_cluster_graph):
+    the Barabasi-Albert process of _ba_edges where, after a new node's first preferential-attachment edge, every further
+    edge is with probability tri_q16 / 65536 a TRIAD step: a uniformly chosen neighbour of the last preferential target that
+    the new node is not adjacent to yet (ascending node id; none -> an ordinary preferential step).  Preferential targets are
+    the m distinct draws of _ba_edges, used in ascending node id, skipping any the new node became adjacent to through a
+    triad.  Words: the m-subset draws as in _ba_edges, then per further edge one decision word (triad iff its top 16 bits
+    < tri_q16) and, for a triad with candidates, one pick word (mulhi(word, #candidates)).  Always m * (n - m) edges."""
+    adj = [set() for _ in range(n)]
+    deg = [0] * n
+
+    def add(a, b):
+        adj[a].add(b)
+        adj[b].add(a)
+        deg[a] += 1
+        deg[b] += 1
+    for i in range(1, m + 1):
+        add(0, i)
+    e2, d = 2 * m, 0
+    for source in range(m + 1, n):
+        targets = []
+        while len(targets) < m:
+            r = (w(ER_PAIR_WORD0 + d) * e2) >> 32
+            d += 1
+            x, acc = 0, deg[0]
+            while acc <= r:
+                x += 1
+                acc += deg[x]
+            if x not in targets:
+                targets.append(x)
+        rest = sorted(targets)
+        target = rest.pop(0)
+        add(target, source)
+        count = 1
+        while count < m:
+            a = w(ER_PAIR_WORD0 + d)
+            d += 1
+            done = False
+            if (a >> 16) < tri_q16:
+                cand = sorted(v for v in adj[target] if v != source and v not in adj[source])
+                if cand:
+                    b = w(ER_PAIR_WORD0 + d)
+                    d += 1
+                    add(cand[(b * len(cand)) >> 32], source)
+                    done = True
+            if not done:
+                rest = [v for v in rest if v not in adj[source]]
+                target = rest.pop(0)
+                add(target, source)
+            count += 1
+        e2 += 2 * m
+    return sorted((u, v) for u in range(n) for v in adj[u] if u < v)
+
+
 def _ba_edges(w, n: int, m: int):
     """Barabasi-Albert after networkx.barabasi_albert_graph: a star on nodes 0..m, then every new node attaches to m
     DISTINCT existing nodes drawn with probability proportional to their degree (degrees as they were before this
@@ -163,6 +217,8 @@ def er_graph(seed: int, gid: int, buckets: Sequence[Tuple[int, int]] = ((10, 20)
     qv = (qu + 1 + ((w(4) * (n - 1)) >> 32)) % n if n > 1 else qu
     if kind == "ba":
         return n, _ba_edges(w, n, min(1 + ((w(2) * num_blocks) >> 32), n - 1)), (qu, qv)
+    if kind == "sfn":      # out_ratio = probability of a triad step
+        return n, _sfn_edges(w, n, min(1 + ((w(2) * num_blocks) >> 32), n - 1), max(0, min(65536, int(round(out_ratio * 65536))))), (qu, qv)
     thr_out = (thr * max(0, min(65536, int(round(out_ratio * 65536))))) >> 16
     edges = []
     k = 0

@@ -29,7 +29,7 @@ def test_version_and_struct_sizes():
     assert ctypes.sizeof(_lib.IbttRulesC) == 56
     assert ctypes.sizeof(_lib.ZincVocabC) == 120
     assert ctypes.sizeof(_lib.CsrBatchC) == 96
-    assert ctypes.sizeof(_lib.SentCfgC) == 40
+    assert ctypes.sizeof(_lib.SentCfgC) == 48
     assert ctypes.sizeof(_lib.ChoiceC) == 32
     assert ctypes.sizeof(_lib.ErSpecC) == 72 and _lib.ErSpecC.seed.offset == 56
 

@@ -360,3 +360,31 @@ def test_zinc_bulk_text_rendering_speed():
     assert len(ex) == 100_000 and ex[7]["text"].startswith("<bos> <atom> ") and ex[7]["text"].endswith(" <eos>")
     assert dt < 5.0, dt                                    # (reference: ~18 s per 100k molecules on one core)
     print(f"100k ZINC items in {dt:.2f} s")
+
+
+def test_ibtt_dataloader_with_workers_as_in_the_reference_yaml(golden_gt):
+    """configs/ibtt_graph_token.yaml:27 / ibtt_zinc.yaml:23 set num_workers: 2 and the trainer builds its loaders with it
+    (trainer/train_ibtt.py:399-402).  Workers cannot touch CUDA: collate() hands back row handles there and K4 pads the batch
+    at the trainer's `.to(device)` (:144).  Batches must equal the num_workers=0 ones (and the reference's golden sha)."""
+    import graph_data_loader as g
+    from torch.utils.data import DataLoader
+    gold = golden_gt["cycle_check_G1000_L600_V600"]
+    _, texts, ex = gt_examples("cycle_check", 1000)
+    vocab, _ = g.build_vocab_from_texts([e["text"] for e in ex], max_tokens=600)
+    ds = g.TokenDataset(ex, vocab, 600)
+    pad_id = vocab["<pad>"]
+    coll = lambda b: g.collate(b, pad_id)                                                    # train_ibtt.py:399
+    device = torch.device("cuda")
+    dl = DataLoader(ds, batch_size=128, shuffle=False, num_workers=2, collate_fn=coll)       # :401
+    seen = 0
+    for k, (X, A, Y) in enumerate(dl):
+        X, A, Y = X.to(device), A.to(device), Y.to(device)                                   # :144
+        assert X.is_cuda and X.dtype == torch.long and A.dtype == torch.bool and Y.dtype == torch.long
+        assert sha_int64([X.cpu().numpy()]) == gold["batch_sha"][k][1]
+        assert sha_int64([Y.cpu().numpy()]) == gold["batch_sha"][k][3]
+        seen += X.shape[0]
+    assert seen == len(ds)
+    # shuffled epochs deliver every row exactly once
+    dl = DataLoader(ds, batch_size=64, shuffle=True, num_workers=2, collate_fn=coll)
+    total = sum(int(A.to(device).sum()) for X, A, Y in dl)
+    assert total == sum(int(s.numel()) for s in ds.seqs)

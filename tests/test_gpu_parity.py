@@ -1110,15 +1110,17 @@ def test_sent_workspace_kernel_above_4096_nodes(dev):
     assert torch.equal(lc, la) and torch.equal(tc[0, :int(la[0])], ta[0, :int(la[0])])
 
 
-@pytest.mark.parametrize("kind", ["sbm", "complete", "star", "path", "ba"])
+@pytest.mark.parametrize("kind", ["sbm", "complete", "star", "path", "ba", "sfn"])
 def test_generator_families_match_oracle(dev, kind):
     """The other generator families of docs/synthetic_data.md:93-94 on the device == oracle/tasks_oracle.py er_graph,
     and their labels follow from the shape (star / path: no cycle; complete on >= 3 nodes: cycle)."""
     from gtok import engine
     from oracle import tasks_oracle as T
     kw = dict(kind=kind, num_blocks=3, out_ratio=0.2, p_min=0.15, p_max=0.5, buckets=((1, 6), (10, 50), (60, 90)))
-    if kind == "ba":
+    if kind in ("ba", "sfn"):
         kw.update(num_blocks=5, buckets=((1, 6), (10, 50), (60, 65)))       # attachments m ~ U{1..5}, at most 64 nodes
+    if kind == "sfn":
+        kw.update(out_ratio=0.6)                                            # triad probability
     okw = dict(kw)
     gb = engine.generate_er(150, seed=8, graph_id_base=40, device=dev, **kw)
     n, eo = gb.num_nodes().cpu().tolist(), gb.edge_off.cpu().tolist()
@@ -1136,13 +1138,13 @@ def test_generator_families_match_oracle(dev, kind):
         assert int(cyc.sum()) == 0 and int((dist < 0).sum()) == 0
     if kind == "complete":
         assert cyc.cpu().tolist() == [int(a >= 3) for a, _, _ in recs]
-    if kind == "ba":
+    if kind in ("ba", "sfn"):
         assert gb.num_entries().cpu().tolist() == [len(e) for _, e, _ in recs] and int((dist < 0).sum()) == 0   # connected
         from gtok._lib import GtokError
         with pytest.raises(GtokError):
-            engine.generate_er(4, kind="ba", buckets=((10, 80),), device=dev)                                   # > 64 nodes
+            engine.generate_er(4, kind=kind, buckets=((10, 80),), device=dev)                                   # > 64 nodes
     with pytest.raises(ValueError):
-        engine.generate_er(4, kind="sfn", device=dev)
+        engine.generate_er(4, kind="smallworld", device=dev)
 
 
 @pytest.mark.parametrize("nmax", [1, 40, 64, 65, 128, 200, 256])
@@ -1341,3 +1343,28 @@ def test_sent_collate_epoch_equals_two_step(dev, labeled, B):
     ep2 = engine.pad_mask_epoch(tok.view(-1), torch.arange(len(mols), device=dev, dtype=torch.int64) * tok.shape[1], ln, 5, B)
     ep1, ln1 = engine.sent_collate_epoch(csr, cfg, 5, B, choice_words=cw, choice_off=co)
     assert torch.equal(ln1, ln) and torch.equal(ep1.X, ep2.X) and torch.equal(ep1.attn, ep2.attn)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,count,use_ws", [(40, 64, True), (40, 64, False), (150, 24, None), (400, 8, None)])
+def test_sent_append_eos_false_every_kernel_family(dev, N, count, use_ws):
+    """Graph2TrailTokenizer(append_eos=False): the row ends without EOS - walk + emission kernels, the single-kernel
+    thread-per-graph path, the 65..256-node kernel and the warp-per-graph kernel, against the oracle (with a max_length that
+    cuts some rows exactly where EOS would have been)."""
+    from gtok import engine, synth
+    gb = synth.er_sparse(count, N, mean_degree=5.0, seed=N, device="cpu")
+    csr = engine.build_csr(gb.to(dev))
+    src, dst = gb.src.numpy(), gb.dst.numpy()
+    eo = gb.edge_off.numpy()
+    full = engine.tokenize_sent(csr, engine.SentConfig(idx_offset=6, max_length=100000, append_eos=False), seed=5,
+                                use_workspace=use_ws)[1].cpu().tolist()
+    for max_length in (100000, full[0], full[1] + 1):
+        cfg = engine.SentConfig(idx_offset=6, max_length=max_length, append_eos=False)
+        tok, ln = engine.tokenize_sent(csr, cfg, seed=5, use_workspace=use_ws)
+        tok, ln = tok.cpu(), ln.cpu().tolist()
+        ocfg = S.SentConfig(idx_offset=6, max_length=max_length, append_eos=False)
+        for g in range(count):
+            rp, col, _ = S.canonical_csr(N, src[eo[g]:eo[g + 1]], dst[eo[g]:eo[g + 1]])
+            want = S.sent_tokenize(N, rp, col, ocfg, S.PhiloxWords(5, g))
+            assert tok[g, :ln[g]].tolist() == want.tolist(), (N, max_length, g)
+            assert S.EOS not in want.tolist()

@@ -154,3 +154,34 @@ def test_ba_generator_shape():
         hub += deg[0]
         tail += deg[n - 1]
     assert hub > 3 * tail
+
+
+def test_sfn_generator_shape():
+    """Holme-Kim family (docs/synthetic_data.md:15 "sfn", the test algorithm of configs/ibtt_graph_token.yaml:5): m * (n - m)
+    edges like ba, connected, triad steps close triangles (clustering rises with the triad probability), hubs stay hubs, and
+    with triad probability 0 the graph is the ba graph of the same words as long as no decision word is consumed (m = 1)."""
+    def triangles(n, e):
+        es = set(e)
+        adj = [set() for _ in range(n)]
+        for u, v in e:
+            adj[u].add(v)
+            adj[v].add(u)
+        return sum(1 for u, v in es for w in adj[u] & adj[v] if w > v)
+    tri = {0.0: 0, 0.9: 0}
+    hub = tail = 0
+    for gid in range(200):
+        for p in tri:
+            n, e, _ = T.er_graph(2, gid, kind="sfn", num_blocks=4, out_ratio=p)
+            m = min(1 + ((T._Words(2, gid)(2) * 4) >> 32), n - 1)
+            assert len(e) == m * (n - m) and e == sorted(set(e)) and all(u < v for u, v in e)
+            assert T.shortest_distance(n, e, 0, n - 1) > 0
+            tri[p] += triangles(n, e)
+            if m == 1:
+                assert e == T.er_graph(2, gid, kind="ba", num_blocks=4)[1]
+        deg = [0] * n
+        for u, v in e:
+            deg[u] += 1
+            deg[v] += 1
+        hub += deg[0]
+        tail += deg[n - 1]
+    assert tri[0.9] > 1.3 * tri[0.0] and hub > 3 * tail

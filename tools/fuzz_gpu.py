@@ -167,7 +167,7 @@ def tasks_round():
     """device generators (all families) + task labels + query positions vs oracle/tasks_oracle.py"""
     global bad
     from oracle import tasks_oracle as T
-    kind = str(rng.choice(["er", "sbm", "complete", "star", "path", "ba"]))
+    kind = str(rng.choice(["er", "sbm", "complete", "star", "path", "ba", "sfn"]))
     nb = int(rng.integers(1, 5))
     lows = sorted(int(v) for v in rng.integers(1, 60, nb))
     buckets = tuple((lo, lo + int(rng.integers(1, 6))) for lo in lows)            # at most 64 nodes (ba)
