@@ -511,7 +511,7 @@ int sent_big_dispatch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokC
 
 extern "C" size_t gtok_sent_workspace_bytes(int64_t total_nodes, int32_t max_nodes) {
   if (total_nodes <= 0) return 0;
-  if (max_nodes <= 64) return gtok::sent_log_bytes(total_nodes);        // the walk's item log (gtok_sent_walk.cu)
+  if (max_nodes <= 256) return gtok::sent_log_bytes(total_nodes);       // the walk's item log (gtok_sent_walk.cu / _walkl.cu)
   return max_nodes > 256 ? (size_t)total_nodes * 8 : 0;
 }
 

@@ -328,14 +328,36 @@ sent_emit_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __res
 struct WalkPlan {
   bool ok;
   bool tok8;
+  bool wide;         // 65..256 nodes: the neighbour-list pair of gtok_sent_walkl.cu
   int row_cap;       // tokens per row buffer
 };
 
+}  // namespace
+
+int sent_walkl_row_cap(const GtokCsrBatch* c, const GtokSentCfg* cfg);
+int sent_walkl_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, void* log, int32_t* len_out,
+                      cudaStream_t st);
+int sent_emitl_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, int row_cap, bool collate, const void* log,
+                      const int32_t* len, int64_t* out, int64_t stride, const int64_t* batch_idx, int64_t num_rows, int64_t B,
+                      const int32_t* lmax, const int64_t* xoff, int64_t pad_id, uint8_t* attn, cudaStream_t st);
+
+namespace {
+
+static bool cfg_force_lists() {     // GTOK_SENT_LISTS=1: neighbour-list kernels for 65..128 nodes too (tests, A/B runs)
+  static const bool f = [] { const char* e = getenv("GTOK_SENT_LISTS"); return e && atoi(e) != 0; }();
+  return f;
+}
+
 static WalkPlan walk_plan(const GtokCsrBatch* c, const GtokSentCfg* cfg) {
-  WalkPlan p{false, false, 0};
-  if (c->max_nodes > 64 || c->adj64 == nullptr || c->adj_words > 1) return p;
-  if (cfg->idx_offset < 0 || cfg->max_length > 32768) return p;
-  long long tmax = (long long)cfg->idx_offset + 64;       // largest token before the remap (needs the label bound)
+  WalkPlan p{false, false, false, 0};
+  if (c->max_nodes > 256 || c->max_nodes < 1) return p;
+  p.wide = c->max_nodes > 64;
+  // 65..128 nodes stay with the two-mask-word single kernel (gtok_sent_mid.cu: 2.9 ms per 32M nodes against 3.3 ms for the
+  // neighbour-list pair); 129..256 nodes: 8.5 -> 5.5 ms (profiles/r2_large_graph_sweep.jsonl)
+  if (p.wide && c->max_nodes <= 128 && c->adj64 != nullptr && !cfg_force_lists()) return p;
+  if (p.wide ? (c->col == nullptr || c->rowptr == nullptr) : (c->adj64 == nullptr || c->adj_words > 1)) return p;
+  if (cfg->idx_offset < 0 || (!p.wide && cfg->max_length > 32768)) return p;
+  long long tmax = (long long)cfg->idx_offset + c->max_nodes;   // largest token before the remap (needs the label bound)
   if (cfg->labeled) {
     if (c->max_label <= 0 || cfg->node_idx_offset < 0 || cfg->edge_idx_offset + cfg->edge_label_shift < 0) return p;
     const long long a = (long long)cfg->node_idx_offset + c->max_label;
@@ -344,6 +366,11 @@ static WalkPlan walk_plan(const GtokCsrBatch* c, const GtokSentCfg* cfg) {
     tmax = b > tmax ? b : tmax;
   }
   if (tmax >= 65536) return p;
+  if (p.wide) {
+    p.row_cap = sent_walkl_row_cap(c, cfg);
+    p.ok = p.row_cap > 0;
+    return p;
+  }
   p.tok8 = tmax < 256;
   p.row_cap = (cfg->max_length + kItemMax + 4 + 15) & ~15;
   if ((size_t)kEmitWarps * p.row_cap * (p.tok8 ? 1 : 2) > 160 * 1024) return p;
@@ -361,6 +388,7 @@ static inline unsigned* log_hi_of(void* log, int64_t total_nodes) {
 
 int sent_walk_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, int64_t total_nodes, void* log,
                      int32_t* len_out, cudaStream_t st) {
+  if (c->max_nodes > 64) return sent_walkl_launch(c, cfg, ch, log, len_out, st);
   auto k = cfg->labeled ? sent_walk_kernel<true> : sent_walk_kernel<false>;
   const size_t smem = (size_t)kSmallWarps * 64 * c->max_nodes;
   GTOK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -377,6 +405,8 @@ static int sent_emit_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const
                             const int32_t* len, int64_t* out, int64_t stride, const int64_t* batch_idx, int64_t num_rows,
                             int64_t B, const int32_t* lmax, const int64_t* xoff, int64_t pad_id, uint8_t* attn,
                             cudaStream_t st) {
+  if (p.wide)
+    return sent_emitl_launch(c, cfg, p.row_cap, COLLATE, log, len, out, stride, batch_idx, num_rows, B, lmax, xoff, pad_id, attn, st);
   void (*k)(GtokCsrBatch, GtokSentCfg, const uint2*, const unsigned*, const int32_t*, int64_t*, int64_t, const int64_t*,
             int64_t, int64_t, const int32_t*, const int64_t*, int64_t, uint8_t*, int);
   if (cfg->remap_zinc) {
@@ -429,8 +459,8 @@ extern "C" int gtok_sent_walk(const GtokCsrBatch* csr, const GtokSentCfg* cfg, c
   GTOK_REQUIRE(csr && cfg && choice, GTOK_EINVAL, "sent_walk: null csr/cfg/choice");
   if (csr->num_graphs <= 0) return GTOK_OK;
   GTOK_REQUIRE(csr->node_off && len_out && log, GTOK_EINVAL, "sent_walk: null pointer");
-  GTOK_REQUIRE(walk_plan(csr, cfg).ok, GTOK_EUNSUPPORTED, "sent_walk: needs adjacency bit rows of graphs up to 64 nodes, a label bound "
-               "and tokens below 65536 (gtok_sent_log_bytes returns 0 for anything else)");
+  GTOK_REQUIRE(walk_plan(csr, cfg).ok, GTOK_EUNSUPPORTED, "sent_walk: needs graphs of at most 256 nodes (adjacency bit rows up to 64), a "
+               "label bound and tokens below 65536 (gtok_sent_log_bytes returns 0 for anything else)");
   GTOK_REQUIRE(cfg->max_length >= 1, GTOK_EINVAL, "sent_walk: max_length must be >= 1");
   GTOK_REQUIRE(log_bytes >= sent_log_bytes(total_nodes) && (reinterpret_cast<uintptr_t>(log) & 7) == 0, GTOK_EINVAL,
                "sent_walk: log of %zu bytes (8-byte aligned) required", sent_log_bytes(total_nodes));

@@ -769,7 +769,7 @@ def tokenize_sent(csr: CsrBatch, cfg: SentConfig, seed: int = 0, graph_id_base: 
     n_total = int(csr.rowptr.numel()) - 1
     if use_workspace is None:
         # <= 64 nodes: the workspace is the walk kernel's item log (walk + emission kernels, csrc/gtok_sent_walk.cu)
-        use_workspace = csr.max_nodes <= 64 or csr.max_nodes * (4 * (2 if cfg.labeled else 1) + 0.375) > 12288
+        use_workspace = csr.max_nodes <= 256 or csr.max_nodes * (4 * (2 if cfg.labeled else 1) + 0.375) > 12288
     nbytes = lib.gtok_sent_workspace_bytes(n_total, max(1, csr.max_nodes)) if use_workspace else 0
     if nbytes:
         if csr.scratch is None or csr.scratch.numel() < nbytes:

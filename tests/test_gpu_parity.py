@@ -1245,12 +1245,12 @@ def test_large_csr_build_equals_sort_based_build(dev, shape):
 
 
 # --------------------------------------------------------------------------- K3 as walk + emission kernels (<= 64 nodes)
-def _mixed_small_graphs(seed, count, labeled):
+def _mixed_small_graphs(seed, count, labeled, nmax=64):
     rng = np.random.default_rng(seed)
     mols = []
     for i in range(count):
         kind = i % 6
-        n = [0, 1, int(rng.integers(2, 12)), int(rng.integers(12, 33)), int(rng.integers(33, 65)), 64][kind]
+        n = [0, 1, int(rng.integers(2, 12)), int(rng.integers(12, 33)), int(rng.integers(33, nmax + 1)), nmax][kind]
         dens = [0, 0, 1.5, 2.5, 3.0, 6.0][kind]
         m = int(n * dens * rng.random() * 2) if n > 1 else 0
         s_, d_ = (rng.integers(0, n, m), rng.integers(0, n, m)) if m else (np.zeros(0, np.int64), np.zeros(0, np.int64))
@@ -1260,27 +1260,29 @@ def _mixed_small_graphs(seed, count, labeled):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nmax", [64, 200, 256])
 @pytest.mark.parametrize("labeled", [False, True])
-def test_sent_walk_emit_kernels_vs_single_kernel_and_oracle(dev, labeled):
+def test_sent_walk_emit_kernels_vs_single_kernel_and_oracle(dev, labeled, nmax):
     """Graphs of 0..64 nodes (empty, single node, 33+ nodes = two emission rounds / 64-bit masks, dense 64-node graphs)
     through the walk + emission kernels (workspace = item log), the single-kernel path (use_workspace=False) and the oracle:
     every max_length (early stops), both restart policies, both bracket orders, query append, remap."""
     from gtok import engine
     from gtok.batch import GraphBatch
-    mols = _mixed_small_graphs(5, 198, labeled)
+    mols = _mixed_small_graphs(5, 198 if nmax == 64 else 90, labeled, nmax)
     gb = GraphBatch.from_lists([m["n"] for m in mols], [list(zip(m["src"], m["dst"])) for m in mols],
                                x_lists=[m["x"] for m in mols] if labeled else None,
                                attr_lists=[m["attr"] for m in mols] if labeled else None,
                                queries=[m["query"] for m in mols]).to(dev)
     csr = engine.build_csr(gb, balance_window=64)
-    assert csr.adj64 is not None and csr.adj_words == 1
+    assert csr.adj64 is not None and csr.adj_words == (1 if nmax == 64 else 2 if nmax <= 128 else 4)
+    no, eo = 6 + nmax, 6 + nmax + 9
     for max_length, restart, order, remap, append in ((600, "open_first", "visit_asc", False, False),
                                                       (1, "open_first", "visit_asc", False, False),
                                                       (2, "open_first", "visit_asc", False, True),
                                                       (37, "unvisited", "visit_desc", labeled, True),
                                                       (100, "open_first", "visit_desc", labeled, False),
                                                       (4000, "unvisited", "visit_asc", False, True)):
-        cfg = engine.SentConfig(6, 70, 79, max_length, labeled, remap_zinc=remap, append_query=append, restart=restart,
+        cfg = engine.SentConfig(6, no, eo, max_length, labeled, remap_zinc=remap, append_query=append, restart=restart,
                                 bracket_order=order)
         assert engine.sent_collate_supported(csr, cfg)
         t1, l1 = engine.tokenize_sent(csr, cfg, seed=17, graph_id_base=5)
@@ -1288,7 +1290,7 @@ def test_sent_walk_emit_kernels_vs_single_kernel_and_oracle(dev, labeled):
         assert torch.equal(l1, l0)
         t1, t0, ln = t1.cpu(), t0.cpu(), l1.cpu().tolist()
         spec = S.SentSpec(restart=restart, bracket_order=order)
-        ocfg = S.SentConfig(6, 70, 79, max_length, labeled)
+        ocfg = S.SentConfig(6, no, eo, max_length, labeled)
         for g, m in enumerate(mols):
             assert t1[g, :ln[g]].tolist() == t0[g, :ln[g]].tolist(), (max_length, g)
             if g % 3 == 0:
@@ -1296,21 +1298,23 @@ def test_sent_walk_emit_kernels_vs_single_kernel_and_oracle(dev, labeled):
                 want = S.sent_tokenize(m["n"], rp, col, ocfg, S.PhiloxWords(17, 5 + g), x=m["x"] if labeled else None, eattr=ea,
                                        spec=spec)
                 if remap:
-                    want = O.remap_zinc(want, 6, 70, 79)
+                    want = O.remap_zinc(want, 6, no, eo)
                 if append:
                     want = O.append_query(want, 6, m["n"], m["query"][0], m["query"][1])
                 assert t1[g, :ln[g]].tolist() == np.asarray(want).tolist(), (max_length, g)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nmax", [64, 256])
 @pytest.mark.parametrize("labeled", [False, True])
 @pytest.mark.parametrize("B", [1, 37, 128])
-def test_sent_collate_epoch_equals_two_step(dev, labeled, B):
+def test_sent_collate_epoch_equals_two_step(dev, labeled, B, nmax):
     """gtok_sent_walk + gtok_batch_extents + gtok_sent_emit_collate == gtok_sent_tokenize + gtok_pad_mask_batched, byte for
     byte, under a shuffled row order, for explicit choice streams too; one batch is checked against the oracle's collate_fn."""
     from gtok import engine
     from gtok.batch import GraphBatch
-    mols = _mixed_small_graphs(9, 300, labeled)
+    mols = _mixed_small_graphs(9, 300 if nmax == 64 else 120, labeled, nmax)
+    no, eo = 6 + nmax, 6 + nmax + 9
     gb = GraphBatch.from_lists([m["n"] for m in mols], [list(zip(m["src"], m["dst"])) for m in mols],
                                x_lists=[m["x"] for m in mols] if labeled else None,
                                attr_lists=[m["attr"] for m in mols] if labeled else None,
@@ -1318,8 +1322,8 @@ def test_sent_collate_epoch_equals_two_step(dev, labeled, B):
     csr = engine.build_csr(gb)
     rng = np.random.default_rng(B)
     perm = torch.from_numpy(rng.permutation(len(mols))).to(dev)
-    for max_length, append, order in ((600, False, None), (50, True, perm), (600, True, perm[:211])):
-        cfg = engine.SentConfig(6, 70, 79, max_length, labeled, remap_zinc=labeled, append_query=append)
+    for max_length, append, order in ((600, False, None), (50, True, perm), (600, True, perm[:len(mols) * 2 // 3])):
+        cfg = engine.SentConfig(6, no, eo, max_length, labeled, remap_zinc=labeled, append_query=append)
         tok, ln = engine.tokenize_sent(csr, cfg, seed=3, graph_id_base=11)
         stride = tok.shape[1]
         rs = torch.arange(len(mols), device=dev, dtype=torch.int64) * stride
@@ -1328,7 +1332,7 @@ def test_sent_collate_epoch_equals_two_step(dev, labeled, B):
         assert torch.equal(ln1, ln) and torch.equal(ep1.lmax, ep2.lmax) and torch.equal(ep1.xoff, ep2.xoff)
         assert torch.equal(ep1.X, ep2.X) and torch.equal(ep1.attn, ep2.attn)
     # oracle collate_fn on the first batch of the last configuration
-    idx = perm[:211][:B].cpu().tolist()
+    idx = perm[:len(mols) * 2 // 3][:B].cpu().tolist()
     rows = [tok[i, :int(ln[i])].cpu().numpy() for i in idx]
     Xw, Aw, _ = O.collate(rows, [0] * len(rows), 5)
     X, A = ep1.batch(0)
@@ -1338,7 +1342,7 @@ def test_sent_collate_epoch_equals_two_step(dev, labeled, B):
     woff = np.zeros(len(mols) + 1, dtype=np.int64)
     woff[1:] = np.cumsum([len(w) for w in words])
     cw, co = torch.from_numpy(np.concatenate(words).view(np.int32)).to(dev), torch.from_numpy(woff).to(dev)
-    cfg = engine.SentConfig(6, 70, 79, 600, labeled)
+    cfg = engine.SentConfig(6, no, eo, 600, labeled)
     tok, ln = engine.tokenize_sent(csr, cfg, choice_words=cw, choice_off=co)
     ep2 = engine.pad_mask_epoch(tok.view(-1), torch.arange(len(mols), device=dev, dtype=torch.int64) * tok.shape[1], ln, 5, B)
     ep1, ln1 = engine.sent_collate_epoch(csr, cfg, 5, B, choice_words=cw, choice_off=co)

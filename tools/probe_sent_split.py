@@ -55,3 +55,12 @@ if WHICH in ("both", "zinc"):
                              remap_zinc=True)
     run("ZINC", zb, cfgz, 384, 0)
     run("ZINC", zb, cfgz, 384, BW)
+if WHICH == "sparse":                                      # large-graph sweep point: python probe_sent_split.py NODES sparse N
+    N = BW
+    Gs = max(64, G // N)
+    G = Gs
+    gb = synth.er_sparse(Gs, N, mean_degree=8.0, seed=N, device=dev)
+    E = gb.src.numel()
+    Lcap = 2 + 2 * N + 2 * (E // Gs + N) + 64
+    Lcap = min(Lcap + (Lcap & 1), 65534)
+    run(f"sparse N={N} G={Gs}", gb, engine.SentConfig(idx_offset=6, max_length=Lcap), Lcap, 0)

@@ -67,5 +67,15 @@ for N in (64, 128, 256, 512, 1024, 2048, 4096):
     cells = int(ep.xoff[-1])
     byt = 8 * tot + 9 * cells
     print(json.dumps({"kind": "sent_collate", "N": N, "G": G, "ms": round(ms, 4), "GBps": byt / ms / 1e6, "frac": byt / ms / 1e6 / PEAK}))
+    if engine.sent_collate_supported(csr, cfg):      # walk -> item log -> emission into the padded batches (<= 256 nodes)
+        Bc = 128 if G >= 128 else G
+        X, A = ep.X, ep.attn
+        ep1, l1 = engine.sent_collate_epoch(csr, cfg, 5, Bc, seed=1, X=X.clone(), attn=A.clone())
+        same = bool(torch.equal(l1, ln) and torch.equal(ep1.X, ep.X) and torch.equal(ep1.attn, ep.attn))
+        ms = timeit(lambda: engine.sent_collate_epoch(csr, cfg, 5, Bc, seed=1, X=X, attn=A), steps=3, warm=1)
+        byt = csr.sent_input_bytes(False) + 9 * cells + 4 * G
+        print(json.dumps({"kind": "sent_epoch_fused", "N": N, "G": G, "ms": round(ms, 4), "identical_to_two_step": same,
+                          "GBps": byt / ms / 1e6, "frac": byt / ms / 1e6 / PEAK}))
+        del ep1, X, A
     del out, csr, gb, ep
     torch.cuda.empty_cache()
