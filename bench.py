@@ -474,7 +474,7 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         kind, what = cpu_kind()
-        per = args.cpu_graphs_per_core if kind == "port" else max(1, args.cpu_graphs_per_core // 4)
+        per = args.cpu_graphs_per_core * 2          # ~10 s of host work on every core (8-10 k graphs/s per core)
         g, t, busy, wall = cpu_pass(per, cores)                              # before CUDA init (fork)
         cpu_base = {"value": g / busy, "unit": UNIT, "cores": cores, "kind": kind,
                     "tokens_per_s": t / busy,
@@ -484,7 +484,7 @@ def run_gpu(args):
             # TokenDataset + collate, SENT through the oracle port (AutoGraph is not in the reference checkout)
             cpu_extra = {}
             if ref_available():
-                g2, t2, b2, _ = cpu_pass(max(1, per // 2), cores, shard=_ref_gt_shard)
+                g2, t2, b2, _ = cpu_pass(max(1, per // 2), cores, shard=_ref_gt_shard)            # ~3 s
                 cpu_extra["ibtt_graph_token"] = {"value": g2 / b2, "unit": UNIT, "cores": cores, "kind": "reference",
                                                  "tokens_per_s": t2 / b2,
                                                  "sample": f"{max(1, per // 2)} ER graph-token texts per core x {cores}: the reference's "

@@ -142,16 +142,26 @@ def sent_round():
     max_length = int(rng.choice([1, 2, 17, 200, 30000]))
     remap, append = bool(labeled and rng.random() < 0.5), bool(rng.random() < 0.4)
     seed = int(rng.integers(0, 2 ** 40))
+    restart, order = str(rng.choice(["open_first", "unvisited"])), str(rng.choice(["visit_asc", "visit_desc"]))
+    eos = bool(rng.random() < 0.8)
     cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + mx, edge_idx_offset=6 + mx + 12, max_length=max_length, labeled=labeled,
-                            remap_zinc=remap, append_query=append)
+                            remap_zinc=remap, append_query=append, append_eos=eos, restart=restart, bracket_order=order)
     use_ws = [None, True, False][int(rng.integers(0, 3))]       # above 256 nodes: HBM-workspace or shared-memory walk state
     tok, ln = engine.tokenize_sent(csr, cfg, seed=seed, graph_id_base=5, use_workspace=use_ws)
     tok, ln = tok.cpu(), ln.cpu().tolist()
-    ocfg = S.SentConfig(6, 6 + mx, 6 + mx + 12, max_length, labeled)
+    ocfg = S.SentConfig(6, 6 + mx, 6 + mx + 12, max_length, labeled, append_eos=eos)
+    spec = S.SentSpec(restart=restart, bracket_order=order)
     ok = csr_ok
+    if engine.sent_collate_supported(csr, cfg):                 # walk -> item log -> emission into the padded batches
+        B = int(rng.choice([1, 7, 32, 128]))
+        perm = torch.from_numpy(rng.permutation(G)).to(dev) if rng.random() < 0.5 else None
+        t2, l2 = engine.tokenize_sent(csr, cfg, seed=seed, graph_id_base=5)
+        ep2 = engine.pad_mask_epoch(t2.view(-1), torch.arange(G, device=dev, dtype=torch.int64) * t2.shape[1], l2, 5, B, batch_idx=perm)
+        ep1, l1 = engine.sent_collate_epoch(csr, cfg, 5, B, seed=seed, graph_id_base=5, batch_idx=perm)
+        ok = ok and torch.equal(l1, l2) and torch.equal(ep1.X, ep2.X) and torch.equal(ep1.attn, ep2.attn)
     for g, m in enumerate(mols):
         rp, col, ea = S.canonical_csr(m["n"], m["src"], m["dst"], m["attr"])
-        w = S.sent_tokenize(m["n"], rp, col, ocfg, S.PhiloxWords(seed, 5 + g), x=m["x"], eattr=ea)
+        w = S.sent_tokenize(m["n"], rp, col, ocfg, S.PhiloxWords(seed, 5 + g), x=m["x"], eattr=ea, spec=spec)
         if remap:
             w = O.remap_zinc(w, 6, 6 + mx, 6 + mx + 12)
         if append:
@@ -159,7 +169,7 @@ def sent_round():
         ok = ok and tok[g, :ln[g]].tolist() == np.asarray(w).tolist()
     if not ok:
         bad += 1
-    print(f"sent   G={G:5d} nmax={nmax:3d} labeled={int(labeled)} remap={int(remap)} query={int(append)} max_length={max_length:5d}: "
+    print(f"sent   G={G:5d} nmax={nmax:3d} labeled={int(labeled)} remap={int(remap)} query={int(append)} max_length={max_length:5d} {restart}/{order} eos={int(eos)} ws={use_ws}: "
           f"{'ok' if ok else 'MISMATCH'}")
 
 
@@ -202,10 +212,15 @@ def tasks_round():
     print(f"tasks  G={G:5d} kind={kind:8s} buckets={buckets} max_len={max_len:4d}: {'ok' if ok else 'MISMATCH'}")
 
 
+only = sys.argv[3] if len(sys.argv) > 3 else "all"          # "sent": SENT rounds only
 for r in range(rounds):
-    zinc_round()
-    gt_round()
-    sent_round()
-    tasks_round()
+    if only in ("all", "zinc"):
+        zinc_round()
+    if only in ("all", "gt"):
+        gt_round()
+    if only in ("all", "sent"):
+        sent_round()
+    if only in ("all", "tasks"):
+        tasks_round()
 print("mismatching rounds:", bad)
 sys.exit(1 if bad else 0)
