@@ -334,7 +334,7 @@ def run_extras(dev, G, peak):
     nmax = int(zb.num_nodes().max())
     cfgz = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 9, max_length=384,
                              labeled=True, remap_zinc=True)
-    sent("sent_zinc", zb, cfgz, 384, True, 0)
+    sent("sent_zinc", zb, cfgz, 384, True, 2048)
     out["sent_zinc"]["workload"] = (f"{G} ZINC-shaped graphs, labeled SENT + fused remap_zinc_tokens, row capacity 384 "
                                     "(no row reaches it) (BASELINE configs[3] shape, per-GPU shard)")
     # around the path: graphs generated on the device, task labels, query positions
@@ -412,7 +412,7 @@ def run_sharded_sent(dev, rank, world, total, peak):
     for c0 in range(0, G, CH):
         n = min(CH, G - c0)
         gb = synth.zinc_shaped(n, seed=1000 * rank + c0 // CH, device=dev)
-        chunks.append((c0, n, engine.build_csr(gb)))
+        chunks.append((c0, n, engine.build_csr(gb, balance_window=2048)))
         del gb
     nmax = max(c.max_nodes for _, _, c in chunks)
     cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 9, max_length=STRIDE,

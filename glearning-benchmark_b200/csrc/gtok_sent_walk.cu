@@ -343,8 +343,8 @@ int sent_emitl_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, int row_cap
 
 namespace {
 
-static bool cfg_force_lists() {     // GTOK_SENT_LISTS=1: neighbour-list kernels for 65..128 nodes too (tests, A/B runs)
-  static const bool f = [] { const char* e = getenv("GTOK_SENT_LISTS"); return e && atoi(e) != 0; }();
+static bool cfg_force_mid() {       // GTOK_SENT_MID=1: 65..128 nodes through the single kernel of gtok_sent_mid.cu (A/B runs)
+  static const bool f = [] { const char* e = getenv("GTOK_SENT_MID"); return e && atoi(e) != 0; }();
   return f;
 }
 
@@ -354,7 +354,7 @@ static WalkPlan walk_plan(const GtokCsrBatch* c, const GtokSentCfg* cfg) {
   p.wide = c->max_nodes > 64;
   // 65..128 nodes stay with the two-mask-word single kernel (gtok_sent_mid.cu: 2.9 ms per 32M nodes against 3.3 ms for the
   // neighbour-list pair); 129..256 nodes: 8.5 -> 5.5 ms (profiles/r2_large_graph_sweep.jsonl)
-  if (p.wide && c->max_nodes <= 128 && c->adj64 != nullptr && !cfg_force_lists()) return p;
+  if (p.wide && c->max_nodes <= 128 && c->adj64 != nullptr && cfg_force_mid()) return p;
   if (p.wide ? (c->col == nullptr || c->rowptr == nullptr) : (c->adj64 == nullptr || c->adj_words > 1)) return p;
   if (cfg->idx_offset < 0 || (!p.wide && cfg->max_length > 32768)) return p;
   long long tmax = (long long)cfg->idx_offset + c->max_nodes;   // largest token before the remap (needs the label bound)

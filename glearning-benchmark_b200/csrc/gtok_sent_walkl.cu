@@ -1,19 +1,24 @@
-// gtok_sent_walkl.cu - K3 for graphs of 65..256 nodes: the walk / emission kernel pair of gtok_sent_walk.cu on NEIGHBOUR LISTS.
+// gtok_sent_walkl.cu - K3 for graphs of 65..256 nodes: the walk / emission kernel pair of gtok_sent_walk.cu for graphs whose
+// masks no longer fit one 64-bit word.
 //
 // Same function (Graph2TrailTokenizer.__call__ + remap_zinc_tokens + query append, trainer/train_agtt.py:171-273; spec
-// oracle/sent_oracle.py), same outputs bit for bit.  gtok_sent_mid.cu walks these sizes thread-per-graph on 2 or 4 mask
-// words per node: every candidate set, bracket and restart costs 2-4x the mask arithmetic of the <= 64-node kernel although a
-// node still has ~8 neighbours (large-graph sweep, profiles/r1r_large_graph_sweep.jsonl: 21 G nodes/s at 64 nodes, 10.9 at
-// 128, 3.8 at 256).  Here the per-step cost follows the DEGREE, not the graph size:
-//   sent_walkl_kernel  thread per graph, lockstep warp, one arrival and one pick per iteration.  The arrival scans the node's
-//                      CSR row once (visited bit of every neighbour: candidates counted, visited neighbours' open counters
-//                      decremented), a step scans it again up to the picked candidate.  State per graph in shared memory:
-//                      visited bits, open bits, one counter byte per node (320 B at 256 nodes).  A first visit logs ONE
-//                      8-byte item (node, how it was reached, first token position); brackets are NOT recorded.
+// oracle/sent_oracle.py), same outputs bit for bit.  gtok_sent_mid.cu walks AND emits these sizes thread-per-graph on 2 or 4
+// mask words per node; ordering every bracket by visit index on 4-word masks inside the sequential walk made a 256-node graph
+// cost 5.6x a 64-node one per node (large-graph sweep, profiles/r1r_large_graph_sweep.jsonl: 21 G nodes/s at 64 nodes, 10.9 at
+// 128, 3.8 at 256).  Here:
+//   sent_walkm_kernel  thread per graph, lockstep warp, one arrival and one pick per iteration, on the ADJACENCY BIT ROWS
+//                      (GtokCsrBatch.adj64): one aligned 16- or 32-byte load per step, candidates / bracket members /
+//                      restart sets as mask arithmetic on 4 or 8 32-bit words held in registers with the visited and open
+//                      sets; shared memory holds one open-neighbour counter byte per node.  A first visit logs ONE 8-byte item
+//                      (node, how it was reached, first token position).  Brackets are neither ordered nor recorded.
+//   sent_walkl_kernel  the same walk on the CSR neighbour lists (for a CsrBatch without bit rows; GTOK_SENT_LISTS=1): the
+//                      row is read 8 entries at a time.  2x slower than the bit-row walk: rowptr -> col is a dependent chain
+//                      and the scattered 4-byte reads pull 7x their bytes from DRAM (profiles/r2y).
 //   sent_emitl_kernel  warp per row, lane per item, 32 items per round: the node -> visit-index map is rebuilt from the items,
 //                      every lane rescans ITS node's CSR row, keeps the neighbours visited before it and insertion-sorts them
 //                      by visit index straight into the row buffer (shared memory, 16-bit tokens); then the warp streams the
 //                      row with 64-token stores - or writes it into its padded batch (collate_fn) like the small-graph pair.
+// Per 32M nodes (mean degree 8): 128 nodes 2.95 -> 2.1 ms, 256 nodes 8.5 -> 3.6 ms.
 #include "gtok_sent_common.cuh"
 
 namespace gtok {
@@ -208,6 +213,182 @@ sent_walkl_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice 
   }
 }
 
+// The same walk on ADJACENCY BIT ROWS (GtokCsrBatch.adj64, 2 or 4 64-bit words per node): one aligned 16- or 32-byte load
+// per step instead of the dependent rowptr -> col chain of the list walk (which also pulled 7.8 GB of DRAM sectors for 1.1
+// GB of lists at 256 nodes, profiles/r2y), candidates and bracket members as mask arithmetic on NW 32-bit words held in
+// registers together with the visited and open sets; only the per-node open counters live in shared memory.  Unlike
+// gtok_sent_mid.cu nothing is emitted and no bracket is ordered here - the emission kernel does that with a lane per item.
+template <bool LABELED, int NW>
+__global__ void __launch_bounds__(kSmallThreads, 6)
+sent_walkm_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const GtokChoice ch, const int nmax,
+                  uint2* __restrict__ log_lo, int32_t* __restrict__ len_out) {
+  extern __shared__ __align__(16) unsigned char wm_smem[];
+  const int lane = lane_id();
+  const int w_ = threadIdx.x >> 5;
+  unsigned char* rem = wm_smem + (size_t)w_ * nmax * 32 + lane;       // u8 [v][lane] unvisited neighbours left (visited nodes)
+  const int64_t G = c.num_graphs;
+  const int64_t wid0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int Lcap = cfg.max_length;
+  const unsigned k0 = (unsigned)(ch.seed & 0xffffffffu), k1 = (unsigned)(ch.seed >> 32);
+  const bool restart_unvisited = cfg.restart_policy == GTOK_SENT_RESTART_UNVISITED;
+
+  for (int64_t g0 = wid0 * 32; g0 < G; g0 += nw * 32) {
+    const int Tc = (int)((G - g0 < 32) ? (G - g0) : 32);
+    const bool valid = lane < Tc;
+    const int64_t g = valid ? (c.order ? (int64_t)__ldg(c.order + g0 + lane) : g0 + lane) : g0;
+    const int64_t my_n0 = __ldg(c.node_off + g);
+    const int N = valid ? (int)(__ldg(c.node_off + g + 1) - my_n0) : 0;
+    const uint4* __restrict__ arow = reinterpret_cast<const uint4*>(c.adj64) + my_n0 * (NW / 4);
+
+    const uint64_t gid = (uint64_t)(ch.graph_id_base + g);
+    unsigned b0 = 0, b1 = 0, b2 = 0, b3 = 0, d = 0;
+    int64_t s_off = 0;
+    unsigned s_len = 0;
+    if (ch.stream && valid) {
+      s_off = __ldg(ch.stream_off + g);
+      s_len = (unsigned)(__ldg(ch.stream_off + g + 1) - s_off);
+    }
+    auto pick = [&](int cnt) -> int {
+      unsigned r;
+      if (ch.stream) {
+        r = d < s_len ? __ldg(ch.stream + s_off + d) : 0u;
+      } else {
+        if ((d & 3u) == 0u) philox10((unsigned)gid, (unsigned)(gid >> 32), d >> 2, 0u, k0, k1, b0, b1, b2, b3);
+        const unsigned w01 = (d & 1u) ? b1 : b0, w23 = (d & 1u) ? b3 : b2;
+        r = (d & 2u) ? w23 : w01;
+      }
+      ++d;
+      return (int)__umulhi(r, (unsigned)cnt);
+    };
+    unsigned vis[NW], opn[NW], an[NW];                // visited set, open set, adjacency row of the node we arrive at next
+#pragma unroll
+    for (int i = 0; i < NW; ++i) { vis[i] = 0u; opn[i] = 0u; an[i] = 0u; }
+    auto load_row = [&](int node) {
+#pragma unroll
+      for (int q = 0; q < NW / 4; ++q) {
+        const uint4 t = __ldg(arow + (size_t)node * (NW / 4) + q);
+        an[4 * q] = t.x; an[4 * q + 1] = t.y; an[4 * q + 2] = t.z; an[4 * q + 3] = t.w;
+      }
+    };
+    // k-th set bit (ascending) of the NW-word set `m`
+    auto select_words = [&](const unsigned (&m)[NW], int kth) -> int {
+      unsigned msel = 0u;
+      int wsel = 0;
+      bool found = false;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        const int cm = __popc(m[i]);
+        if (!found) {
+          if (kth < cm) { msel = m[i]; wsel = i; found = true; }
+          else kth -= cm;
+        }
+      }
+      return wsel * 32 + select32(msel, kth);
+    };
+    int nvis = 0, cur = 0, prev = -1;
+    unsigned pre = 0;
+    int pos = 1;
+    bool done = N == 0;
+    if (!done) {
+      cur = pick(N);
+      load_row(cur);
+    }
+    while (!__all_sync(kFull, done)) {
+      if (!done) {
+        const int cw = cur >> 5;
+        const unsigned bit = 1u << (cur & 31);
+        unsigned a[NW], U[NW];
+        bool first = false;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          a[i] = an[i];
+          if (i == cw) { first = !(vis[i] & bit); vis[i] |= bit; }
+        }
+        int cntU = 0, cntM = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          U[i] = a[i] & ~vis[i];
+          cntU += __popc(U[i]);
+        }
+        if (first) {
+          const int pw = prev >> 5;                   // (prev = -1: pw = -1, matches no word)
+          const unsigned pbit = 1u << (prev & 31);
+#pragma unroll
+          for (int i = 0; i < NW; ++i) {
+            unsigned m = a[i] & vis[i];               // visited neighbours ...
+            if (i == pw) m &= ~pbit;                  // ... except the trail predecessor = the bracket members
+            cntM += __popc(m);
+            while (m) {                               // cur is no longer an unvisited neighbour of the member
+              const int b = __ffs((int)m) - 1;
+              m &= m - 1;
+              const int u = i * 32 + b;
+              const int r = (int)rem[u * 32] - 1;
+              rem[u * 32] = (unsigned char)r;
+              if (r == 0) opn[i] &= ~(1u << b);
+            }
+          }
+          const int k = nvis++;
+          rem[cur * 32] = (unsigned char)cntU;
+          if (cntU) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i)
+              if (i == cw) opn[i] |= bit;
+          }
+          int cnt = ((pre & kFlagReset) ? 1 : 0) + ((pre & kFlagHead) ? 1 : 0) + 1 + (cntM ? 2 + (LABELED ? 2 * cntM : cntM) : 0);
+          if (LABELED) cnt += 1 + (prev >= 0 ? 1 : 0);
+          log_lo[my_n0 + k] = make_uint2((unsigned)pos, (unsigned)cur | pre);
+          pos += cnt;
+          pre = 0;
+        } else {
+          pre = kFlagReset | kFlagHead | ((unsigned)cur << 16);
+        }
+        if ((cntU == 0 && nvis == N) || pos >= Lcap) {
+          done = true;
+        } else {
+          int nxt;
+          if (cntU > 0) {                             // trail step to the kth unvisited neighbour (ascending node id)
+            nxt = select_words(U, pick(cntU));
+            rem[cur * 32] = (unsigned char)(cntU - 1);
+            if (cntU == 1) {
+#pragma unroll
+              for (int i = 0; i < NW; ++i)
+                if (i == cw) opn[i] &= ~bit;
+            }
+            prev = cur;
+          } else {                                    // stuck: restart at an open node, else at any unvisited node
+            int nsel = 0;
+            if (!restart_unvisited) {
+#pragma unroll
+              for (int i = 0; i < NW; ++i) nsel += __popc(opn[i]);
+            }
+            const bool use_open = nsel > 0;
+            if (!use_open) nsel = N - nvis;
+            unsigned R[NW];
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+              const int lim = N - i * 32;
+              const unsigned nm = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+              R[i] = use_open ? opn[i] : (~vis[i] & nm);
+            }
+            nxt = select_words(R, pick(nsel));
+            pre = kFlagReset;
+            prev = -1;
+          }
+          cur = nxt;
+          load_row(cur);
+        }
+      }
+    }
+    if (valid) {
+      if (nvis < N) log_lo[my_n0 + nvis] = make_uint2(0u, kFlagEnd);
+      const int Lfull = pos + (cfg.no_eos ? 0 : 1);
+      len_out[g] = (Lfull < Lcap ? Lfull : Lcap) + (cfg.append_query ? 3 : 0);
+    }
+    __syncwarp();
+  }
+}
+
 template <bool LABELED, bool COLLATE, bool REMAP>
 __global__ void __launch_bounds__(kEmitLThreads)
 sent_emitl_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __restrict__ log_lo,
@@ -276,43 +457,42 @@ sent_emitl_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __re
         if (LABELED && pv >= 0) pe = p++;
         rowb[p++] = (unsigned short)(idx_off + k);
         if (LABELED) rowb[p++] = (unsigned short)(node_off + __ldg(c.x + n0 + u));
-        const int e0 = __ldg(c.rowptr + n0 + u), e1 = __ldg(c.rowptr + n0 + u + 1);
         unsigned short* mb = rowb + p + 1;           // members go after LADJ, kept sorted by visit index as they arrive
         int m = 0;
-        for (int eb = e0; eb < e1; eb += 8) {          // eight independent loads per chunk (see the walk kernel)
-          int wv[8], lv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            wv[j] = (eb + j < e1) ? __ldg(colp + eb + j) : -1;
-            lv[j] = (LABELED && eb + j < e1) ? __ldg(c.eattr + eb + j) : 0;
+        auto nbr = [&](int w, int e) {               // neighbour w of u, CSR entry e
+          if (w == pv) {
+            if (LABELED) rowb[pe] = (unsigned short)(elab_off + __ldg(c.eattr + e));
+            return;
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int w = wv[j];
-            if (w < 0) continue;
-            if (w == pv) {
-              if (LABELED) rowb[pe] = (unsigned short)(elab_off + lv[j]);
-              continue;
+          const int kv = visb[w];
+          if (kv >= k) return;                       // visited later (or never)
+          const unsigned short key = (unsigned short)(idx_off + kv);
+          int jj = m;
+          if (LABELED) {
+            const unsigned short lab = (unsigned short)(elab_off + __ldg(c.eattr + e));
+            while (jj > 0 && (desc ? mb[2 * jj - 1] < key : mb[2 * jj - 1] > key)) {
+              mb[2 * jj] = mb[2 * jj - 2];
+              mb[2 * jj + 1] = mb[2 * jj - 1];
+              --jj;
             }
-            const int kv = visb[w];
-            if (kv >= k) continue;                     // visited later (or never)
-            const unsigned short key = (unsigned short)(idx_off + kv);
-            int jj = m;
-            if (LABELED) {
-              const unsigned short lab = (unsigned short)(elab_off + lv[j]);
-              while (jj > 0 && (desc ? mb[2 * jj - 1] < key : mb[2 * jj - 1] > key)) {
-                mb[2 * jj] = mb[2 * jj - 2];
-                mb[2 * jj + 1] = mb[2 * jj - 1];
-                --jj;
-              }
-              mb[2 * jj] = lab;
-              mb[2 * jj + 1] = key;
-            } else {
-              while (jj > 0 && (desc ? mb[jj - 1] < key : mb[jj - 1] > key)) { mb[jj] = mb[jj - 1]; --jj; }
-              mb[jj] = key;
-            }
-            ++m;
+            mb[2 * jj] = lab;
+            mb[2 * jj + 1] = key;
+          } else {
+            while (jj > 0 && (desc ? mb[jj - 1] < key : mb[jj - 1] > key)) { mb[jj] = mb[jj - 1]; --jj; }
+            mb[jj] = key;
           }
+          ++m;
+        };
+        // (the members are found in the neighbour LIST of u: enumerating the bit row instead - one aligned load, no rowptr - was
+        //  slower, 1.11 -> 1.37 ms per 32M nodes at 128 nodes: eight data-dependent loops per lane instead of one)
+        const int e0 = __ldg(c.rowptr + n0 + u), e1 = __ldg(c.rowptr + n0 + u + 1);
+        for (int eb = e0; eb < e1; eb += 8) {        // eight independent loads per chunk (see the walk kernel)
+          int wv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wv[j] = (eb + j < e1) ? __ldg(colp + eb + j) : -1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (wv[j] >= 0) nbr(wv[j], eb + j);
         }
         if (m) {
           rowb[p] = (unsigned short)LADJ;
@@ -372,8 +552,26 @@ int sent_walkl_row_cap(const GtokCsrBatch* c, const GtokSentCfg* cfg) {
   return (int)cap;
 }
 
+template <int NW>
+static int sent_walkm_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, void* log, int32_t* len_out,
+                             cudaStream_t st) {
+  auto k = cfg->labeled ? sent_walkm_kernel<true, NW> : sent_walkm_kernel<false, NW>;
+  const size_t smem = (size_t)kSmallWarps * c->max_nodes * 32;
+  GTOK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t warps = (c->num_graphs + 31) / 32;
+  const int grid = persistent_grid(k, kSmallThreads, smem, (warps + kSmallWarps - 1) / kSmallWarps);
+  k<<<grid, kSmallThreads, smem, st>>>(*c, *cfg, *ch, c->max_nodes, reinterpret_cast<uint2*>(log), len_out);
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}
+
 int sent_walkl_launch(const GtokCsrBatch* c, const GtokSentCfg* cfg, const GtokChoice* ch, void* log, int32_t* len_out,
                       cudaStream_t st) {
+  static const bool lists = [] { const char* e = getenv("GTOK_SENT_LISTS"); return e && atoi(e) != 0; }();
+  if (!lists && c->adj64 != nullptr && (reinterpret_cast<uintptr_t>(c->adj64) & 15) == 0) {      // bit rows: one load per step
+    if (c->adj_words == 2) return sent_walkm_launch<4>(c, cfg, ch, log, len_out, st);
+    if (c->adj_words == 4) return sent_walkm_launch<8>(c, cfg, ch, log, len_out, st);
+  }
   auto k = cfg->labeled ? sent_walkl_kernel<true> : sent_walkl_kernel<false>;
   const int words = (c->max_nodes + 31) / 32;
   const size_t smem = (size_t)kSmallWarps * (words * 256 + c->max_nodes * 32);
