@@ -655,10 +655,24 @@ def run_gpu(args):
             avg = sum(v) / len(v)
             two_step[name] = {"ms": avg, "algo_bytes": algo[name], "GBps": algo[name] / avg / 1e6,
                               "frac": algo[name] / avg / 1e6 / peak}
-        traffic = None
+        # ncu's DRAM bytes of the dominant kernel (one `--set full` capture of this 1M-graph launch, tools/update_traffic.py):
+        # reported only while the kernel's source still hashes to what was captured - never a stale figure
+        traffic, traffic_note = None, "no ncu capture for this workload size"
         tj = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tj) and G == 1_000_000:
-            traffic = json.load(open(tj)).get(dom, {}).get("dram_bytes_per_launch")
+            ent = json.load(open(tj)).get(dom, {})
+            import hashlib
+            h = hashlib.sha256()
+            try:
+                for f in ent.get("source_files", []):
+                    h.update(open(os.path.join(ROOT, "glearning-benchmark_b200", "csrc", f), "rb").read())
+                fresh = bool(ent.get("source_files")) and h.hexdigest()[:16] == ent.get("source_sha16")
+            except OSError:
+                fresh = False
+            if fresh:
+                traffic, traffic_note = ent.get("dram_bytes_per_launch"), f"ncu capture {ent.get('source')} (kernel source unchanged since)"
+            else:
+                traffic_note = "kernel source changed since the last ncu capture (profiles/traffic.json): re-capture with tools/update_traffic.py"
         step_algo = algo["zinc_serialize"] + 9 * padded_cells - 8 * total_tokens     # SURVEY 8d "fused" figure for the whole step
         step_s = ms / 1e3 / args.steps
         line = {
@@ -692,7 +706,7 @@ def run_gpu(args):
                                       "(pack_ms_untimed = that host-side cost on this box, per shard); not the headline"},
             "gpu_launches": pipe.kernel_launches_per_pass * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                         "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                          "algo_bytes_per_launch": kernels[dom]["algo_bytes"]},
             "kernels": kernels,
             "kernels_two_step": two_step,
