@@ -118,7 +118,7 @@ class GraphTokenDatasetForAutoGraph(Dataset):
         self.split, self.use_split_tasks_dirs, self.seed = split, use_split_tasks_dirs, seed
         self.num_graphs, self.num_pairs_per_graph = num_graphs, num_pairs_per_graph
         self._root, self.transform, self.pre_transform, self.pre_filter = root, transform, pre_transform, pre_filter
-        self._records = self._process()
+        self._records = self._load_or_process()
         self._gb = None
 
     # ------------------------------------------------------------------
@@ -146,6 +146,27 @@ class GraphTokenDatasetForAutoGraph(Dataset):
         if self.num_pairs_per_graph is not None:
             name += f"_np{self.num_pairs_per_graph}"
         return os.path.join(self._root, 'processed', name)
+
+    def _load_or_process(self):
+        """The reference is an InMemoryDataset: process() runs once, later constructions load processed/<key>/data.pt
+        (reference :233-253, :406-408).  Same contract here: the parsed records (node count, edge list, label, query) are
+        cached under the same directory name (file `gtok_records.pt`: the reference's own `data.pt` holds collated PyG
+        tensors and must stay readable by the reference)."""
+        path = os.path.join(self.processed_dir, 'gtok_records.pt')
+        if os.path.exists(path):
+            try:
+                return torch.load(path, weights_only=False)
+            except Exception:                       # unreadable / truncated cache: rebuild it
+                pass
+        recs = self._process()
+        try:
+            os.makedirs(self.processed_dir, exist_ok=True)
+            tmp = path + f".{os.getpid()}.tmp"
+            torch.save(recs, tmp)
+            os.replace(tmp, path)
+        except OSError:                             # read-only dataset root: keep working without the cache
+            pass
+        return recs
 
     def _process(self):
         import random
@@ -175,6 +196,11 @@ class GraphTokenDatasetForAutoGraph(Dataset):
                     query = parse_query_nodes_from_text(rec['text'])
                 if per_file and query is None:
                     continue
+                if self.pre_filter is not None:       # reference :350-351 / :396-397: the filter sees the Data object
+                    el = [tuple(e) for e in edges]
+                    ei = torch.tensor(el, dtype=torch.long).t().contiguous() if el else torch.empty((2, 0), dtype=torch.long)
+                    if not self.pre_filter(GraphData(ei, torch.tensor([int(label)], dtype=torch.long), n, query)):
+                        continue
                 bucket.append((n, [tuple(e) for e in edges], int(label), query))
             if per_file and len(bucket) > self.num_pairs_per_graph:
                 bucket = rng.sample(bucket, self.num_pairs_per_graph)

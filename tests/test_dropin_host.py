@@ -122,3 +122,24 @@ def test_balance_helpers():
     assert len(g.balance_classes(ex, "oversample", seed=1)) == 40
     with pytest.raises(ValueError):
         g.balance_classes(ex, "bogus")
+
+
+def test_autograph_dataset_processed_cache_and_pre_filter(tmp_path):
+    """InMemoryDataset contract of the reference class (graph_token_dataset_autograph.py:233-253, :350-351, :406-408): the
+    parse runs once per (task, algorithms, split, sampling) key and later constructions load the processed file - here even
+    after the raw JSON files are gone; pre_filter sees Data-like objects and drops graphs before they are stored."""
+    import shutil
+    import graph_data_loader as g
+    _write_tree(tmp_path, "cycle_check")
+    ds = g.GraphTokenDatasetForAutoGraph(str(tmp_path), task="cycle_check", algorithm=["er", "ba"], split="train", seed=3)
+    first = [(d.num_nodes, d.edge_index.tolist(), int(d.y)) for d in ds]
+    assert os.path.exists(os.path.join(ds.processed_dir, "gtok_records.pt"))
+    shutil.rmtree(tmp_path / "tasks_train")
+    ds2 = g.GraphTokenDatasetForAutoGraph(str(tmp_path), task="cycle_check", algorithm=["er", "ba"], split="train", seed=3)
+    assert [(d.num_nodes, d.edge_index.tolist(), int(d.y)) for d in ds2] == first
+    # another key -> another cache entry; its raw files are still there
+    big = g.GraphTokenDatasetForAutoGraph(str(tmp_path), task="cycle_check", algorithm="er", split="test", seed=3,
+                                          pre_filter=lambda d: d.num_nodes >= 10 and int(d.y) in (0, 1))
+    allg = g.GraphTokenDatasetForAutoGraph(str(tmp_path / "."), task="cycle_check", algorithm="er", split="test", seed=3,
+                                           num_graphs=1000)
+    assert 0 < len(big) <= len(allg) and all(d.num_nodes >= 10 for d in big)
