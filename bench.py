@@ -399,6 +399,80 @@ def run_extras(dev, G, peak):
     return out
 
 
+def run_large_sweep(dev, rank, world, nodes_per_gpu, peak):
+    """BASELINE configs[4]: large-graph sweep, 64..4096 nodes per graph (mean degree 8), `nodes_per_gpu` nodes per point and
+    GPU (weak scaling: every rank generates and tokenizes its own graphs, no collective on the data path).  Per point: fused
+    IBTT tokenize -> padded batches (batch 128), SENT stand-alone, and the whole SENT epoch (trails + collate_fn; fused walk ->
+    emission up to 256 nodes, SENT + K4 beyond).  Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from gtok import engine, synth
+    def timeit(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    vocab = {t: i for i, t in enumerate(["<pad>", "<bos>", "<e>", "<n>", "<q>", "<p>", "<eos>", "yes", "no"])}
+    for k in range(4096):
+        vocab[str(k)] = len(vocab)
+    vocab["has_cycle"] = len(vocab)
+    points = []
+    for N in (64, 128, 256, 512, 1024, 2048, 4096):
+        G = max(128, nodes_per_gpu // N)
+        gb = synth.er_sparse(G, N, mean_degree=8.0, seed=1000 * N + rank, device=dev)
+        E = gb.src.numel()
+        B = 128
+        max_len = 3 * int(gb.num_entries().max()) + N + 5
+        ep, lens = engine.ibtt_collate_epoch(gb, vocab, "cycle_check", max_len, B)
+        cells = int(ep.xoff[-1])
+        X, A = ep.X, ep.attn
+        ms_i = timeit(lambda: engine.ibtt_collate_epoch(gb, vocab, "cycle_check", max_len, B, max_nodes=N, X=X, attn=A), 3, 1)
+        b_i = 8 * E + 32 * G + 9 * cells
+        del ep, X, A
+        csr = engine.build_csr(gb)
+        Lcap = 2 + 2 * N + 2 * (E // G + N) + 64
+        Lcap = min(Lcap + (Lcap & 1), 65534)
+        cfg = engine.SentConfig(idx_offset=6, max_length=Lcap)
+        out = torch.empty((G, Lcap), dtype=torch.int64, device=dev)
+        ms_s = timeit(lambda: engine.tokenize_sent(csr, cfg, seed=1, graph_id_base=rank * G, out=out, stride=Lcap), 3, 1)
+        _, ln = engine.tokenize_sent(csr, cfg, seed=1, graph_id_base=rank * G, out=out, stride=Lcap)
+        tot = int(ln.sum())
+        b_s = csr.sent_input_bytes(False) + 8 * tot + 4 * G
+        off = torch.arange(G, device=dev, dtype=torch.int64) * Lcap
+        ep = engine.pad_mask_epoch(out.view(-1), off, ln, 5, B)
+        cells_s = int(ep.xoff[-1])
+        X, A = ep.X, ep.attn
+        fused = engine.sent_collate_supported(csr, cfg)
+        if fused:
+            ms_e = timeit(lambda: engine.sent_collate_epoch(csr, cfg, 5, B, seed=1, graph_id_base=rank * G, X=X, attn=A), 3, 1)
+        else:
+            def two():
+                engine.tokenize_sent(csr, cfg, seed=1, graph_id_base=rank * G, out=out, stride=Lcap)
+                engine.pad_mask_epoch(out.view(-1), off, ln, 5, B, X=X, attn=A)
+            ms_e = timeit(two, 3, 1)
+        b_e = csr.sent_input_bytes(False) + 9 * cells_s + 4 * G
+        t = torch.tensor([ms_i, ms_s, ms_e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_i, ms_s, ms_e = (float(v) for v in t)
+        points.append({"nodes_per_graph": N, "graphs_per_gpu": G, "ibtt_collate_ms": ms_i, "ibtt_collate_frac": b_i / ms_i / 1e6 / peak,
+                       "sent_ms": ms_s, "sent_frac": b_s / ms_s / 1e6 / peak, "sent_mean_len": tot / G,
+                       "sent_epoch_ms": ms_e, "sent_epoch_frac": b_e / ms_e / 1e6 / peak, "sent_epoch_fused": bool(fused),
+                       "nodes_per_s_all_gpus": G * N * world / ms_s * 1e3})
+        del out, csr, gb, ep, X, A
+        torch.cuda.empty_cache()
+    return {"workload": f"large-graph sweep, {nodes_per_gpu} nodes per point and GPU on {world} GPU(s), mean degree 8, batch 128 "
+                        "(BASELINE configs[4]); fractions = algorithmic bytes / time / measured HBM peak, per GPU",
+            "n_gpus": world, "scaling": "weak", "points": points}
+
+
 def run_sharded_sent(dev, rank, world, total, peak):
     """BASELINE configs[3]: labeled SENT + fused remap + collate_fn over `total` ZINC-shaped graphs sharded by index
     across the ranks (STRONG scaling: total fixed).  No collective on the data path; Philox words keyed by the GLOBAL
@@ -622,6 +696,8 @@ def run_gpu(args):
     if not args.no_extras:
         sh = run_sharded_sent(dev, rank, world, args.sharded_sent_graphs, peak_gbs())
         extras = dict(extras or {}, sent_zinc_10M_sharded=sh)
+        if args.sweep_nodes > 0:
+            extras["large_graph_sweep"] = run_large_sweep(dev, rank, world, args.sweep_nodes, peak_gbs())
     names = list(pre)
     t = torch.tensor([ms, e2e_ms] + [pre[n][0] for n in names], dtype=torch.float64, device=dev)
     if world > 1:
@@ -755,6 +831,8 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="keep the launcher's CPU affinity (default: bind each rank to its GPU's NUMA node)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pieces the int64 PyG tensors travel in (copy / narrow overlap)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (graph-token IBTT, SENT)")
+    ap.add_argument("--sweep-nodes", type=int, default=32_000_000,
+                    help="nodes per point and GPU of the large-graph sweep extra (BASELINE configs[4]); 0 = skip")
     ap.add_argument("--sharded-sent-graphs", type=int, default=10_000_000,
                     help="total graphs of the strong-scaling SENT extra (BASELINE configs[3]), split over the ranks")
     ap.add_argument("--zinc-fused", type=int, default=-1, help="-1 auto, 0 three-kernel path, 1 fused single pass")

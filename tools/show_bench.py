@@ -11,6 +11,12 @@ print("  roofline", d["roofline"])
 print("  step_roofline", round(d["step_roofline"]["frac"], 3), d["clocks"])
 print("  cpu_baseline", d.get("cpu_baseline"))
 for k, v in (d.get("extras") or {}).items():
+    if "points" in v:
+        print(f"  extra {k}: {v['workload']}")
+        for p in v["points"]:
+            print(f"      N={p['nodes_per_graph']:5d} G={p['graphs_per_gpu']:7d}  ibtt_collate {p['ibtt_collate_ms']:.3f} ms ({p['ibtt_collate_frac']:.2f})  "
+                  f"sent {p['sent_ms']:.3f} ms ({p['sent_frac']:.3f})  sent epoch {p['sent_epoch_ms']:.3f} ms ({p['sent_epoch_frac']:.3f}, fused={p['sent_epoch_fused']})")
+        continue
     if "ms_per_step" not in v:
         print(f"  extra {k}: " + "  ".join(f"{a}={b:.4g}" if isinstance(b, float) else f"{a}={b}" for a, b in v.items() if a != "workload"))
         continue
