@@ -397,8 +397,10 @@ extern "C" int gtok_ibtt_collate(const GtokGraphBatch* batch, const GtokIbttRule
   const bool narrow = maxid < 65536 && rules->max_token_id > 0 && rules->max_token_id < 65536;
   const int esz = narrow ? 2 : 4;
   const int tbl_cap = rules->node_tok_len < 4096 ? rules->node_tok_len : 4096;
+  // rows up to 4096 tokens (16-bit staging: 8 KB per warp, still 3 CTAs per SM) go through the row buffer when EVERY row fits;
+  // workloads with longer rows keep the 2048-token buffer (more resident warps for the closed-form path they mostly take)
   int row_cap = rules->max_len + 8;
-  if (row_cap > 2048) row_cap = 2048;
+  if (row_cap > (narrow ? 4096 : 2048)) row_cap = 2048;
   row_cap = (row_cap + 7) & ~7;
   const size_t smem = (((size_t)tbl_cap * esz + 15) & ~(size_t)15) + (size_t)kIcWarps * row_cap * esz;
   cudaStream_t st = (cudaStream_t)stream;
