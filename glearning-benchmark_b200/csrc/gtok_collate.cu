@@ -96,8 +96,14 @@ batch_extents_kernel(const int32_t* __restrict__ row_len, const int64_t* __restr
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(kFull, m, d));
   if (lane == 0) {
+    const int64_t cells = (r1 - r0) * (int64_t)m;
+    if (cells > 0x7fffffffll) {          // one batch of >= 2^31 cells (17 GB of int64): fail loudly, never wrap into a wrong xoff
+      printf("gtok batch_extents: batch %lld has %lld rows x %d tokens >= 2^31 cells; use a smaller batch size\n",
+             (long long)k, (long long)(r1 - r0), m);
+      __trap();
+    }
     lmax_out[k] = m;
-    cells_out[k] = (int32_t)((r1 - r0) * m);
+    cells_out[k] = (int32_t)cells;
   }
 }
 

@@ -399,7 +399,7 @@ GTOK_API int gtok_pad_mask(const int64_t* tok, const int64_t* row_start, const i
  *      batch_idx order (batch k = rows [k*B, min(G,(k+1)*B))); batch k is padded
  *      to its OWN Lmax_k = max row_len in the batch, exactly as collate does.
  *      gtok_batch_extents writes lmax int32[nb] and cells int32[nb]
- *      (= rows_k * Lmax_k; the caller scans cells into xoff int64[nb+1] with
+ *      (= rows_k * Lmax_k, which must stay below 2^31 per batch: the kernel traps otherwise; the caller scans cells into xoff int64[nb+1] with
  *      gtok_scan_offsets); gtok_pad_mask_batched then writes batch k at
  *      X + xoff[k] / attn + xoff[k], row-major [rows_k, Lmax_k]. nb = ceil(G/B). */
 GTOK_API int gtok_batch_extents(const int32_t* row_len, const int64_t* batch_idx, int64_t G, int64_t B,
