@@ -51,5 +51,50 @@ __device__ __forceinline__ int select64(unsigned long long m, int k) {
 }
 
 
+// r / B for 0 <= r, 0 < B (both below 2^31 on the fast path): float estimate + fix-up instead of a 64-bit division
+// (~70 instructions per row in the emission kernels, which are issue bound).
+__device__ __forceinline__ int64_t row_batch(int64_t r, int64_t B) {
+  if ((r | B) >> 31) return r / B;
+  const unsigned ru = (unsigned)r, bu = (unsigned)B;
+  unsigned q = (unsigned)__fdividef((float)ru, (float)bu);
+  while ((unsigned long long)q * bu > ru) --q;                 // the estimate is off by at most a few units
+  while ((unsigned long long)(q + 1u) * bu <= ru) ++q;
+  return (int64_t)q;
+}
+
+// One warp writes a padded batch row from its narrow row buffer: X[0..Lm) = tok(q) for q < L, pad beyond; the mask bytes come
+// from a 17-entry table in shared memory (tbl[k] = 16 bytes whose low k are 0x01, fill_mask_table).  Like warp_pad_row, with the
+// mask half on the table.
+template <typename F>
+__device__ __forceinline__ void warp_pad_row_tbl(int len, int Lmax, int64_t pad, int64_t* __restrict__ xrow,
+                                                 uint8_t* __restrict__ arow, const ulonglong2* __restrict__ tbl, F tok) {
+  const int lane = lane_id();
+  const int head = (int)((reinterpret_cast<uintptr_t>(xrow) >> 3) & 1);
+  if (head && lane == 0 && Lmax > 0) st_stream_i64(xrow, 0 < len ? (int64_t)tok(0) : pad);
+  const int npair = (Lmax - head) >> 1;
+  const int nfull = (len - head) >> 1;                   // pairs that lie entirely inside the row
+  for (int j = lane; j < npair; j += kWarp) {
+    const int p = head + 2 * j;
+    int64_t a = pad, b = pad;
+    if (j < nfull) { a = (int64_t)tok(p); b = (int64_t)tok(p + 1); }
+    else if (p < len) a = (int64_t)tok(p);
+    st_stream_i64x2(xrow + p, a, b);
+  }
+  const int tailx = head + 2 * npair;
+  if (tailx < Lmax && lane == 31) st_stream_i64(xrow + tailx, tailx < len ? (int64_t)tok(tailx) : pad);
+  int mh = (int)((16 - (reinterpret_cast<uintptr_t>(arow) & 15)) & 15);
+  if (mh > Lmax) mh = Lmax;
+  if (lane < mh) arow[lane] = (uint8_t)(lane < len);
+  const int nvec = (Lmax - mh) >> 4;
+  for (int q = lane; q < nvec; q += kWarp) {
+    const int p = mh + 16 * q;
+    int nv = len - p;
+    nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
+    __stcs(reinterpret_cast<ulonglong2*>(arow + p), tbl[nv]);
+  }
+  const int tail = mh + 16 * nvec;
+  if (tail + lane < Lmax && lane < 16) arow[tail + lane] = (uint8_t)(tail + lane < len);
+}
+
 }  // namespace
 }  // namespace gtok

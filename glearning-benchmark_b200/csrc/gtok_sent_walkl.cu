@@ -400,6 +400,11 @@ sent_emitl_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __re
   __shared__ unsigned short s_remap[kRemapN];
   __shared__ unsigned char s_ord[kEmitLWarps][256];
   __shared__ unsigned char s_vis[kEmitLWarps][256];
+  __shared__ ulonglong2 s_m16[17];
+  if (COLLATE) {
+    fill_mask_table(s_m16, threadIdx.x);
+    __syncthreads();
+  }
   const int lane = lane_id();
   const int w_ = threadIdx.x >> 5;
   unsigned short* rowb = reinterpret_cast<unsigned short*>(el_smem) + (size_t)w_ * row_cap;
@@ -522,7 +527,7 @@ sent_emitl_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __re
       if ((L0 & 1) && lane == 0) st_stream_i64(row + L0 - 1, tokv(L0 - 1));
       if (q3 && lane < 3) row[L0 + lane] = qt;
     } else {
-      const int64_t kbatch = r / B;
+      const int64_t kbatch = row_batch(r, B);
       const int Lm = __ldg(lmax + kbatch);
       const int64_t cell0 = __ldg(xoff + kbatch) + (r - kbatch * B) * (int64_t)Lm;
       const int64_t q0 = q3 ? __shfl_sync(kFull, qt, 0) : 0, q1 = q3 ? __shfl_sync(kFull, qt, 1) : 0,
@@ -531,7 +536,7 @@ sent_emitl_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __re
         if (q < L0) return tokv(q);
         return q == L0 ? q0 : (q == L0 + 1 ? q1 : q2);
       };
-      warp_pad_row(L, Lm, pad_id, out + cell0, attn + cell0, full);
+      warp_pad_row_tbl(L, Lm, pad_id, out + cell0, attn + cell0, s_m16, full);
     }
     __syncwarp();
   }

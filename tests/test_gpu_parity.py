@@ -1288,6 +1288,12 @@ def test_sent_walk_emit_kernels_vs_single_kernel_and_oracle(dev, labeled, nmax):
         t1, l1 = engine.tokenize_sent(csr, cfg, seed=17, graph_id_base=5)
         t0, l0 = engine.tokenize_sent(csr, cfg, seed=17, graph_id_base=5, use_workspace=False)
         assert torch.equal(l1, l0)
+        if nmax > 64:       # a CSR without adjacency bit rows: the neighbour-list walk kernel instead of the bit-row walk
+            import dataclasses
+            bare = dataclasses.replace(csr, adj64=None, adj_words=0, scratch=None, order=None)
+            t2, l2 = engine.tokenize_sent(bare, cfg, seed=17, graph_id_base=5)
+            m2 = torch.arange(t2.shape[1], device=dev)[None, :] < l2[:, None]
+            assert torch.equal(l2, l1) and torch.equal(t2[m2], t1[m2])
         t1, t0, ln = t1.cpu(), t0.cpu(), l1.cpu().tolist()
         spec = S.SentSpec(restart=restart, bracket_order=order)
         ocfg = S.SentConfig(6, no, eo, max_length, labeled)
