@@ -489,14 +489,19 @@ def run_sharded_sent(dev, rank, world, total, peak):
         chunks.append((c0, n, engine.build_csr(gb, balance_window=2048)))
         del gb
     nmax = max(c.max_nodes for _, _, c in chunks)
-    cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 9, max_length=STRIDE,
+    # configs/agtt_zinc.yaml:5 has max_len 1024; the fused path takes it as it is (no [G, max_length] buffer exists), the
+    # two-step fallback caps the row buffer at 384 tokens (no ZINC-shaped row reaches 200)
+    cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 9, max_length=1024,
                             labeled=True, remap_zinc=True)
-    m = min(CH, G)
-    buf = torch.empty((m, STRIDE), dtype=torch.int64, device=dev)
-    row_start = torch.arange(m, device=dev, dtype=torch.int64) * STRIDE
-    Xc, Ac = torch.empty(m * 200, dtype=torch.int64, device=dev), torch.empty(m * 200, dtype=torch.bool, device=dev)
-
     fused = all(engine.sent_collate_supported(c, cfg) for _, _, c in chunks)
+    m = min(CH, G)
+    buf = row_start = None
+    if not fused:
+        cfg = engine.SentConfig(idx_offset=6, node_idx_offset=6 + nmax, edge_idx_offset=6 + nmax + 9, max_length=STRIDE,
+                                labeled=True, remap_zinc=True)
+        buf = torch.empty((m, STRIDE), dtype=torch.int64, device=dev)
+        row_start = torch.arange(m, device=dev, dtype=torch.int64) * STRIDE
+    Xc, Ac = torch.empty(m * 200, dtype=torch.int64, device=dev), torch.empty(m * 200, dtype=torch.bool, device=dev)
 
     def epoch(seed):
         toks = 0
@@ -533,7 +538,7 @@ def run_sharded_sent(dev, rank, world, total, peak):
     del buf, Xc, Ac, chunks
     return {"workload": f"AGTT SENT (labeled + fused remap_zinc_tokens) + collate_fn of every batch of {BATCH}: {G * world} "
                         f"ZINC-shaped graphs sharded by index over {world} GPU(s) (BASELINE configs[3])",
-            "n_gpus": world, "graphs_per_gpu": G, "fused_walk_emit_collate": bool(fused), "ms_per_epoch": ms,
+            "n_gpus": world, "graphs_per_gpu": G, "max_length": cfg.max_length, "fused_walk_emit_collate": bool(fused), "ms_per_epoch": ms,
             "graphs_per_s": G * world / ms * 1e3,
             "tokens_per_s": tokens / ms * 1e3, "scaling": "strong"}
 
