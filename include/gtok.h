@@ -361,9 +361,10 @@ GTOK_API int gtok_sent_tokenize(const GtokCsrBatch* csr, const GtokSentCfg* cfg,
  *      gtok_sent_tokenize).  The workspace carries no state between calls.  Measured on B200 (32M nodes per call,
  *      mean degree 8): the shared-memory kernel is faster up to ~2048 nodes per graph (14.6 vs 15.8 ms), the
  *      workspace kernel beyond (18.2 vs 28.7 ms at 4096 nodes) - gtok/engine.py picks by that rule. */
-/*      Graphs of at most 64 nodes: the workspace (12 bytes per node of the batch) is the walk's ITEM LOG - the walk kernel
+/*      Graphs of at most 256 nodes: the workspace (12 bytes per node of the batch) is the walk's ITEM LOG - the walk kernel
  *      (thread per graph) records one 8-byte item per first visit and the emission kernel (warp per row) expands the
- *      items into tokens with full-sector stores; without it the one-kernel path runs (1.23 -> ... ms per 1M ER graphs). */
+ *      items into tokens with full-sector stores; without it the one-kernel paths run (measured on B200 per 1M graphs:
+ *      ZINC-shaped labeled 1.17 -> 0.85 ms, ER 1.22 -> 1.16 ms; per 32M nodes at 256 nodes per graph 8.5 -> 3.6 ms). */
 GTOK_API size_t gtok_sent_workspace_bytes(int64_t total_nodes, int32_t max_nodes);
 GTOK_API int gtok_sent_tokenize_ws(const GtokCsrBatch* csr, const GtokSentCfg* cfg, const GtokChoice* choice,
                                    int32_t* len_out, int64_t* tok_out, int64_t stride, int64_t total_nodes, void* ws,
