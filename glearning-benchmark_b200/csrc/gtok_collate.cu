@@ -181,6 +181,65 @@ extern "C" int gtok_pad_mask(const int64_t* tok, const int64_t* row_start, const
   return GTOK_OK;
 }
 
+namespace gtok {
+// Everything of a padded epoch that is NOT a token, plus where every row starts: row r of batch k = r / B begins at cell
+// xoff[k] + (r - k*B) * lmax[k]; the cells [len, lmax) of the row get pad_id, the mask row gets len ones.  A tokenizer then
+// writes the tokens straight at row_off (gtok_zinc_serialize_rows): the padded batches cost 9 * Lmax bytes per row, written
+// once, for ANY batch size and molecule size (the single-pass fused kernel covers batches of 32..256 molecule-sized graphs).
+__global__ void __launch_bounds__(kColThreads)
+pad_tail_kernel(const int32_t* __restrict__ row_len, int64_t G, int64_t B, const int32_t* __restrict__ lmax,
+                const int64_t* __restrict__ xoff, int64_t pad, int64_t* __restrict__ X, uint8_t* __restrict__ attn,
+                int64_t* __restrict__ row_off) {
+  const int lane = lane_id();
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < G; r += nw) {
+    const int64_t k = r / B;
+    const int Lm = __ldg(lmax + k);
+    const int len = __ldg(row_len + r);
+    const int64_t cell0 = __ldg(xoff + k) + (r - k * B) * (int64_t)Lm;
+    if (lane == 0) {
+      row_off[r] = cell0;
+      if (r == G - 1) row_off[G] = cell0 + Lm;
+    }
+    int64_t* __restrict__ xr = X + cell0;
+    int p0 = len;                                        // pad cells [len, Lm): scalar head to 16-byte alignment, then pairs
+    if (p0 < Lm && ((reinterpret_cast<uintptr_t>(xr + p0) >> 3) & 1)) {
+      if (lane == 0) st_stream_i64(xr + p0, pad);
+      ++p0;
+    }
+    const int npair = (Lm - p0) >> 1;
+    for (int j = lane; j < npair; j += kWarp) st_stream_i64x2(xr + p0 + 2 * j, pad, pad);
+    if (((Lm - p0) & 1) && lane == 31) st_stream_i64(xr + Lm - 1, pad);
+    uint8_t* __restrict__ ar = attn + cell0;
+    int mh = (int)((16 - (reinterpret_cast<uintptr_t>(ar) & 15)) & 15);
+    if (mh > Lm) mh = Lm;
+    if (lane < mh) ar[lane] = (uint8_t)(lane < len);
+    const int nvec = (Lm - mh) >> 4;
+    for (int q = lane; q < nvec; q += kWarp) {
+      const int p = mh + 16 * q;
+      const int nv = len - p;
+      __stcs(reinterpret_cast<ulonglong2*>(ar + p), make_ulonglong2(mask8(nv), mask8(nv - 8)));
+    }
+    const int tail = mh + 16 * nvec;
+    if (tail + lane < Lm && lane < 16) ar[tail + lane] = (uint8_t)(tail + lane < len);
+  }
+}
+}  // namespace gtok
+
+extern "C" int gtok_pad_tail_batched(const int32_t* row_len, int64_t G, int64_t B, const int32_t* lmax, const int64_t* xoff,
+                                     int64_t pad_id, int64_t* X, uint8_t* attn, int64_t* row_off_out, void* stream) {
+  using namespace gtok;
+  GTOK_REQUIRE(G >= 0 && B > 0, GTOK_EINVAL, "pad_tail_batched: need G >= 0 and B > 0");
+  if (G == 0) return GTOK_OK;
+  GTOK_REQUIRE(row_len && lmax && xoff && X && attn && row_off_out, GTOK_EINVAL, "pad_tail_batched: null pointer");
+  const int64_t blocks = (G + kColWarps - 1) / kColWarps;
+  const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 16;
+  pad_tail_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kColThreads, 0, (cudaStream_t)stream>>>(row_len, G, B, lmax, xoff, pad_id, X,
+                                                                                                 attn, row_off_out);
+  GTOK_CUDA_TRY(cudaGetLastError());
+  return GTOK_OK;
+}
+
 extern "C" int gtok_batch_extents(const int32_t* row_len, const int64_t* batch_idx, int64_t G, int64_t B,
                                   int32_t* lmax_out, int32_t* cells_out, void* stream) {
   using namespace gtok;

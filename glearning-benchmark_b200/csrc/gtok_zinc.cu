@@ -52,7 +52,7 @@ __host__ __device__ __forceinline__ int zinc_row_length(int N, int Eu, int item_
 template <int H, int MAXE, bool WRITE>
 __global__ void __launch_bounds__(kZincThreads)
 zinc_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v, const int64_t* __restrict__ off,
-            int32_t* __restrict__ len_out, int64_t* __restrict__ out) {
+            int32_t* __restrict__ len_out, int64_t* __restrict__ out, const int32_t* __restrict__ row_len) {
   __shared__ unsigned s_key[kZincWarps][H];
   __shared__ unsigned s_min[kZincWarps][H];
   __shared__ unsigned short s_kept[WRITE ? kZincWarps : 1][WRITE ? MAXE : 1];
@@ -116,7 +116,7 @@ zinc_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v, con
       continue;
     }
     __syncwarp();
-    const int L = (int)(o1 - o0);  // == Lfull by construction
+    const int L = row_len ? __ldg(row_len + g) : (int)(o1 - o0);  // == Lfull by construction (row_len: rows placed by the caller)
     const int32_t* __restrict__ x = b.x + n0;
     const int32_t* __restrict__ attr = b.edge_attr ? b.edge_attr + e0 : nullptr;
     const int32_t* __restrict__ node_tok = v.node_tok;
@@ -205,7 +205,8 @@ zinc_small_lengths_kernel(const GtokGraphBatch b, int item_max, int ds_max, int3
 
 __global__ void __launch_bounds__(kZincThreads, 8)
 zinc_small_serialize_kernel(const GtokGraphBatch b, const __grid_constant__ GtokZincVocab v,
-                            const int64_t* __restrict__ off, int64_t* __restrict__ out, int cap) {
+                            const int64_t* __restrict__ off, int64_t* __restrict__ out, int cap,
+                            const int32_t* __restrict__ row_len) {
   extern __shared__ __align__(16) unsigned char z_smem[];
   const int lane = lane_id();
   const int w = threadIdx.x >> 5;
@@ -221,6 +222,7 @@ zinc_small_serialize_kernel(const GtokGraphBatch b, const __grid_constant__ Gtok
   for (int64_t g = warp0; g < b.num_graphs; g += nwarps) {
     int64_t n0, e0, o0; int N, Ed, L;
     load_graph_header(b, off, g, lane, true, n0, N, e0, Ed, o0, L);
+    if (row_len) L = __ldg(row_len + g);               // rows placed by the caller (padded batches): off[g] = row start
     const int32_t* __restrict__ src = b.src + e0;
     const int32_t* __restrict__ dst = b.dst + e0;
     const int32_t* __restrict__ attr = b.edge_attr ? b.edge_attr + e0 : nullptr;
@@ -311,17 +313,17 @@ static int zinc_check(const GtokGraphBatch* b, const GtokZincVocab* v, const cha
 
 template <int H, int MAXE, bool WRITE>
 static int zinc_launch(const GtokGraphBatch* b, const GtokZincVocab* v, const int64_t* off, int32_t* len_out,
-                       int64_t* out, cudaStream_t st) {
+                       int64_t* out, const int32_t* row_len, cudaStream_t st) {
   auto k = zinc_kernel<H, MAXE, WRITE>;
   const int64_t work = (b->num_graphs + kZincWarps - 1) / kZincWarps;
   const int grid = persistent_grid(k, kZincThreads, 0, work);
-  k<<<grid, kZincThreads, 0, st>>>(*b, *v, off, len_out, out);
+  k<<<grid, kZincThreads, 0, st>>>(*b, *v, off, len_out, out, row_len);
   GTOK_CUDA_TRY(cudaGetLastError());
   return GTOK_OK;
 }
 
 static int zinc_small_launch(bool write, const GtokGraphBatch* b, const GtokZincVocab* v, const int64_t* off,
-                             int32_t* len_out, int64_t* out, cudaStream_t st) {
+                             int32_t* len_out, int64_t* out, const int32_t* row_len, cudaStream_t st) {
   const int64_t work = (b->num_graphs + kZincWarps - 1) / kZincWarps;
   if (!write) {
     const int grid = persistent_grid(zinc_small_lengths_kernel, kZincThreads, 0, work);
@@ -336,18 +338,18 @@ static int zinc_small_launch(bool write, const GtokGraphBatch* b, const GtokZinc
   const size_t smem = (size_t)kZincWarps * (2 * kSmallN + cap) * 4;
   GTOK_CUDA_TRY(cudaFuncSetAttribute(zinc_small_serialize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = persistent_grid(zinc_small_serialize_kernel, kZincThreads, smem, work);
-  zinc_small_serialize_kernel<<<grid, kZincThreads, smem, st>>>(*b, *v, off, out, cap);
+  zinc_small_serialize_kernel<<<grid, kZincThreads, smem, st>>>(*b, *v, off, out, cap, row_len);
   GTOK_CUDA_TRY(cudaGetLastError());
   return GTOK_OK;
 }
 
 template <bool WRITE>
 static int zinc_dispatch(const GtokGraphBatch* b, const GtokZincVocab* v, const int64_t* off, int32_t* len_out,
-                         int64_t* out, cudaStream_t st) {
-  if (b->max_nodes <= kSmallN && b->max_entries <= 256) return zinc_small_launch(WRITE, b, v, off, len_out, out, st);
+                         int64_t* out, cudaStream_t st, const int32_t* row_len = nullptr) {
+  if (b->max_nodes <= kSmallN && b->max_entries <= 256) return zinc_small_launch(WRITE, b, v, off, len_out, out, row_len, st);
   // static shared memory budget is 48 KB per CTA: 8 warps * (8 B * H + 2 B * MAXE)
-  if (b->max_entries <= 128) return zinc_launch<256, 128, WRITE>(b, v, off, len_out, out, st);
-  return zinc_launch<512, 256, WRITE>(b, v, off, len_out, out, st);
+  if (b->max_entries <= 128) return zinc_launch<256, 128, WRITE>(b, v, off, len_out, out, row_len, st);
+  return zinc_launch<512, 256, WRITE>(b, v, off, len_out, out, row_len, st);
 }
 
 }  // namespace gtok
@@ -372,4 +374,15 @@ extern "C" int gtok_zinc_serialize(const GtokGraphBatch* batch, const GtokZincVo
   GTOK_REQUIRE(batch->x != nullptr, GTOK_EINVAL, "zinc_serialize: batch.x (atom types) is required");
   GTOK_REQUIRE((reinterpret_cast<uintptr_t>(tok_out) & 15) == 0, GTOK_EINVAL, "zinc_serialize: tok_out must be 16-byte aligned");
   return zinc_dispatch<true>(batch, vocab, off, nullptr, tok_out, (cudaStream_t)stream);
+}
+
+extern "C" int gtok_zinc_serialize_rows(const GtokGraphBatch* batch, const GtokZincVocab* vocab, const int64_t* row_off,
+                                        const int32_t* row_len, int64_t* tok_out, void* stream) {
+  using namespace gtok;
+  int rc = zinc_check(batch, vocab, "zinc_serialize_rows");
+  if (rc) return rc;
+  if (batch->num_graphs == 0) return GTOK_OK;
+  GTOK_REQUIRE(row_off && row_len && tok_out, GTOK_EINVAL, "zinc_serialize_rows: null row_off/row_len/tok_out");
+  GTOK_REQUIRE(batch->x != nullptr, GTOK_EINVAL, "zinc_serialize_rows: batch.x (atom types) is required");
+  return zinc_dispatch<true>(batch, vocab, row_off, nullptr, tok_out, (cudaStream_t)stream, row_len);
 }

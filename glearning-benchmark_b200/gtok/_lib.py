@@ -109,6 +109,8 @@ PROTOTYPES = {
     "gtok_sent_walk": (C.c_int, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), C.POINTER(ChoiceC), i64, vp, C.c_size_t, vp, vp]),
     "gtok_sent_emit_collate": (C.c_int, [C.POINTER(CsrBatchC), C.POINTER(SentCfgC), i64, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp,
                                          vp]),
+    "gtok_pad_tail_batched": (C.c_int, [vp, i64, i64, vp, vp, i64, vp, vp, vp, vp]),
+    "gtok_zinc_serialize_rows": (C.c_int, [C.POINTER(GraphBatchC), C.POINTER(ZincVocabC), vp, vp, vp, vp]),
     "gtok_pad_mask": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp]),
     "gtok_batch_extents": (C.c_int, [vp, vp, i64, i64, vp, vp, vp]),
     "gtok_pad_mask_batched": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, vp]),

@@ -409,6 +409,16 @@ GTOK_API int gtok_pad_mask_batched(const int64_t* tok, const int64_t* row_start,
                           const int64_t* batch_idx, int64_t G, int64_t B, const int32_t* lmax,
                           const int64_t* xoff, int64_t pad_id, int64_t* X, uint8_t* attn, void* stream);
 
+/* K2+K4 for ANY batch size / molecule size (the single-pass gtok_zinc_collate covers batches of 32..256 molecule-sized
+ *      graphs): gtok_zinc_lengths -> gtok_batch_extents -> gtok_scan_offsets give lmax / xoff; gtok_pad_tail_batched writes
+ *      everything of the padded batches that is not a token (pad cells [len, lmax) of every row, the mask rows) and
+ *      row_off_out int64[G+1] = first cell of every row; gtok_zinc_serialize_rows then writes row g's tokens at
+ *      tok_out + row_off[g] (row_len[g] of them).  9 * Lmax bytes per row, written once; no ragged stream in between. */
+GTOK_API int gtok_pad_tail_batched(const int32_t* row_len, int64_t G, int64_t B, const int32_t* lmax, const int64_t* xoff,
+                                   int64_t pad_id, int64_t* X, uint8_t* attn, int64_t* row_off_out, void* stream);
+GTOK_API int gtok_zinc_serialize_rows(const GtokGraphBatch* batch, const GtokZincVocab* vocab, const int64_t* row_off,
+                                      const int32_t* row_len, int64_t* tok_out, void* stream);
+
 /* Plumbing kernels (no torch op computes anything on the product path):
  *      gtok_compact_rows: strided rows [num_rows, stride] + row_len -> ragged stream, row r at out[off[r] ..]
  *      (off = gtok_scan_offsets(row_len)); the AGTT shim serves Graph2TrailTokenizer.__call__ results from it

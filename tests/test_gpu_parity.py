@@ -272,13 +272,25 @@ def test_fused_entry_points_edge_cases(dev):
     assert lens.cpu().tolist() == [4] * 70 and ep.batch(0)[0][0].cpu().tolist() == [zvoc["<bos>"], zvoc["<q>"], zvoc["regression"], zvoc["<p>"]]
     rag = engine.tokenize_zinc(gbb, zvoc, 1024, max_nodes=20, max_entries=2)
     assert rag.lengths.cpu().tolist() == [4] * 70
-    # unsupported shapes raise GTOK_EUNSUPPORTED instead of falling back to anything
+    # the single-pass kernel reports shapes it does not cover (GTOK_EUNSUPPORTED, never a silent fallback inside the library) ...
     with pytest.raises(GtokError) as ei:
-        engine.zinc_collate_epoch(gb, zvoc, 64, 48)                       # batch size not a multiple of 32
+        bc48 = engine._batch_c(gb, 3, 3)
+        zv48, _t48 = engine.zinc_vocab_c(zvoc, 64, 64, 3, dev)
+        lm48, xo48 = torch.empty(1, dtype=torch.int32, device=dev), torch.zeros(2, dtype=torch.int64, device=dev)
+        X48, A48 = torch.empty(4096, dtype=torch.int64, device=dev), torch.empty(4096, dtype=torch.bool, device=dev)
+        ws48 = torch.empty(max(16, lib.gtok_zinc_collate_workspace_bytes(33, 48)), dtype=torch.uint8, device=dev)
+        engine.check(lib.gtok_zinc_collate(C.byref(bc48), C.byref(zv48), 48, 2, _ptr(lens), _ptr(lm48), _ptr(xo48), _ptr(X48), _ptr(A48),
+                                           4096, _ptr(ws48), ws48.numel(), _stream()))
     assert ei.value.code == _lib.GTOK_EUNSUPPORTED
-    with pytest.raises(GtokError) as ei:
-        engine.zinc_collate_epoch(gb, zvoc, 64, 32, max_nodes=100)        # beyond molecule shapes
-    assert ei.value.code == _lib.GTOK_EUNSUPPORTED
+    # ... and the engine routes them through lengths -> extents -> pad cells / masks / row offsets -> tokens at their padded
+    # position (gtok_pad_tail_batched + gtok_zinc_serialize_rows): any batch size, any molecule size the tokenizer takes
+    for Bx, kw in ((48, {}), (1, {}), (7, {}), (500, {}), (32, {"max_nodes": 100})):
+        ep, lens = engine.zinc_collate_epoch(gb, zvoc, 64, Bx, **kw)
+        assert lens.cpu().tolist() == [len(w_) for w_ in want] and ep.num_batches == (33 + Bx - 1) // Bx
+        for k in range(ep.num_batches):
+            Xw, Aw, _ = O.collate(want[k * Bx:(k + 1) * Bx], [0] * len(want[k * Bx:(k + 1) * Bx]), zvoc["<pad>"])
+            X, A = ep.batch(k)
+            assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw), (Bx, k)
     with pytest.raises(GtokError) as ei:                                   # null pointers are EINVAL, not a crash
         bc = engine._batch_c(gb, 3, 3)
         zv, _t = engine.zinc_vocab_c(zvoc, 64, 64, 3, dev)
@@ -1378,3 +1390,38 @@ def test_sent_append_eos_false_every_kernel_family(dev, N, count, use_ws):
             want = S.sent_tokenize(N, rp, col, ocfg, S.PhiloxWords(5, g))
             assert tok[g, :ln[g]].tolist() == want.tolist(), (N, max_length, g)
             assert S.EOS not in want.tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 100, 128, 333, 1000])
+def test_zinc_collate_any_batch_size_and_big_molecules(dev, golden_zinc, B):
+    """K2+K4 outside the single-pass kernel's shapes: every batch size (the golden molecules vs the reference's own collate
+    through the two-step path) and molecules beyond 64 atoms (vs the oracle), incl. truncating max_len values."""
+    from gtok import engine
+    mols = golden_zinc["mols"]
+    gb = _zinc_batch(mols, dev)
+    vocab = golden_zinc["L1024"]["vocab"]
+    for max_len in (1024, 64):
+        ep, lens = engine.zinc_collate_epoch(gb, vocab, max_len, B)
+        rag = engine.tokenize_zinc(gb, vocab, max_len)
+        ep2 = engine.pad_mask_epoch(rag.tokens, rag.offsets, rag.lengths, vocab["<pad>"], B)
+        assert torch.equal(lens, rag.lengths) and torch.equal(ep.xoff, ep2.xoff) and torch.equal(ep.lmax, ep2.lmax)
+        assert torch.equal(ep.X, ep2.X) and torch.equal(ep.attn, ep2.attn)
+    # molecules of 65..150 atoms (general tokenizer: hash dedupe), odd batch size
+    rng = np.random.default_rng(B)
+    big = []
+    for i in range(90):
+        n = int(rng.integers(65, 151))
+        m = int(rng.integers(1, 120))
+        big.append({"n": n, "src": rng.integers(0, n, m).tolist(), "dst": rng.integers(0, n, m).tolist(),
+                    "x": rng.integers(0, 12, n).tolist(), "attr": rng.integers(0, 6, m).tolist()})
+    gbb = _zinc_batch(big, dev)
+    voc = O.zinc_extend_vocab(O.zinc_fixed_vocab(), [str(k) for k in range(150)] + ["X", "unknown"])
+    Bb = min(B, 37)
+    ep, lens = engine.zinc_collate_epoch(gbb, voc, 1024, Bb)
+    want = [O.zinc_ids(m["x"], m["src"], m["dst"], m["attr"], voc, 1024, 1024) for m in big]
+    assert lens.cpu().tolist() == [len(w_) for w_ in want]
+    for k in range(ep.num_batches):
+        Xw, Aw, _ = O.collate(want[k * Bb:(k + 1) * Bb], [0] * len(want[k * Bb:(k + 1) * Bb]), voc["<pad>"])
+        X, A = ep.batch(k)
+        assert np.array_equal(X.cpu().numpy(), Xw) and np.array_equal(A.cpu().numpy(), Aw), k
