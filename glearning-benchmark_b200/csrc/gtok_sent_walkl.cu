@@ -471,20 +471,12 @@ sent_emitl_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __re
           }
           const int kv = visb[w];
           if (kv >= k) return;                       // visited later (or never)
-          const unsigned short key = (unsigned short)(idx_off + kv);
-          int jj = m;
+          const unsigned short key = (unsigned short)(idx_off + kv);     // appended in neighbour order, sorted below
           if (LABELED) {
-            const unsigned short lab = (unsigned short)(elab_off + __ldg(c.eattr + e));
-            while (jj > 0 && (desc ? mb[2 * jj - 1] < key : mb[2 * jj - 1] > key)) {
-              mb[2 * jj] = mb[2 * jj - 2];
-              mb[2 * jj + 1] = mb[2 * jj - 1];
-              --jj;
-            }
-            mb[2 * jj] = lab;
-            mb[2 * jj + 1] = key;
+            mb[2 * m] = (unsigned short)(elab_off + __ldg(c.eattr + e));
+            mb[2 * m + 1] = key;
           } else {
-            while (jj > 0 && (desc ? mb[jj - 1] < key : mb[jj - 1] > key)) { mb[jj] = mb[jj - 1]; --jj; }
-            mb[jj] = key;
+            mb[m] = key;
           }
           ++m;
         };
@@ -498,6 +490,26 @@ sent_emitl_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __re
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (wv[j] >= 0) nbr(wv[j], eb + j);
+        }
+        // one insertion sort per item, by visit index (the sort sat inside the 8-way unrolled neighbour scan before: eight
+        // copies of a data-dependent loop, 45 % of this kernel's instructions)
+        for (int i = 1; i < m; ++i) {
+          if (LABELED) {
+            const unsigned short lab = mb[2 * i], key = mb[2 * i + 1];
+            int jj = i;
+            while (jj > 0 && (desc ? mb[2 * jj - 1] < key : mb[2 * jj - 1] > key)) {
+              mb[2 * jj] = mb[2 * jj - 2];
+              mb[2 * jj + 1] = mb[2 * jj - 1];
+              --jj;
+            }
+            mb[2 * jj] = lab;
+            mb[2 * jj + 1] = key;
+          } else {
+            const unsigned short key = mb[i];
+            int jj = i;
+            while (jj > 0 && (desc ? mb[jj - 1] < key : mb[jj - 1] > key)) { mb[jj] = mb[jj - 1]; --jj; }
+            mb[jj] = key;
+          }
         }
         if (m) {
           rowb[p] = (unsigned short)LADJ;
