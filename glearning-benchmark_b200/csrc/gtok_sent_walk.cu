@@ -245,8 +245,10 @@ sent_emit_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __res
       const int nk = endm ? __ffs((int)endm) - 1 : 32;                // items of this round: lanes [0, nk)
       more = endm == 0u;
       if (nk > 0) end_pos = -1;                                        // a later round holds the last item
-      if (lane < nk) ordb[k] = (unsigned char)u;
-      __syncwarp();
+      if (LABELED) {                                                   // visit index -> node: edge labels of predecessors / members
+        if (lane < nk) ordb[k] = (unsigned char)u;
+        __syncwarp();
+      }
       if (lane < nk) {
         unsigned long long a_u = 0;
         int rp_u = 0, xl = 0;
@@ -258,8 +260,10 @@ sent_emit_kernel(const GtokCsrBatch c, const GtokSentCfg cfg, const uint2* __res
         const int pr = (it.y >> 8) & 0xff;
         int p = (int)(it.y >> 16);
         int pv = -1;                                                   // trail predecessor (node id), -1 = none
-        if (pr & kPreHead) pv = ordb[pr & 63];
-        else if (!(pr & kPreReset) && k > 0) pv = ordb[k - 1];
+        if (LABELED) {
+          if (pr & kPreHead) pv = ordb[pr & 63];
+          else if (!(pr & kPreReset) && k > 0) pv = ordb[k - 1];
+        }
         if (pr & kPreReset) rowb[p++] = (TokT)RESET;
         if (pr & kPreHead) rowb[p++] = (TokT)(idx_off + (pr & 63));
         unsigned vlo = it.x;
